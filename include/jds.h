@@ -1,0 +1,180 @@
+/*
+ * jds.h - C ABI of libjds.so, the B200 (sm_100a) implementation of JPEG-DSP Studio's
+ * compression round trip.
+ *
+ * The reference has no FFI of its own: its operator boundary for this path is the
+ * Python function
+ *     engines/pipeline.py:17-21   compress_reconstruct(image_rgb, params, selected_block_idx)
+ * called from gui/worker.py:29 (single run), gui/worker.py:68 (quality sweep) and
+ * main.py:81 (CLI).  This header is what a ctypes/cffi binding for that call binds
+ * (see INTEGRATION.md for the stub): plain pointers and sizes, no Python.h, no torch
+ * types, status codes instead of exceptions.  jpeg_dsp_studio_b200/_native.py is
+ * that binding.
+ *
+ * Conventions
+ *   - every entry point returns 0 (JDS_OK) or a negative jds_status; the message for
+ *     the calling thread's last failure is jds_last_error().
+ *   - image buffers are packed RGB uint8, row-major H x W x 3, no row padding.
+ *   - a buffer argument may be a host pointer or a device pointer; the matching
+ *     `*_loc` argument says which (JDS_HOST / JDS_DEVICE).  Host buffers are copied
+ *     with cudaMemcpyAsync on the context's stream inside the call.
+ *   - all work of a context is issued on one CUDA stream (jds_ctx_set_stream to use
+ *     the caller's); calls return after the stream has been synchronised unless the
+ *     JDS_OUT_ASYNC flag is set (device buffers only).
+ *   - no entry point falls back to the CPU: without a CUDA device every compute
+ *     entry point fails with JDS_ERR_CUDA.
+ */
+#ifndef JDS_H_
+#define JDS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JDS_ABI_VERSION 1
+
+typedef enum jds_status {
+    JDS_OK = 0,
+    JDS_ERR_INVALID = -1,      /* bad argument (NULL, size, quality, mode ...)        */
+    JDS_ERR_UNSUPPORTED = -2,  /* valid for the reference but not implemented (odd
+                                  plane sizes with chroma subsampling)               */
+    JDS_ERR_CUDA = -3,         /* CUDA runtime error; text in jds_last_error()       */
+    JDS_ERR_NOMEM = -4
+} jds_status;
+
+/* subsampling_mode of models/compression_params.py:13 */
+enum { JDS_SUB_444 = 0, JDS_SUB_422 = 1, JDS_SUB_420 = 2 };
+
+/* arithmetic mode (BASELINE.json north_star) */
+enum {
+    JDS_EXACT = 0, /* fp64, operation order of the reference's NumPy/SciPy/OpenCV calls:
+                      int16 coefficients and uint8 pixels bit-identical             */
+    JDS_FAST = 1   /* fp32, fused arithmetic; PSNR within 1e-3 dB, SSIM within 1e-5  */
+};
+
+enum { JDS_HOST = 0, JDS_DEVICE = 1 };
+
+/* what to produce besides the reconstructed image (IntermediateData fields,
+ * models/intermediate_data.py:8-23, filled at engines/pipeline.py:119-124) */
+enum {
+    JDS_OUT_RECON   = 1u << 0, /* reconstructed_image, uint8 H x W x 3                */
+    JDS_OUT_COEFFS  = 1u << 1, /* all_quantized_coeffs, int16, Y|Cb|Cr, block raster  */
+    JDS_OUT_ERR_Y   = 1u << 2, /* error_map_y, fp64 H x W                             */
+    JDS_OUT_ERR_RGB = 1u << 3, /* error_map_rgb, fp64 H x W                           */
+    JDS_OUT_HIST    = 1u << 4, /* quantized_histogram (50 bins over [-100,100])       */
+    JDS_OUT_SSIM    = 1u << 5, /* SSIM partial sums (utils/metrics.py:12-14,21)       */
+    JDS_OUT_PSNR    = 1u << 6, /* SSE partial sums (utils/metrics.py:11,20)           */
+    JDS_OUT_ASYNC   = 1u << 31 /* do not synchronise the stream before returning      */
+};
+
+/* CompressionParams (models/compression_params.py:7-20) plus the frame geometry. */
+typedef struct jds_params {
+    int32_t height;
+    int32_t width;
+    int32_t quality;      /* 1..100                                                  */
+    int32_t subsampling;  /* JDS_SUB_*                                               */
+    int32_t prefilter;    /* use_prefilter: 3x3 sigma=0.75 Gaussian before decimation */
+    int32_t precision;    /* JDS_EXACT / JDS_FAST                                    */
+    uint32_t outputs;     /* JDS_OUT_* flags                                         */
+    int32_t reserved;
+} jds_params;
+
+/*
+ * Metric partials of one round trip.  The host turns them into the floats of
+ * CompressionResult exactly as utils/metrics.py does:
+ *   psnr_rgb = 10 log10(255^2 / (sse_rgb / (3 H W)))           (metrics.py:11)
+ *   psnr_y   = 10 log10(255^2 / (sse_y / (H W)))               (metrics.py:17-20)
+ *   ssim_rgb = mean_c(ssim_sum[c] / ssim_count), c = R,G,B     (metrics.py:12-14)
+ *   ssim_y   = ssim_sum[3] / ssim_count                        (metrics.py:21)
+ *   bits     = 2 * luma_blocks + coeff_bits                    (metrics.py:63-85)
+ */
+typedef struct jds_metrics {
+    uint64_t sse_rgb;       /* sum (a-b)^2 over the 3*H*W uint8 samples, exact          */
+    double   sse_y;         /* sum (Ya-Yb)^2, Y = .299r+.587g+.114b of the uint8 images */
+    double   ssim_sum[4];   /* sum of the SSIM map over the (H-6)(W-6) windows: R,G,B,Y */
+    uint64_t ssim_count;    /* (H-6)*(W-6)                                              */
+    uint64_t coeff_bits;    /* 6*nnz + sum_{v!=0} (bit_length(|v|) + 1), exact          */
+    uint64_t nnz;           /* non-zero quantised coefficients                          */
+    uint64_t total_coeffs;  /* 64 * (blocks of Y + Cb + Cr)                             */
+    uint64_t luma_blocks;   /* ceil(H/8)*ceil(W/8)                                      */
+    int64_t  hist50[50];    /* np.histogram(coeffs, 50, (-100,100)) (pipeline.py:124)   */
+    double   gpu_ms;        /* device time of this unit's kernels (CUDA events)         */
+    uint64_t reserved[3];
+} jds_metrics;
+
+typedef struct jds_ctx jds_ctx;
+
+/* ---- library / context ------------------------------------------------------- */
+int jds_abi_version(void);
+const char* jds_last_error(void);
+int jds_device_count(int* count);
+int jds_ctx_create(int device, jds_ctx** ctx);
+int jds_ctx_destroy(jds_ctx* ctx);
+/* use the caller's cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); 0 = default */
+int jds_ctx_set_stream(jds_ctx* ctx, void* cuda_stream);
+int jds_ctx_synchronize(jds_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int jds_ctx_launch_count(jds_ctx* ctx, uint64_t* launches);
+
+/* ---- host-only helpers (no GPU needed) ---------------------------------------- */
+/* engines/quantizer.py:7-19 scale_quant_matrix(JPEG_LUMA_Q50, quality) -> 64 doubles */
+int jds_quant_table(int quality, double table[64]);
+/* element counts of the outputs for a frame geometry (padding per block_processor.py:7-16) */
+int jds_coeff_count(int height, int width, int subsampling, uint64_t* count);
+int jds_plane_dims(int height, int width, int subsampling, int* chroma_h, int* chroma_w);
+
+/* ---- the round trip ------------------------------------------------------------- */
+/*
+ * One frame: replaces engines/pipeline.py:17-167 (everything except the six 8x8
+ * selected-block arrays, which jds_selected_block produces).
+ * rgb    [in]  H*W*3 uint8.
+ * recon  [out] H*W*3 uint8                        (JDS_OUT_RECON, else may be NULL)
+ * coeffs [out] jds_coeff_count() int16            (JDS_OUT_COEFFS, else NULL)
+ * err_y, err_rgb [out] H*W fp64 each              (JDS_OUT_ERR_*, else NULL)
+ * metrics [out] host struct, always filled (fields not requested stay 0).
+ */
+int jds_roundtrip(jds_ctx* ctx, const jds_params* params,
+                  const uint8_t* rgb, int rgb_loc,
+                  uint8_t* recon, int16_t* coeffs, double* err_y, double* err_rgb,
+                  int out_loc, jds_metrics* metrics);
+
+/*
+ * A batch of n_frames frames of identical geometry and parameters, frame k at
+ * rgb + k*H*W*3 (BASELINE.json config 5: frames sharded across GPUs by the caller).
+ * recon/coeffs are batch-strided the same way or NULL; metrics is an array of
+ * n_frames host structs.  Error maps are not produced in batch mode.
+ */
+int jds_roundtrip_batch(jds_ctx* ctx, const jds_params* params, int n_frames,
+                        const uint8_t* rgb, int rgb_loc,
+                        uint8_t* recon, int16_t* coeffs, int out_loc,
+                        jds_metrics* metrics);
+
+/*
+ * Quality sweep on one frame (gui/worker.py:55-74 BatchSweepWorker.run): the same
+ * frame at each quality in qualities[0..n_q); params->quality is ignored.
+ * recon is n_q frames or NULL (the sweep's consumers read only the metrics,
+ * gui/compression_tab.py:752-754); metrics is an array of n_q host structs.
+ */
+int jds_sweep(jds_ctx* ctx, const jds_params* params, const int32_t* qualities, int n_q,
+              const uint8_t* rgb, int rgb_loc,
+              uint8_t* recon, int out_loc, jds_metrics* metrics);
+
+/*
+ * The six 8x8 arrays of IntermediateData.selected_block_* for luma block
+ * (block_row, block_col) (engines/pipeline.py:126-151): original, shifted, dct,
+ * dequantized, reconstructed as fp64[64] and quantized as int16[64], all host
+ * pointers.  *present = 0 (arrays untouched) when row*blocks_per_row+col is outside
+ * [0, n_blocks) - the reference then leaves the fields None.
+ */
+int jds_selected_block(jds_ctx* ctx, const jds_params* params,
+                       const uint8_t* rgb, int rgb_loc, int block_row, int block_col,
+                       double original[64], double shifted[64], double dct[64],
+                       int16_t quantized[64], double dequantized[64],
+                       double reconstructed[64], int* present);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JDS_H_ */
