@@ -19,8 +19,8 @@
  *     `*_loc` argument says which (JDS_HOST / JDS_DEVICE).  Host buffers are copied
  *     with cudaMemcpyAsync on the context's stream inside the call.
  *   - all work of a context is issued on one CUDA stream (jds_ctx_set_stream to use
- *     the caller's); calls return after the stream has been synchronised unless the
- *     JDS_OUT_ASYNC flag is set (device buffers only).
+ *     the caller's); calls return after that stream has been synchronised, so the
+ *     outputs and the metrics struct are valid on return.
  *   - no entry point falls back to the CPU: without a CUDA device every compute
  *     entry point fails with JDS_ERR_CUDA.
  */
@@ -65,8 +65,7 @@ enum {
     JDS_OUT_ERR_RGB = 1u << 3, /* error_map_rgb, fp64 H x W                           */
     JDS_OUT_HIST    = 1u << 4, /* quantized_histogram (50 bins over [-100,100])       */
     JDS_OUT_SSIM    = 1u << 5, /* SSIM partial sums (utils/metrics.py:12-14,21)       */
-    JDS_OUT_PSNR    = 1u << 6, /* SSE partial sums (utils/metrics.py:11,20)           */
-    JDS_OUT_ASYNC   = 1u << 31 /* do not synchronise the stream before returning      */
+    JDS_OUT_PSNR    = 1u << 6  /* SSE partial sums (utils/metrics.py:11,20); always on */
 };
 
 /* CompressionParams (models/compression_params.py:7-20) plus the frame geometry. */
@@ -117,6 +116,11 @@ int jds_ctx_set_stream(jds_ctx* ctx, void* cuda_stream);
 int jds_ctx_synchronize(jds_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int jds_ctx_launch_count(jds_ctx* ctx, uint64_t* launches);
+
+/* accumulated device time (ms, CUDA events on the context's stream) and launch counts of
+ * the four stage kernels - forward colour, block codec, inverse colour, SSIM - since
+ * the last reset; bench.py's roofline line is computed from these */
+int jds_ctx_stage_times(jds_ctx* ctx, double ms[4], uint64_t launches[4], int reset);
 
 /* ---- host-only helpers (no GPU needed) ---------------------------------------- */
 /* engines/quantizer.py:7-19 scale_quant_matrix(JPEG_LUMA_Q50, quality) -> 64 doubles */

@@ -1,0 +1,41 @@
+// jds_internal.cuh - device-side structures shared by the kernels and the C ABI.
+#pragma once
+#include <stdint.h>
+#include "jds_math.cuh"
+
+namespace jds {
+
+// Frame geometry.  Planes live in scratch with padded (multiple-of-8) strides.
+struct Geom {
+    int H, W;        // luma / image size
+    int hc, wc;      // chroma plane size after decimation (engines/color_space.py:44-49)
+    int Hp, Wp;      // luma padded to a multiple of 8 (engines/block_processor.py:7-16)
+    int hcp, wcp;    // chroma padded
+    int nbx_y, nby_y, nbx_c, nby_c;   // 8x8 blocks per plane
+    int sub;         // JDS_SUB_*
+    int W4;          // 4*floor(W/4): columns the OpenCV blur row pass does with FMA (A2)
+    double sx, sy;   // wc/W, hc/H: cv2.resize(INTER_LINEAR) source step (A8)
+    long long nblk_y, nblk_c;         // blocks per plane
+    long long plane_y, plane_c;       // elements per padded plane
+};
+
+// Per-unit (frame or sweep point) accumulators, device resident, zeroed per call.
+struct DevMetrics {
+    unsigned long long sse_rgb;
+    double sse_y;
+    double ssim_sum[4];
+    unsigned long long coeff_bits;
+    unsigned long long nnz;
+    unsigned long long hist[50];
+};
+
+// Quantiser tables of one unit, in the arithmetic the policy needs.
+//   exact: q[i] = Q (fp64, integer valued);         fq unused, dq = Q
+//   fast : fq[i] = 1 / (Q * AAN_FWD[u] * AAN_FWD[v]);  dq[i] = Q * AAN_INV[u] * AAN_INV[v]
+struct QTables {
+    double q[64];
+    float fq[64];
+    float dq[64];
+};
+
+}  // namespace jds

@@ -1,0 +1,279 @@
+"""Engine: one libjds context on one GPU, with NumPy / torch buffer handoff.
+
+This is the host-side object behind the drop-in ``compress_reconstruct``
+(engines/pipeline.py) and behind the batch / sweep entry points that BASELINE.json's
+configs 4 and 5 need.  It owns no arithmetic: every pixel, coefficient and metric
+partial comes from the CUDA kernels through the C ABI (``_native``).  PyTorch is
+used only where the caller hands over device tensors or pinned host tensors
+(``data_ptr()``), never for compute.
+"""
+
+import ctypes as C
+import threading
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _native as N
+from .models import CompressionParams
+from .utils.metrics import bitrate_from_partials, metrics_from_partials
+
+
+@dataclass
+class RoundTripOutputs:
+    """Raw outputs of one unit (frame or sweep point)."""
+    recon: Optional[np.ndarray]
+    coeffs: Optional[np.ndarray]
+    err_y: Optional[np.ndarray]
+    err_rgb: Optional[np.ndarray]
+    metrics: "N.JdsMetrics"
+    scalars: dict          # psnr_y, ssim_y, psnr_rgb, ssim_rgb, bpp, compression_ratio, ...
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def _mode_code(mode) -> int:
+    try:
+        return N.SUBSAMPLING[mode]
+    except (KeyError, TypeError):
+        # same exception type and text as engines/color_space.py:51
+        raise ValueError(f"Unknown subsampling mode: {mode}") from None
+
+
+def _precision_code(precision) -> int:
+    try:
+        return N.PRECISION[precision]
+    except (KeyError, TypeError):
+        raise ValueError(f"precision must be 'exact' or 'fast', got {precision!r}") from None
+
+
+class Engine:
+    """A libjds context bound to one CUDA device."""
+
+    def __init__(self, device: int = 0):
+        self._lib = N.load()
+        self._ctx = C.c_void_p()
+        self.device = int(device)
+        N.check(self._lib.jds_ctx_create(self.device, C.byref(self._ctx)))
+        self._lock = threading.Lock()        # one call in flight per context
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx:
+            self._lib.jds_ctx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers ---------------------------------------------------------------------
+    def launch_count(self) -> int:
+        n = C.c_uint64()
+        N.check(self._lib.jds_ctx_launch_count(self._ctx, C.byref(n)))
+        return int(n.value)
+
+    STAGES = ("forward_colour", "block_codec", "inverse_colour", "ssim")
+
+    def stage_times(self, reset: bool = True) -> dict:
+        """Accumulated device ms and launch count per stage kernel since the last reset."""
+        ms = (C.c_double * 4)()
+        ln = (C.c_uint64 * 4)()
+        N.check(self._lib.jds_ctx_stage_times(self._ctx, ms, ln, int(reset)))
+        return {name: {"ms": float(ms[i]), "launches": int(ln[i])}
+                for i, name in enumerate(self.STAGES)}
+
+    def use_stream(self, cuda_stream: int):
+        """Issue this context's work on the caller's cudaStream_t (an int handle)."""
+        N.check(self._lib.jds_ctx_set_stream(self._ctx, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        N.check(self._lib.jds_ctx_synchronize(self._ctx))
+
+    @staticmethod
+    def _frame_geometry(image) -> tuple:
+        shape = tuple(image.shape)
+        if len(shape) < 3:
+            # the reference indexes rgb[:, :, 0] on a 2-D array (color_space.py:10)
+            raise IndexError("too many indices for array: array is 2-dimensional, "
+                             "but 3 were indexed")
+        if shape[-1] != 3:
+            raise ValueError(f"expected an RGB image with 3 channels, got shape {shape}")
+        return shape
+
+    def _params(self, h, w, quality, mode, prefilter, precision, outputs) -> "N.JdsParams":
+        return N.JdsParams(int(h), int(w), int(quality), _mode_code(mode), int(bool(prefilter)),
+                           _precision_code(precision), int(outputs), 0)
+
+    @staticmethod
+    def _in_ptr(image):
+        """(pointer, location, keepalive) for a uint8 NumPy array or torch tensor."""
+        if _is_torch(image):
+            import torch
+            if image.dtype != torch.uint8:
+                raise TypeError(f"image tensor must be uint8, got {image.dtype}")
+            t = image.contiguous()
+            loc = N.JDS_DEVICE if t.is_cuda else N.JDS_HOST
+            return C.c_void_p(t.data_ptr()), loc, t
+        a = np.ascontiguousarray(image)
+        if a.dtype != np.uint8:
+            raise TypeError(f"image must be uint8, got {a.dtype}")
+        return C.c_void_p(a.ctypes.data), N.JDS_HOST, a
+
+    def _scalars(self, m, h, w) -> dict:
+        out = metrics_from_partials(m, h, w)
+        out.update(bitrate_from_partials(m, h, w))
+        return out
+
+    # -- single frame ----------------------------------------------------------------
+    def roundtrip(self, image, quality=50, mode="4:2:0", prefilter=False, *,
+                  precision="exact", want_coeffs=False, want_error_maps=False,
+                  want_hist=False, want_ssim=True, recon_out=None) -> RoundTripOutputs:
+        """One frame through the kernels.  ``image``: uint8 H x W x 3 NumPy array
+        (host) or torch tensor (host or CUDA).  Outputs follow the input's location
+        (CUDA tensor in -> CUDA tensors out)."""
+        h, w, _ = self._frame_geometry(image)
+        ptr, loc, keep = self._in_ptr(image)
+        flags = N.JDS_OUT_RECON | N.JDS_OUT_PSNR
+        flags |= N.JDS_OUT_COEFFS if want_coeffs else 0
+        flags |= (N.JDS_OUT_ERR_Y | N.JDS_OUT_ERR_RGB) if want_error_maps else 0
+        flags |= N.JDS_OUT_HIST if want_hist else 0
+        flags |= N.JDS_OUT_SSIM if want_ssim else 0
+        p = self._params(h, w, quality, mode, prefilter, precision, flags)
+        ncoef = C.c_uint64()
+        N.check(self._lib.jds_coeff_count(h, w, p.subsampling, C.byref(ncoef)))
+        m = N.JdsMetrics()
+        if loc == N.JDS_DEVICE:
+            import torch
+            dev = keep.device
+            recon = recon_out if recon_out is not None else torch.empty((h, w, 3), dtype=torch.uint8, device=dev)
+            coeffs = torch.empty(ncoef.value, dtype=torch.int16, device=dev) if want_coeffs else None
+            ey = torch.empty((h, w), dtype=torch.float64, device=dev) if want_error_maps else None
+            ergb = torch.empty((h, w), dtype=torch.float64, device=dev) if want_error_maps else None
+            gp = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        else:
+            recon = recon_out if recon_out is not None else np.empty((h, w, 3), dtype=np.uint8)
+            coeffs = np.empty(ncoef.value, dtype=np.int16) if want_coeffs else None
+            ey = np.empty((h, w), dtype=np.float64) if want_error_maps else None
+            ergb = np.empty((h, w), dtype=np.float64) if want_error_maps else None
+            if _is_torch(recon):
+                gp = lambda t: C.c_void_p(t.data_ptr() if _is_torch(t) else t.ctypes.data) if t is not None else None
+            else:
+                gp = lambda t: C.c_void_p(t.ctypes.data) if t is not None else None
+        with self._lock:
+            N.check(self._lib.jds_roundtrip(self._ctx, C.byref(p), ptr, loc, gp(recon), gp(coeffs),
+                                            gp(ey), gp(ergb), loc, C.byref(m)))
+        return RoundTripOutputs(recon, coeffs, ey, ergb, m, self._scalars(m, h, w))
+
+    def selected_block(self, image, quality, block_row, block_col):
+        """IntermediateData.selected_block_* (engines/pipeline.py:126-151) or None."""
+        h, w, _ = self._frame_geometry(image)
+        ptr, loc, keep = self._in_ptr(image)
+        p = self._params(h, w, quality, "4:4:4", False, "exact", 0)
+        arrs = {k: np.empty((8, 8), dtype=np.float64)
+                for k in ("original", "shifted", "dct", "dequantized", "reconstructed")}
+        arrs["quantized"] = np.empty((8, 8), dtype=np.int16)
+        present = C.c_int(0)
+        vp = lambda a: C.c_void_p(a.ctypes.data)
+        with self._lock:
+            N.check(self._lib.jds_selected_block(
+                self._ctx, C.byref(p), ptr, loc, int(block_row), int(block_col),
+                vp(arrs["original"]), vp(arrs["shifted"]), vp(arrs["dct"]), vp(arrs["quantized"]),
+                vp(arrs["dequantized"]), vp(arrs["reconstructed"]), C.byref(present)))
+        return arrs if present.value else None
+
+    # -- batch (BASELINE config 5) -----------------------------------------------------
+    def roundtrip_batch(self, frames, quality=50, mode="4:2:0", prefilter=False, *,
+                        precision="fast", want_recon=True, want_coeffs=False,
+                        want_hist=False, want_ssim=True, recon_out=None) -> List[RoundTripOutputs]:
+        """N frames of one geometry: ``frames`` is uint8 N x H x W x 3 (NumPy, pinned
+        or pageable torch host tensor, or CUDA tensor)."""
+        shape = tuple(frames.shape)
+        if len(shape) != 4 or shape[-1] != 3:
+            raise ValueError(f"expected N x H x W x 3 frames, got shape {shape}")
+        n, h, w, _ = shape
+        ptr, loc, keep = self._in_ptr(frames)
+        flags = N.JDS_OUT_PSNR | (N.JDS_OUT_RECON if want_recon else 0)
+        flags |= N.JDS_OUT_COEFFS if want_coeffs else 0
+        flags |= N.JDS_OUT_HIST if want_hist else 0
+        flags |= N.JDS_OUT_SSIM if want_ssim else 0
+        p = self._params(h, w, quality, mode, prefilter, precision, flags)
+        ncoef = C.c_uint64()
+        N.check(self._lib.jds_coeff_count(h, w, p.subsampling, C.byref(ncoef)))
+        ms = (N.JdsMetrics * n)()
+        recon = coeffs = None
+        if loc == N.JDS_DEVICE:
+            import torch
+            if want_recon:
+                recon = recon_out if recon_out is not None else torch.empty((n, h, w, 3), dtype=torch.uint8, device=keep.device)
+            if want_coeffs:
+                coeffs = torch.empty((n, ncoef.value), dtype=torch.int16, device=keep.device)
+        else:
+            if want_recon:
+                recon = recon_out if recon_out is not None else np.empty((n, h, w, 3), dtype=np.uint8)
+            if want_coeffs:
+                coeffs = np.empty((n, ncoef.value), dtype=np.int16)
+
+        def gp(t):
+            if t is None:
+                return None
+            return C.c_void_p(t.data_ptr() if _is_torch(t) else t.ctypes.data)
+        with self._lock:
+            N.check(self._lib.jds_roundtrip_batch(self._ctx, C.byref(p), n, ptr, loc, gp(recon),
+                                                  gp(coeffs), loc, ms))
+        return [RoundTripOutputs(recon[i] if recon is not None else None,
+                                 coeffs[i] if coeffs is not None else None, None, None, ms[i],
+                                 self._scalars(ms[i], h, w)) for i in range(n)]
+
+    # -- quality sweep (BASELINE config 4; gui/worker.py:55-74) -------------------------
+    def sweep(self, image, qualities: Sequence[int], mode="4:2:0", prefilter=False, *,
+              precision="fast", want_recon=False, want_ssim=True) -> List[RoundTripOutputs]:
+        h, w, _ = self._frame_geometry(image)
+        ptr, loc, keep = self._in_ptr(image)
+        qs = [int(q) for q in qualities]
+        for q in qs:
+            CompressionParams(quality=q)            # same validation / message as the reference
+        nq = len(qs)
+        if nq == 0:
+            return []
+        flags = N.JDS_OUT_PSNR | (N.JDS_OUT_RECON if want_recon else 0)
+        flags |= N.JDS_OUT_SSIM if want_ssim else 0
+        p = self._params(h, w, 50, mode, prefilter, precision, flags)
+        ms = (N.JdsMetrics * nq)()
+        qarr = (C.c_int32 * nq)(*qs)
+        recon = None
+        if want_recon:
+            if loc == N.JDS_DEVICE:
+                import torch
+                recon = torch.empty((nq, h, w, 3), dtype=torch.uint8, device=keep.device)
+            else:
+                recon = np.empty((nq, h, w, 3), dtype=np.uint8)
+        rp = None if recon is None else C.c_void_p(recon.data_ptr() if _is_torch(recon) else recon.ctypes.data)
+        with self._lock:
+            N.check(self._lib.jds_sweep(self._ctx, C.byref(p), qarr, nq, ptr, loc, rp, loc, ms))
+        return [RoundTripOutputs(recon[i] if recon is not None else None, None, None, None, ms[i],
+                                 self._scalars(ms[i], h, w)) for i in range(nq)]
+
+
+_engines = {}
+_engines_lock = threading.Lock()
+
+
+def get_engine(device: Optional[int] = None) -> Engine:
+    """Process-wide engine per device (created on first use)."""
+    if device is None:
+        device = 0
+        try:
+            import os
+            device = int(os.environ.get("JDS_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        except ValueError:
+            device = 0
+    with _engines_lock:
+        eng = _engines.get(device)
+        if eng is None:
+            eng = _engines[device] = Engine(device)
+        return eng

@@ -1,0 +1,16 @@
+"""Shared utilities of the round trip (mirror of the reference's ``utils`` package,
+minus file I/O which is out of scope)."""
+
+from .constants import JPEG_LUMA_Q50, ZIGZAG_ORDER
+from .metrics import Timer, metrics_from_partials, bitrate_from_partials, psnr_from_sse
+from .test_images import (generate_colored_checkerboard, generate_thin_stripes,
+                          generate_gradient, generate_text_edges, generate_chroma_stripes,
+                          generate_photo, generate_demo_image)
+
+__all__ = [
+    'JPEG_LUMA_Q50', 'ZIGZAG_ORDER', 'Timer', 'metrics_from_partials',
+    'bitrate_from_partials', 'psnr_from_sse',
+    'generate_colored_checkerboard', 'generate_thin_stripes', 'generate_gradient',
+    'generate_text_edges', 'generate_chroma_stripes', 'generate_photo',
+    'generate_demo_image',
+]

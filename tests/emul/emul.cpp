@@ -1,0 +1,113 @@
+// emul.cpp - TEST INFRASTRUCTURE: runs the product's per-work-item device functions
+// (jpeg_dsp_studio_b200/csrc/jds_stages.cuh, the bodies of the CUDA kernels) on the CPU,
+// one call per thread of the corresponding kernel, so that the arithmetic can be
+// checked against the oracle in the GPU-less build container.  Never linked into
+// libjds.so and never imported by the product package.
+//
+// Build (tests/emul/build.py): g++ -O2 -ffp-contract=off (no -mfma / -march=native),
+// so every fp64 operation of the Exact policy is individually rounded as on the GPU.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../jpeg_dsp_studio_b200/csrc/jds_host.h"
+#include "../../jpeg_dsp_studio_b200/csrc/jds_stages.cuh"
+
+using namespace jds;
+
+template <class P, int SUB, bool PF>
+static void run_forward(const Geom& g, const uint8_t* rgb, typename P::T* Y, typename P::T* Cb,
+                        typename P::T* Cr) {
+    for (int cy = 0; cy < g.hc; ++cy)
+        for (int cx = 0; cx < g.wc; ++cx) forward_cell<P, SUB, PF>(g, rgb, cx, cy, Y, Cb, Cr);
+}
+
+template <class P>
+static int run(int H, int W, int quality, int sub, int prefilter, const uint8_t* rgb,
+               uint8_t* recon, int16_t* coeffs, double* err_y, double* err_rgb, uint64_t* bits,
+               uint64_t* nnz, int64_t* hist, uint64_t* sse_rgb, double* sse_y) {
+    typedef typename P::T T;
+    Geom g;
+    int rc = geom_init(H, W, sub, &g);
+    if (rc) return -rc;
+    QTables tb;
+    fill_tables(quality, &tb);
+    const size_t pe = (size_t)(g.plane_y + 2 * g.plane_c);
+    std::vector<T> fwd(pe, T(0)), rec(pe, T(0));
+    T *Y = fwd.data(), *Cb = Y + g.plane_y, *Cr = Cb + g.plane_c;
+    if (sub == 0) run_forward<P, 0, false>(g, rgb, Y, Cb, Cr);
+    else if (sub == 1 && !prefilter) run_forward<P, 1, false>(g, rgb, Y, Cb, Cr);
+    else if (sub == 1) run_forward<P, 1, true>(g, rgb, Y, Cb, Cr);
+    else if (!prefilter) run_forward<P, 2, false>(g, rgb, Y, Cb, Cr);
+    else run_forward<P, 2, true>(g, rgb, Y, Cb, Cr);
+
+    *bits = 0;
+    *nnz = 0;
+    memset(hist, 0, 50 * sizeof(int64_t));
+    const long long total = g.nblk_y + 2 * g.nblk_c;
+    for (long long b = 0; b < total; ++b) {
+        int plane = 0;
+        long long lb = b;
+        if (lb >= g.nblk_y) { lb -= g.nblk_y; plane = 1; if (lb >= g.nblk_c) { lb -= g.nblk_c; plane = 2; } }
+        const int nbx = plane ? g.nbx_c : g.nbx_y;
+        const int h = plane ? g.hc : g.H, w = plane ? g.wc : g.W;
+        const int stride = plane ? g.wcp : g.Wp;
+        const size_t poff = plane == 0 ? 0 : (plane == 1 ? g.plane_y : g.plane_y + g.plane_c);
+        const int by = (int)(lb / nbx), bx = (int)(lb % nbx);
+        T v[64];
+        int16_t q[64];
+        BlockStats st;
+        load_block<T>(fwd.data() + poff, stride, h, w, bx, by, v);
+        BlockCodec<P>::run(v, q, tb, st, nullptr, nullptr);
+        store_block<T>(rec.data() + poff, stride, h, w, bx, by, v);
+        *bits += st.bits;
+        *nnz += st.nnz;
+        for (int i = 0; i < 64; ++i) {
+            coeffs[b * 64 + i] = q[i];
+            int hb = hist_bin(q[i]);
+            if (hb >= 0) hist[hb]++;
+        }
+    }
+    *sse_rgb = 0;
+    *sse_y = 0.0;
+    const T* Yr = rec.data();
+    const T* Cbr = Yr + g.plane_y;
+    const T* Crr = Cbr + g.plane_c;
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            PixelOut o = inverse_pixel<P>(g, rgb, x, y, Y, Yr, Cbr, Crr);
+            uint8_t* out = recon + ((size_t)y * W + x) * 3;
+            out[0] = o.r; out[1] = o.g; out[2] = o.b;
+            err_y[(size_t)y * W + x] = o.err_y;
+            err_rgb[(size_t)y * W + x] = o.err_rgb;
+            *sse_rgb += o.sse_rgb;
+            *sse_y += o.sse_y;
+        }
+    return 0;
+}
+
+extern "C" int emul_roundtrip(int exact, int H, int W, int quality, int sub, int prefilter,
+                              const uint8_t* rgb, uint8_t* recon, int16_t* coeffs, double* err_y,
+                              double* err_rgb, uint64_t* bits, uint64_t* nnz, int64_t* hist,
+                              uint64_t* sse_rgb, double* sse_y) {
+    if (exact)
+        return run<Exact>(H, W, quality, sub, prefilter, rgb, recon, coeffs, err_y, err_rgb, bits,
+                          nnz, hist, sse_rgb, sse_y);
+    return run<Fast>(H, W, quality, sub, prefilter, rgb, recon, coeffs, err_y, err_rgb, bits, nnz,
+                     hist, sse_rgb, sse_y);
+}
+
+// SSIM of one window from its sums, both precisions (checked against the stand-in)
+extern "C" double emul_ssim_window(int use_float, const double* x, const double* y, double shift) {
+    double sx = 0, sy = 0, sxx = 0, syy = 0, sxy = 0;
+    for (int i = 0; i < 49; ++i) {
+        const double a = x[i] - shift, b = y[i] - shift;
+        sx += a; sy += b; sxx += a * a; syy += b * b; sxy += a * b;
+    }
+    if (use_float)
+        return (double)ssim_from_sums<float>((float)sx, (float)sy, (float)sxx, (float)syy,
+                                             (float)sxy, (float)shift);
+    return ssim_from_sums<double>(sx, sy, sxx, syy, sxy, shift);
+}

@@ -1,0 +1,121 @@
+"""CPU-side checks of the boundary: the C-ABI library loads and exports every symbol
+include/jds.h declares, host-only entry points agree with the oracle, the API
+dataclasses validate like the reference's, and compute entry points fail loudly
+without a GPU (no fallback).  No kernels are launched here."""
+
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import numpy_port as P
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def native():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "_jds_build", os.path.join(ROOT, "jpeg_dsp_studio_b200", "build.py"))
+    build = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(build)
+    build.build_native()
+    from jpeg_dsp_studio_b200 import _native
+    _native.load()
+    return _native
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, "include", "jds.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(jds_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(native):
+    lib = C.CDLL(native.LIB_PATH)
+    names = declared_functions()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(lib, n), f"libjds.so lacks {n} declared in include/jds.h"
+    assert set(names) == set(native.PROTOTYPES), "binding and header disagree"
+    assert lib.jds_abi_version() == native.JDS_ABI_VERSION
+
+
+def test_struct_layouts_match_header(native):
+    assert C.sizeof(native.JdsParams) == 32
+    assert C.sizeof(native.JdsMetrics) == 8 * (1 + 1 + 4 + 1 + 1 + 1 + 1 + 1 + 50 + 1 + 3)
+
+
+def test_quant_table_matches_reference_formula(native):
+    lib = native.load()
+    for q in range(1, 101):
+        t = (C.c_double * 64)()
+        native.check(lib.jds_quant_table(q, t))
+        assert np.array_equal(np.array(t).reshape(8, 8), P.scale_quant_matrix(q)), q
+    t = (C.c_double * 64)()
+    assert lib.jds_quant_table(0, t) == native.JDS_ERR_INVALID
+    assert b"Quality must be 1-100" in lib.jds_last_error()
+
+
+@pytest.mark.parametrize("h,w,mode,want", [
+    (512, 512, "4:2:0", 393216), (1080, 1920, "4:4:4", 6220800),
+    (1080, 1920, "4:2:2", 4147200), (2160, 3840, "4:2:0", 12441600),
+    (250, 334, "4:2:0", 64 * (32 * 42 + 2 * 16 * 21)),
+])
+def test_coeff_count(native, h, w, mode, want):
+    lib = native.load()
+    n = C.c_uint64()
+    native.check(lib.jds_coeff_count(h, w, native.SUBSAMPLING[mode], C.byref(n)))
+    assert n.value == want
+
+
+def test_odd_sizes_with_subsampling_are_refused_loudly(native):
+    lib = native.load()
+    n = C.c_uint64()
+    assert lib.jds_coeff_count(251, 333, native.JDS_SUB_420, C.byref(n)) == native.JDS_ERR_UNSUPPORTED
+    assert lib.jds_coeff_count(251, 333, native.JDS_SUB_444, C.byref(n)) == native.JDS_OK
+
+
+def test_params_validation_like_reference():
+    from jpeg_dsp_studio_b200 import CompressionParams
+    p = CompressionParams()
+    assert (p.block_size, p.quality, p.subsampling_mode, p.use_prefilter) == (8, 50, '4:2:0', False)
+    with pytest.raises(ValueError, match="Quality must be 1-100, got 0"):
+        CompressionParams(quality=0)
+    with pytest.raises(ValueError, match="Block size must be 4, 8, 16, or 32, got 7"):
+        CompressionParams(block_size=7)
+    CompressionParams(subsampling_mode="bogus")       # not validated at construction
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the drop-in must raise, not compute on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from jpeg_dsp_studio_b200 import CompressionParams, compress_reconstruct
+    from jpeg_dsp_studio_b200._native import NativeError
+    with pytest.raises(NativeError):
+        compress_reconstruct(np.zeros((16, 16, 3), np.uint8), CompressionParams())
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "jpeg_dsp_studio_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert not re.search(r"^\s*(from|import)\s+(scipy|cv2|skimage)\b", src, flags=re.M), f
+
+
+def test_metric_finalisation_formulas():
+    from jpeg_dsp_studio_b200.utils.metrics import psnr_from_sse
+    assert psnr_from_sse(0, 100) == float("inf")
+    a = np.random.default_rng(0).integers(0, 256, (40, 40, 3), dtype=np.uint8)
+    b = np.random.default_rng(1).integers(0, 256, (40, 40, 3), dtype=np.uint8)
+    from oracle.skimage_standin import peak_signal_noise_ratio
+    sse = int(np.sum((a.astype(np.int64) - b.astype(np.int64)) ** 2))
+    assert psnr_from_sse(sse, a.size) == peak_signal_noise_ratio(a, b, data_range=255)
