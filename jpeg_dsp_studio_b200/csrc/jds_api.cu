@@ -64,6 +64,9 @@ struct jds_ctx {
     size_t h_tables_bytes = 0;
     void* h_selected = nullptr;  // pinned
     uint64_t launches = 0;
+    int sm_count = 148;
+    bool legacy_ssim = false;     // JDS_LEGACY_SSIM=1: use the tile kernel (debug / A-B runs)
+    bool no_fused = false;        // JDS_NO_FUSED=1: fast mode through the staged kernels
     size_t scratch_budget = (size_t)1 << 30;
 };
 
@@ -128,6 +131,11 @@ extern "C" int jds_ctx_create(int device, jds_ctx** out) {
         return fail(JDS_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(e));
     }
     c->own_stream = true;
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    const char* ls = getenv("JDS_LEGACY_SSIM");
+    c->legacy_ssim = ls && atoi(ls) != 0;
+    const char* nf = getenv("JDS_NO_FUSED");
+    c->no_fused = nf && atoi(nf) != 0;
     const char* mb = getenv("JDS_SCRATCH_MB");
     if (mb && atol(mb) > 0) c->scratch_budget = (size_t)atol(mb) << 20;
     *out = c;
@@ -355,24 +363,62 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
         JDS_CUDA(cudaMemsetAsync(d_metrics, 0, sizeof(DevMetrics) * n, s));
         JDS_CUDA(cudaEventRecord(c->ev0, s));
         JDS_CUDA(cudaEventRecord(c->evs[0], s));
-        const bool do_fwd = !J.shared_input || u0 == 0;
-        if (do_fwd) {
-            launch_forward(exact, g, p->prefilter, d_rgb, rgb_stride, fwd, fwd_stride,
-                           J.shared_input ? 1 : n, s);
+        // fast mode on block-aligned frames runs the fused kernels (jds_fused.cu); exact
+        // mode, prefiltered / ragged frames and the GUI-only outputs (histogram, error
+        // maps) run the staged kernels (jds_kernels.cu)
+        const bool fused = !exact && !c->no_fused && !want_hist && !want_ey && !want_ergb &&
+                           fused_supported(g, p->prefilter, d_rgb, rgb_stride, d_recon, frame_bytes) &&
+                           ssim_strip_supported(g.H, g.W, d_rgb, rgb_stride, d_recon, frame_bytes);
+        bool do_fwd, do_inv, do_ssim;
+        if (fused) {
+            float* cpl = (float*)c->planes.p;
+            const size_t cpl_stride = fused_chroma_plane_floats(g);
+            do_fwd = g.sub != 0;
+            if (do_fwd) {
+                JDS_CUDA(launch_fused_chroma(g, d_rgb, rgb_stride, cpl, cpl_stride, d_tables,
+                                             J.qualities ? 1 : 0, d_coeffs, ncoef, d_metrics, n, s));
+                c->launches++;
+            }
+            JDS_CUDA(cudaEventRecord(c->evs[1], s));
+            JDS_CUDA(launch_fused_luma(g, d_rgb, rgb_stride, cpl, cpl_stride, d_tables,
+                                       J.qualities ? 1 : 0, d_coeffs, ncoef, d_recon, frame_bytes,
+                                       d_metrics, n, s));
             c->launches++;
-        }
-        JDS_CUDA(cudaEventRecord(c->evs[1], s));
-        launch_codec(exact, g, fwd, fwd_stride, rec, rec_stride, d_tables, J.qualities ? 1 : 0,
-                     d_coeffs, ncoef, want_hist, d_metrics, n, s);
-        JDS_CUDA(cudaEventRecord(c->evs[2], s));
-        launch_inverse(exact, g, d_rgb, rgb_stride, fwd, fwd_stride, rec, rec_stride, d_recon,
-                       frame_bytes, d_ey, d_ergb, d_metrics, n, s);
-        JDS_CUDA(cudaEventRecord(c->evs[3], s));
-        c->launches += 2;
-        const bool do_ssim = want_ssim && g.H >= 7 && g.W >= 7;
-        if (do_ssim) {
-            launch_ssim(exact, g.H, g.W, d_rgb, rgb_stride, d_recon, frame_bytes, d_metrics, n, s);
+            JDS_CUDA(cudaEventRecord(c->evs[2], s));
+            JDS_CUDA(cudaEventRecord(c->evs[3], s));
+            do_inv = false;
+            do_ssim = true;     // squared errors always come from the strip kernel here
+            JDS_CUDA(launch_ssim_strip(g.H, g.W, d_rgb, rgb_stride, d_recon, frame_bytes, d_metrics,
+                                       n, want_ssim, true, c->sm_count, s));
             c->launches++;
+        } else {
+            do_fwd = !J.shared_input || u0 == 0;
+            do_inv = true;
+            if (do_fwd) {
+                launch_forward(exact, g, p->prefilter, d_rgb, rgb_stride, fwd, fwd_stride,
+                               J.shared_input ? 1 : n, s);
+                c->launches++;
+            }
+            JDS_CUDA(cudaEventRecord(c->evs[1], s));
+            launch_codec(exact, g, fwd, fwd_stride, rec, rec_stride, d_tables,
+                         J.qualities ? 1 : 0, d_coeffs, ncoef, want_hist, d_metrics, n, s);
+            JDS_CUDA(cudaEventRecord(c->evs[2], s));
+            launch_inverse(exact, g, d_rgb, rgb_stride, fwd, fwd_stride, rec, rec_stride, d_recon,
+                           frame_bytes, d_ey, d_ergb, d_metrics, n, s);
+            JDS_CUDA(cudaEventRecord(c->evs[3], s));
+            c->launches += 2;
+            do_ssim = want_ssim && g.H >= 7 && g.W >= 7;
+            if (do_ssim) {
+                if (!c->legacy_ssim &&
+                    ssim_strip_supported(g.H, g.W, d_rgb, rgb_stride, d_recon, frame_bytes)) {
+                    JDS_CUDA(launch_ssim_strip(g.H, g.W, d_rgb, rgb_stride, d_recon, frame_bytes,
+                                               d_metrics, n, true, false, c->sm_count, s));
+                } else {
+                    launch_ssim(exact, g.H, g.W, d_rgb, rgb_stride, d_recon, frame_bytes,
+                                d_metrics, n, s);
+                }
+                c->launches++;
+            }
         }
         JDS_CUDA(cudaEventRecord(c->evs[4], s));
         JDS_CUDA(cudaEventRecord(c->ev1, s));
@@ -398,7 +444,7 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
         float ms = 0.f;
         JDS_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
         {
-            const bool ran[4] = {do_fwd, true, true, do_ssim};
+            const bool ran[4] = {do_fwd, true, do_inv, do_ssim};
             for (int k = 0; k < 4; ++k) {
                 float t = 0.f;
                 JDS_CUDA(cudaEventElapsedTime(&t, c->evs[k], c->evs[k + 1]));

@@ -1,0 +1,789 @@
+// jds_fused.cu - fused fast-mode (fp32) codec kernels for sm_100a.
+//
+//   k_fast_chroma<SUB>   RGB tile -> decimated Cb/Cr (byte sums via IDP4A) -> 8x8 AAN DCT,
+//                        quantise, bit model, dequantise, IDCT, clamp -> reconstructed
+//                        chroma planes (fp32 in [0,1], L2 resident scratch)
+//   k_fast_luma<SUB>     RGB tile -> Y -> 8x8 codec in registers -> (chroma tile from
+//                        the planes above, bilinear upsample) -> YCbCr->RGB, clamp,
+//                        truncate -> packed uint8 RGB
+//   k_fast_444           all three channels of a tile in one CTA (no chroma planes)
+//
+// Common structure: one thread owns one 8x8 block (64 samples in registers, both DCT
+// passes without any exchange); tiles are staged through shared memory with TMA bulk
+// row copies (cp.async.bulk + mbarrier) so that global traffic is 128-byte coalesced;
+// the block layout in shared memory has a 68-float stride so per-thread LDS.128 /
+// STS.128 are conflict free.  Level shift, the 1/255 output scale and the AAN scale
+// factors are folded into the tables / the DC term; the [0,255] clamps are the free
+// .SAT modifier of the last butterfly add; uint8 truncation is one FFMA.RM against
+// 2^23.  Squared errors and SSIM are left to k_ssim_strip (jds_ssim.cu), which reads
+// the two uint8 images back through L2.
+//
+// Reference stages covered: engines/color_space.py:8-14,27-53,56-66,17-24;
+// engines/dct_engine.py:17-27; engines/quantizer.py:22-29; utils/metrics.py:63-85
+// (bit model); engines/pipeline.py:47-95.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "jds_kernels.cuh"
+#include "jds_math.cuh"
+
+namespace jds {
+
+// ------------------------------------------------------------------------------
+// TMA / mbarrier helpers
+// ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t f_smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void f_mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(f_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void f_mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(f_smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void f_mbar_wait(unsigned long long* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "F_WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra F_DONE;\n"
+        "bra F_WAIT_LOOP;\n"
+        "F_DONE:\n"
+        "}\n" ::"r"(f_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void f_bulk_g2s(void* dst, const void* src, uint32_t bytes,
+                                           unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(f_smem_u32(dst)), "l"(src), "r"(bytes), "r"(f_smem_u32(bar))
+        : "memory");
+}
+
+// ------------------------------------------------------------------------------
+// small arithmetic helpers
+// ------------------------------------------------------------------------------
+constexpr float kMagicRound = 12582912.0f;        // 1.5 * 2^23: round-half-even of |x| < 2^22
+constexpr int kMagicRoundBits = 0x4B400000;
+constexpr float kInv255 = 1.0f / 255.0f;
+constexpr float k128_255 = 128.0f / 255.0f;
+constexpr int BLK_STRIDE = 68;                    // floats per 8x8 block slot in shared memory
+
+template <int B>
+__device__ __forceinline__ float f_byte_centered(uint32_t w) {
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440 | B)) - 8388736.0f;
+}
+
+// inverse AAN butterfly whose eight outputs are saturated to [0,1] (FADD.SAT)
+__device__ __forceinline__ void idct8_aan_sat(float* d) {
+    float t10 = d[0] + d[4], t11 = d[0] - d[4];
+    float t13 = d[2] + d[6];
+    float t12 = fmaf(d[2] - d[6], 1.414213562373095049f, -t13);
+    float t0 = t10 + t13, t3 = t10 - t13;
+    float t1 = t11 + t12, t2 = t11 - t12;
+    float z13 = d[5] + d[3], z10 = d[5] - d[3];
+    float z11 = d[1] + d[7], z12 = d[1] - d[7];
+    float t7 = z11 + z13;
+    float t11b = (z11 - z13) * 1.414213562373095049f;
+    float z5 = (z10 + z12) * 1.847759065022573512f;
+    float t10b = fmaf(-1.082392200292393968f, z12, z5);
+    float t12b = fmaf(-2.613125929752753055f, z10, z5);
+    float t6 = t12b - t7;
+    float t5 = t11b - t6;
+    float t4 = t10b - t5;
+    d[0] = __saturatef(t0 + t7);
+    d[7] = __saturatef(t0 - t7);
+    d[1] = __saturatef(t1 + t6);
+    d[6] = __saturatef(t1 - t6);
+    d[2] = __saturatef(t2 + t5);
+    d[5] = __saturatef(t2 - t5);
+    d[3] = __saturatef(t3 + t4);
+    d[4] = __saturatef(t3 - t4);
+}
+
+// One 8x8 block, level-shifted samples in v (row-major) -> reconstructed samples / 255
+// clamped to [0,1].  s_fq / s_dq: shared-memory tables (dq already divided by 255).
+// esum accumulates the fp32 exponent fields of the non-zero quantised values
+// (bits = esum - 119 * nnz, utils/metrics.py:75-79), nnz their count.
+template <bool COEFFS>
+__device__ __forceinline__ void codec_fast(float* v, const float* __restrict__ s_fq,
+                                           const float* __restrict__ s_dq, unsigned& esum,
+                                           unsigned& nnz, int16_t* __restrict__ coef_out) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        float t[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) t[r] = v[r * 8 + c];
+        dct8_aan(t);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) v[r * 8 + c] = t[r];
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) dct8_aan(v + r * 8);
+
+    unsigned e_acc = 0, n_acc = 0;
+    uint32_t packed[32];
+#pragma unroll
+    for (int i = 0; i < 64; i += 4) {
+        const float4 fq = *reinterpret_cast<const float4*>(s_fq + i);
+        const float4 dq = *reinterpret_cast<const float4*>(s_dq + i);
+        const float fqv[4] = {fq.x, fq.y, fq.z, fq.w};
+        const float dqv[4] = {dq.x, dq.y, dq.z, dq.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float t = fmaf(v[i + k], fqv[k], kMagicRound);
+            const float qf = t - kMagicRound;
+            const unsigned e = (__float_as_uint(qf) >> 23) & 0xFFu;
+            e_acc += e;
+            n_acc += (e + 1u) >> 7;
+            v[i + k] = qf * dqv[k];
+            if (COEFFS) {
+                const uint32_t qi = (uint32_t)(__float_as_int(t) - kMagicRoundBits) & 0xFFFFu;
+                if (k & 1) packed[(i + k) >> 1] |= qi << 16;
+                else packed[(i + k) >> 1] = qi;
+            }
+        }
+    }
+    esum += e_acc;
+    nnz += n_acc;
+    if (COEFFS) {
+        uint4* out = reinterpret_cast<uint4*>(coef_out);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            out[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+    }
+    v[0] += k128_255;                      // +128 (in 1/255 units) on every output sample
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        float t[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) t[r] = v[r * 8 + c];
+        idct8_aan(t);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) v[r * 8 + c] = t[r];
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) idct8_aan_sat(v + r * 8);
+}
+
+__device__ __forceinline__ void load_tables(const QTables* __restrict__ src, float* s_fq,
+                                            float* s_dq, int tid, int nthreads) {
+    for (int i = tid; i < 64; i += nthreads) {
+        s_fq[i] = src->fq[i];
+        s_dq[i] = src->dq[i] * kInv255;
+    }
+}
+
+__device__ __forceinline__ void flush_stats(unsigned esum, unsigned nnz, DevMetrics* m) {
+    // bits = 6*nnz + sum(bit_length + 1) = esum - 119*nnz  (exponent = 126 + bit_length)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        esum += __shfl_down_sync(0xffffffffu, esum, o);
+        nnz += __shfl_down_sync(0xffffffffu, nnz, o);
+    }
+    if ((threadIdx.x & 31) == 0 && nnz) {
+        atomicAdd(&m->coeff_bits, (unsigned long long)esum - 119ull * nnz);
+        atomicAdd(&m->nnz, (unsigned long long)nnz);
+    }
+}
+
+// floor(255 * s) for s in [0,1] as the low byte of the returned word
+__device__ __forceinline__ uint32_t trunc_byte(float s01) {
+    return __float_as_uint(__fmaf_rd(s01, 255.0f, 8388608.0f));
+}
+__device__ __forceinline__ uint32_t pack4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+}
+
+// ------------------------------------------------------------------------------
+// chroma kernel: SUB = 1 (4:2:2) or 2 (4:2:0), no prefilter
+// tile = 16 x 4 chroma blocks per channel; thread t: channel t/64, block t%64
+// ------------------------------------------------------------------------------
+constexpr int CA_BX = 16, CA_BY = 4, CA_NT = 128;
+constexpr int CA_ROWB = CA_BX * 16 * 3;          // 768 bytes of RGB per tile row
+
+template <int SUB>
+struct ChromaSmem {
+    static constexpr int ROWS = CA_BY * 8 * (SUB == 2 ? 2 : 1);
+    alignas(128) uint8_t raw[ROWS][CA_ROWB];
+    alignas(16) float plane[2][CA_BX * CA_BY][BLK_STRIDE];
+    alignas(16) float fq[64];
+    alignas(16) float dq[64];
+    alignas(8) unsigned long long bar;
+};
+
+template <int SUB, bool COEFFS>
+__global__ void __launch_bounds__(CA_NT)
+k_fast_chroma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
+              float* __restrict__ cplanes, size_t cplane_stride,
+              const QTables* __restrict__ tables, int table_stride,
+              int16_t* __restrict__ coeffs, size_t coeff_stride, DevMetrics* __restrict__ metrics) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    ChromaSmem<SUB>& sm = *reinterpret_cast<ChromaSmem<SUB>*>(smem_raw);
+    constexpr int VS = (SUB == 2) ? 2 : 1;            // luma rows per chroma row
+    constexpr int ROWS = ChromaSmem<SUB>::ROWS;
+    const int tid = threadIdx.x;
+    const int unit = blockIdx.z;
+    const uint8_t* in = rgb + (size_t)unit * rgb_stride;
+    const int bx0 = blockIdx.x * CA_BX, by0 = blockIdx.y * CA_BY;   // chroma block origin
+    const int x0 = bx0 * 16, y0 = by0 * 8 * VS;                      // luma pixel origin
+    const int n_rows = min(ROWS, g.H - y0);
+    const int n_px = min(CA_BX * 16, g.W - x0);
+    const uint32_t row_bytes = (uint32_t)n_px * 3u;
+
+    if (tid == 0) {
+        f_mbar_init(&sm.bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid < 32) {
+        if (tid == 0) f_mbar_expect_tx(&sm.bar, row_bytes * (uint32_t)n_rows);
+        __syncwarp();
+        for (int r = tid; r < n_rows; r += 32)
+            f_bulk_g2s(&sm.raw[r][0], in + ((size_t)(y0 + r) * g.W + x0) * 3, row_bytes, &sm.bar);
+    }
+    load_tables(tables + (size_t)unit * table_stride, sm.fq, sm.dq, tid, CA_NT);
+    f_mbar_wait(&sm.bar, 0);
+
+    // ---- decimation: a task = one chroma row x 8 chroma samples (16 luma pixels) ----
+    // channel sums over the 2x1 / 2x2 footprint with IDP4A on the interleaved bytes,
+    // accumulated on top of 2^23's bit pattern so the fp32 value is one FADD away
+    constexpr int C_ROWS = CA_BY * 8, C_SEGS = CA_BX;
+    const float ks = (SUB == 2) ? 0.25f : 0.5f;
+    for (int task = tid; task < C_ROWS * C_SEGS; task += CA_NT) {
+        const int cr = task / C_SEGS, seg = task % C_SEGS;
+        if (cr * VS < n_rows && seg * 16 < n_px) {
+            uint32_t w[VS][12];
+#pragma unroll
+            for (int v = 0; v < VS; ++v) {
+                const uint4* q = reinterpret_cast<const uint4*>(&sm.raw[cr * VS + v][seg * 48]);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const uint4 a = q[i];
+                    w[v][4 * i] = a.x; w[v][4 * i + 1] = a.y; w[v][4 * i + 2] = a.z; w[v][4 * i + 3] = a.w;
+                }
+            }
+            float cb[8], crr[8];
+#pragma unroll
+            for (int gq = 0; gq < 4; ++gq) {        // 12-byte group = 4 pixels = 2 chroma samples
+                unsigned rA = 0x4B000000u, gA = 0x4B000000u, bA = 0x4B000000u;
+                unsigned rB = 0x4B000000u, gB = 0x4B000000u, bB = 0x4B000000u;
+#pragma unroll
+                for (int v = 0; v < VS; ++v) {
+                    const uint32_t w0 = w[v][3 * gq], w1 = w[v][3 * gq + 1], w2 = w[v][3 * gq + 2];
+                    rA = __dp4a(w0, 0x01000001u, rA);                        // bytes 0,3
+                    gA = __dp4a(w0, 0x00000100u, __dp4a(w1, 0x00000001u, gA)); // bytes 1,4
+                    bA = __dp4a(w0, 0x00010000u, __dp4a(w1, 0x00000100u, bA)); // bytes 2,5
+                    rB = __dp4a(w1, 0x00010000u, __dp4a(w2, 0x00000100u, rB)); // bytes 6,9
+                    gB = __dp4a(w1, 0x01000000u, __dp4a(w2, 0x00010000u, gB)); // bytes 7,10
+                    bB = __dp4a(w2, 0x01000001u, bB);                        // bytes 8,11
+                }
+                const float fr0 = __uint_as_float(rA) - 8388608.0f, fg0 = __uint_as_float(gA) - 8388608.0f,
+                            fb0 = __uint_as_float(bA) - 8388608.0f;
+                const float fr1 = __uint_as_float(rB) - 8388608.0f, fg1 = __uint_as_float(gB) - 8388608.0f,
+                            fb1 = __uint_as_float(bB) - 8388608.0f;
+                // level-shifted chroma (the +128 of colour_space.py:12-13 cancels the -128
+                // of dct_engine.py:19)
+                cb[2 * gq] = fmaf(-0.168736f * ks, fr0, fmaf(-0.331264f * ks, fg0, (0.5f * ks) * fb0));
+                crr[2 * gq] = fmaf(0.5f * ks, fr0, fmaf(-0.418688f * ks, fg0, (-0.081312f * ks) * fb0));
+                cb[2 * gq + 1] = fmaf(-0.168736f * ks, fr1, fmaf(-0.331264f * ks, fg1, (0.5f * ks) * fb1));
+                crr[2 * gq + 1] = fmaf(0.5f * ks, fr1, fmaf(-0.418688f * ks, fg1, (-0.081312f * ks) * fb1));
+            }
+            const int blk = (cr >> 3) * CA_BX + seg, ry = cr & 7;
+            float4* pb = reinterpret_cast<float4*>(&sm.plane[0][blk][ry * 8]);
+            float4* pr = reinterpret_cast<float4*>(&sm.plane[1][blk][ry * 8]);
+            pb[0] = make_float4(cb[0], cb[1], cb[2], cb[3]);
+            pb[1] = make_float4(cb[4], cb[5], cb[6], cb[7]);
+            pr[0] = make_float4(crr[0], crr[1], crr[2], crr[3]);
+            pr[1] = make_float4(crr[4], crr[5], crr[6], crr[7]);
+        }
+    }
+    __syncthreads();
+
+    // ---- codec: one block per thread ---------------------------------------------
+    const int ch = tid >> 6, blk = tid & 63;
+    const int bx = bx0 + (blk & (CA_BX - 1)), by = by0 + (blk >> 4);
+    unsigned esum = 0, nnz = 0;
+    if (bx < g.nbx_c && by < g.nby_c) {
+        float v[64];
+        const float4* src = reinterpret_cast<const float4*>(&sm.plane[ch][blk][0]);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float4 a = src[i];
+            v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = a.z; v[4 * i + 3] = a.w;
+        }
+        int16_t* cout = nullptr;
+        if (COEFFS)
+            cout = coeffs + (size_t)unit * coeff_stride +
+                   ((size_t)g.nblk_y + (size_t)ch * g.nblk_c + (size_t)by * g.nbx_c + bx) * 64;
+        codec_fast<COEFFS>(v, sm.fq, sm.dq, esum, nnz, cout);
+        float* dst = cplanes + (size_t)unit * cplane_stride + (size_t)ch * g.plane_c +
+                     (size_t)(by * 8) * g.wcp + bx * 8;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            float4* d4 = reinterpret_cast<float4*>(dst + (size_t)r * g.wcp);
+            d4[0] = make_float4(v[r * 8], v[r * 8 + 1], v[r * 8 + 2], v[r * 8 + 3]);
+            d4[1] = make_float4(v[r * 8 + 4], v[r * 8 + 5], v[r * 8 + 6], v[r * 8 + 7]);
+        }
+    }
+    flush_stats(esum, nnz, metrics + unit);
+}
+
+// ------------------------------------------------------------------------------
+// luma + compose kernel: SUB = 1 (4:2:2) or 2 (4:2:0)
+// tile = 32 x 4 luma blocks (256 x 32 pixels); thread t owns block t
+// ------------------------------------------------------------------------------
+constexpr int LU_BX = 32, LU_BY = 4, LU_NT = 128;
+constexpr int LU_TW = LU_BX * 8, LU_TH = LU_BY * 8;      // 256 x 32
+constexpr int LU_ROWB = LU_TW * 3;                       // 768
+constexpr int CT_COLS = LU_TW / 2 + 8;                   // 136 chroma columns staged
+
+template <int SUB>
+struct LumaSmem {
+    static constexpr int CT_ROWS = (SUB == 2) ? LU_TH / 2 + 2 : LU_TH;
+    alignas(128) uint8_t raw[LU_TH][LU_ROWB];
+    alignas(16) float plane[LU_BX * LU_BY][BLK_STRIDE];
+    alignas(128) float ctile[2][CT_ROWS][CT_COLS];
+    alignas(16) float fq[64];
+    alignas(16) float dq[64];
+    alignas(8) unsigned long long bar[2];
+};
+
+// 16 horizontally upsampled chroma samples from staged samples c[0..15], where c[4+k]
+// is the chroma sample under output pair k (cv2.resize INTER_LINEAR 2x: weights .25/.75)
+__device__ __forceinline__ void upsample_row16(const float* c, float* o) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float q = 0.75f * c[4 + k];
+        o[2 * k] = fmaf(0.25f, c[3 + k], q);
+        o[2 * k + 1] = fmaf(0.25f, c[5 + k], q);
+    }
+}
+
+// load 16 staged chroma samples (k0-4 .. k0+11), replicate at the image border, upsample
+__device__ __forceinline__ void stage_up16(const float* src, bool left_edge, bool right_edge,
+                                           float* o) {
+    float c[16];
+    const float4* q = reinterpret_cast<const float4*>(src);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float4 a = q[i];
+        c[4 * i] = a.x; c[4 * i + 1] = a.y; c[4 * i + 2] = a.z; c[4 * i + 3] = a.w;
+    }
+    if (left_edge) c[3] = c[4];
+    if (right_edge) c[12] = c[11];
+    upsample_row16(c, o);
+}
+
+template <int SUB, bool COEFFS>
+__global__ void __launch_bounds__(LU_NT)
+k_fast_luma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
+            const float* __restrict__ cplanes, size_t cplane_stride,
+            const QTables* __restrict__ tables, int table_stride,
+            int16_t* __restrict__ coeffs, size_t coeff_stride,
+            uint8_t* __restrict__ recon, size_t recon_stride, DevMetrics* __restrict__ metrics) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    LumaSmem<SUB>& sm = *reinterpret_cast<LumaSmem<SUB>*>(smem_raw);
+    constexpr int CT_ROWS = LumaSmem<SUB>::CT_ROWS;
+    const int tid = threadIdx.x;
+    const int unit = blockIdx.z;
+    const uint8_t* in = rgb + (size_t)unit * rgb_stride;
+    const int x0 = blockIdx.x * LU_TW, y0 = blockIdx.y * LU_TH;
+    const int n_rows = min(LU_TH, g.H - y0);
+    const int n_px = min(LU_TW, g.W - x0);
+    const uint32_t row_bytes = (uint32_t)n_px * 3u;
+
+    // chroma tile geometry: columns [ccol0, ccol0 + ncc), rows [crow0, crow0 + ncr)
+    const int cx0 = x0 >> 1;
+    const int cy0 = (SUB == 2) ? (y0 >> 1) : y0;
+    const int ccol_lo = cx0 - 4;                              // smem column 0
+    const int ccol0 = max(ccol_lo, 0);
+    const int ccol1 = min(cx0 + (n_px >> 1) + 4, g.wc);
+    const int crow_lo = (SUB == 2) ? cy0 - 1 : cy0;           // smem row 0
+    const int crow0 = max(crow_lo, 0);
+    const int crow1 = (SUB == 2) ? min(cy0 + (n_rows >> 1) + 1, g.hc) : min(cy0 + n_rows, g.hc);
+
+    if (tid == 0) {
+        f_mbar_init(&sm.bar[0], 1);
+        f_mbar_init(&sm.bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid < 32) {
+        if (tid == 0) {
+            f_mbar_expect_tx(&sm.bar[0], row_bytes * (uint32_t)n_rows);
+            f_mbar_expect_tx(&sm.bar[1], (uint32_t)(ccol1 - ccol0) * 4u * 2u * (uint32_t)(crow1 - crow0));
+        }
+        __syncwarp();
+        for (int r = tid; r < n_rows; r += 32)
+            f_bulk_g2s(&sm.raw[r][0], in + ((size_t)(y0 + r) * g.W + x0) * 3, row_bytes, &sm.bar[0]);
+        // reconstructed chroma (written by k_fast_chroma earlier in this stream)
+        const float* cp = cplanes + (size_t)unit * cplane_stride;
+        const int ncr = crow1 - crow0;
+        for (int i = tid; i < 2 * ncr; i += 32) {
+            const int chn = i / ncr, r = crow0 + i % ncr;
+            f_bulk_g2s(&sm.ctile[chn][r - crow_lo][ccol0 - ccol_lo],
+                       cp + (size_t)chn * g.plane_c + (size_t)r * g.wcp + ccol0,
+                       (uint32_t)(ccol1 - ccol0) * 4u, &sm.bar[1]);
+        }
+    }
+    load_tables(tables + (size_t)unit * table_stride, sm.fq, sm.dq, tid, LU_NT);
+    f_mbar_wait(&sm.bar[0], 0);
+
+    // ---- RGB -> level-shifted Y, block layout: a task = one row x 16 pixels ----------
+    for (int task = tid; task < LU_TH * (LU_TW / 16); task += LU_NT) {
+        const int r = task / (LU_TW / 16), seg = task % (LU_TW / 16);
+        if (r < n_rows && seg * 16 < n_px) {
+            const uint4* q = reinterpret_cast<const uint4*>(&sm.raw[r][seg * 48]);
+            uint32_t w[12];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const uint4 a = q[i];
+                w[4 * i] = a.x; w[4 * i + 1] = a.y; w[4 * i + 2] = a.z; w[4 * i + 3] = a.w;
+            }
+            float yv[16];
+#pragma unroll
+            for (int gq = 0; gq < 4; ++gq) {
+                const uint32_t w0 = w[3 * gq], w1 = w[3 * gq + 1], w2 = w[3 * gq + 2];
+                yv[4 * gq + 0] = fmaf(0.299f, f_byte_centered<0>(w0), fmaf(0.587f, f_byte_centered<1>(w0), 0.114f * f_byte_centered<2>(w0)));
+                yv[4 * gq + 1] = fmaf(0.299f, f_byte_centered<3>(w0), fmaf(0.587f, f_byte_centered<0>(w1), 0.114f * f_byte_centered<1>(w1)));
+                yv[4 * gq + 2] = fmaf(0.299f, f_byte_centered<2>(w1), fmaf(0.587f, f_byte_centered<3>(w1), 0.114f * f_byte_centered<0>(w2)));
+                yv[4 * gq + 3] = fmaf(0.299f, f_byte_centered<1>(w2), fmaf(0.587f, f_byte_centered<2>(w2), 0.114f * f_byte_centered<3>(w2)));
+            }
+            const int blk = (r >> 3) * LU_BX + seg * 2, ry = r & 7;
+            float4* p0 = reinterpret_cast<float4*>(&sm.plane[blk][ry * 8]);
+            float4* p1 = reinterpret_cast<float4*>(&sm.plane[blk + 1][ry * 8]);
+            p0[0] = make_float4(yv[0], yv[1], yv[2], yv[3]);
+            p0[1] = make_float4(yv[4], yv[5], yv[6], yv[7]);
+            p1[0] = make_float4(yv[8], yv[9], yv[10], yv[11]);
+            p1[1] = make_float4(yv[12], yv[13], yv[14], yv[15]);
+        }
+    }
+    __syncthreads();
+
+    // ---- codec: one luma block per thread, in place -------------------------------
+    {
+        const int bx = (x0 >> 3) + (tid & (LU_BX - 1)), by = (y0 >> 3) + (tid >> 5);
+        unsigned esum = 0, nnz = 0;
+        if (bx < g.nbx_y && by < g.nby_y) {
+            float v[64];
+            float4* slot = reinterpret_cast<float4*>(&sm.plane[tid][0]);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float4 a = slot[i];
+                v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = a.z; v[4 * i + 3] = a.w;
+            }
+            int16_t* cout = nullptr;
+            if (COEFFS)
+                cout = coeffs + (size_t)unit * coeff_stride + ((size_t)by * g.nbx_y + bx) * 64;
+            codec_fast<COEFFS>(v, sm.fq, sm.dq, esum, nnz, cout);
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                slot[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+        flush_stats(esum, nnz, metrics + unit);
+    }
+    __syncthreads();
+    f_mbar_wait(&sm.bar[1], 0);
+
+    // ---- compose: a task = 2 rows (SUB 2) or 1 row (SUB 1) x 16 pixels ---------------
+    constexpr int RPT = (SUB == 2) ? 2 : 1;                   // rows per task
+    uint8_t* out = recon + (size_t)unit * recon_stride;
+    for (int task = tid; task < (LU_TH / RPT) * (LU_TW / 16); task += LU_NT) {
+        const int rp = task / (LU_TW / 16), seg = task % (LU_TW / 16);
+        const int r0 = rp * RPT;
+        if (r0 >= n_rows || seg * 16 >= n_px) continue;
+        // staged chroma columns: smem column of chroma sample k0 is k0 - ccol_lo = 8*seg + 4
+        const int sc = 8 * seg;                               // 16 floats from here: k0-4 .. k0+11
+        const bool left_edge = (cx0 + 8 * seg) == 0;
+        const bool right_edge = (cx0 + 8 * seg + 8) >= g.wc;
+        float up[2][RPT][16];                                 // [channel][row][pixel]
+#pragma unroll
+        for (int chn = 0; chn < 2; ++chn) {
+            if (SUB == 2) {
+                const int cyg = cy0 + rp;                     // chroma row under this row pair
+                const int ra = max(cyg - 1, 0) - crow_lo, rb = cyg - crow_lo,
+                          rc = min(cyg + 1, g.hc - 1) - crow_lo;
+                float ua[16], ub[16], uc[16];
+                stage_up16(&sm.ctile[chn][ra][sc], left_edge, right_edge, ua);
+                stage_up16(&sm.ctile[chn][rb][sc], left_edge, right_edge, ub);
+                stage_up16(&sm.ctile[chn][rc][sc], left_edge, right_edge, uc);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float q = 0.75f * ub[i];
+                    up[chn][0][i] = fmaf(0.25f, ua[i], q);    // even luma row: .25 above + .75 here
+                    up[chn][RPT - 1][i] = fmaf(0.25f, uc[i], q);   // odd row: .75 here + .25 below
+                }
+            } else {
+                stage_up16(&sm.ctile[chn][cy0 + r0 - crow_lo][sc], left_edge, right_edge, up[chn][0]);
+            }
+        }
+#pragma unroll
+        for (int rr = 0; rr < RPT; ++rr) {
+            const int r = r0 + rr;
+            if (r >= n_rows) break;
+            const int blk = (r >> 3) * LU_BX + seg * 2, ry = r & 7;
+            float yv[16];
+            {
+                const float4* p0 = reinterpret_cast<const float4*>(&sm.plane[blk][ry * 8]);
+                const float4* p1 = reinterpret_cast<const float4*>(&sm.plane[blk + 1][ry * 8]);
+                float4 a = p0[0], b = p0[1], c = p1[0], d = p1[1];
+                yv[0] = a.x; yv[1] = a.y; yv[2] = a.z; yv[3] = a.w;
+                yv[4] = b.x; yv[5] = b.y; yv[6] = b.z; yv[7] = b.w;
+                yv[8] = c.x; yv[9] = c.y; yv[10] = c.z; yv[11] = c.w;
+                yv[12] = d.x; yv[13] = d.y; yv[14] = d.z; yv[15] = d.w;
+            }
+            uint32_t bytes[48];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                // planes hold value/255 in [0,1]; chroma offset 128/255 folded into constants
+                const float cbv = up[0][rr][i], crv = up[1][rr][i];
+                const float rf = __saturatef(fmaf(1.402f, crv, yv[i] - 1.402f * k128_255));
+                const float gf = __saturatef(fmaf(-0.344136f, cbv, fmaf(-0.714136f, crv, yv[i] + (0.344136f + 0.714136f) * k128_255)));
+                const float bf = __saturatef(fmaf(1.772f, cbv, yv[i] - 1.772f * k128_255));
+                bytes[3 * i] = trunc_byte(rf);
+                bytes[3 * i + 1] = trunc_byte(gf);
+                bytes[3 * i + 2] = trunc_byte(bf);
+            }
+            uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)(y0 + r) * g.W + x0 + seg * 16) * 3);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                uint4 o;
+                o.x = pack4(bytes[16 * i + 0], bytes[16 * i + 1], bytes[16 * i + 2], bytes[16 * i + 3]);
+                o.y = pack4(bytes[16 * i + 4], bytes[16 * i + 5], bytes[16 * i + 6], bytes[16 * i + 7]);
+                o.z = pack4(bytes[16 * i + 8], bytes[16 * i + 9], bytes[16 * i + 10], bytes[16 * i + 11]);
+                o.w = pack4(bytes[16 * i + 12], bytes[16 * i + 13], bytes[16 * i + 14], bytes[16 * i + 15]);
+                dst[i] = o;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------
+// 4:4:4 kernel: tile = 16 x 4 blocks (128 x 32 pixels); 192 threads = 64 blocks x 3
+// ------------------------------------------------------------------------------
+constexpr int F4_BX = 16, F4_BY = 4, F4_NT = 192;
+constexpr int F4_TW = F4_BX * 8, F4_TH = F4_BY * 8;
+constexpr int F4_ROWB = F4_TW * 3;                       // 384
+
+struct F444Smem {
+    alignas(128) uint8_t raw[F4_TH][F4_ROWB];
+    alignas(16) float plane[3][F4_BX * F4_BY][BLK_STRIDE];
+    alignas(16) float fq[64];
+    alignas(16) float dq[64];
+    alignas(8) unsigned long long bar;
+};
+
+template <bool COEFFS>
+__global__ void __launch_bounds__(F4_NT)
+k_fast_444(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
+           const QTables* __restrict__ tables, int table_stride,
+           int16_t* __restrict__ coeffs, size_t coeff_stride,
+           uint8_t* __restrict__ recon, size_t recon_stride, DevMetrics* __restrict__ metrics) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    F444Smem& sm = *reinterpret_cast<F444Smem*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int unit = blockIdx.z;
+    const uint8_t* in = rgb + (size_t)unit * rgb_stride;
+    const int x0 = blockIdx.x * F4_TW, y0 = blockIdx.y * F4_TH;
+    const int n_rows = min(F4_TH, g.H - y0);
+    const int n_px = min(F4_TW, g.W - x0);
+    const uint32_t row_bytes = (uint32_t)n_px * 3u;
+    if (tid == 0) {
+        f_mbar_init(&sm.bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid < 32) {
+        if (tid == 0) f_mbar_expect_tx(&sm.bar, row_bytes * (uint32_t)n_rows);
+        __syncwarp();
+        for (int r = tid; r < n_rows; r += 32)
+            f_bulk_g2s(&sm.raw[r][0], in + ((size_t)(y0 + r) * g.W + x0) * 3, row_bytes, &sm.bar);
+    }
+    load_tables(tables + (size_t)unit * table_stride, sm.fq, sm.dq, tid, F4_NT);
+    f_mbar_wait(&sm.bar, 0);
+
+    for (int task = tid; task < F4_TH * (F4_TW / 16); task += F4_NT) {
+        const int r = task / (F4_TW / 16), seg = task % (F4_TW / 16);
+        if (r < n_rows && seg * 16 < n_px) {
+            const uint4* q = reinterpret_cast<const uint4*>(&sm.raw[r][seg * 48]);
+            uint32_t w[12];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const uint4 a = q[i];
+                w[4 * i] = a.x; w[4 * i + 1] = a.y; w[4 * i + 2] = a.z; w[4 * i + 3] = a.w;
+            }
+            float yv[16], cb[16], cr[16];
+#pragma unroll
+            for (int gq = 0; gq < 4; ++gq) {
+                const uint32_t w0 = w[3 * gq], w1 = w[3 * gq + 1], w2 = w[3 * gq + 2];
+                const float R[4] = {f_byte_centered<0>(w0), f_byte_centered<3>(w0), f_byte_centered<2>(w1), f_byte_centered<1>(w2)};
+                const float G[4] = {f_byte_centered<1>(w0), f_byte_centered<0>(w1), f_byte_centered<3>(w1), f_byte_centered<2>(w2)};
+                const float B[4] = {f_byte_centered<2>(w0), f_byte_centered<1>(w1), f_byte_centered<0>(w2), f_byte_centered<3>(w2)};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    // all three planes level-shifted by -128 (chroma: +128 then -128 cancel;
+                    // the coefficient rows of Cb and Cr sum to zero so centring R,G,B is free)
+                    yv[4 * gq + k] = fmaf(0.299f, R[k], fmaf(0.587f, G[k], 0.114f * B[k]));
+                    cb[4 * gq + k] = fmaf(-0.168736f, R[k], fmaf(-0.331264f, G[k], 0.5f * B[k]));
+                    cr[4 * gq + k] = fmaf(0.5f, R[k], fmaf(-0.418688f, G[k], -0.081312f * B[k]));
+                }
+            }
+            const int blk = (r >> 3) * F4_BX + seg * 2, ry = r & 7;
+            const float* srcs[3] = {yv, cb, cr};
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+                float4* p0 = reinterpret_cast<float4*>(&sm.plane[p][blk][ry * 8]);
+                float4* p1 = reinterpret_cast<float4*>(&sm.plane[p][blk + 1][ry * 8]);
+                const float* s = srcs[p];
+                p0[0] = make_float4(s[0], s[1], s[2], s[3]);
+                p0[1] = make_float4(s[4], s[5], s[6], s[7]);
+                p1[0] = make_float4(s[8], s[9], s[10], s[11]);
+                p1[1] = make_float4(s[12], s[13], s[14], s[15]);
+            }
+        }
+    }
+    __syncthreads();
+    {
+        const int ch = tid >> 6, blk = tid & 63;
+        const int bx = (x0 >> 3) + (blk & (F4_BX - 1)), by = (y0 >> 3) + (blk >> 4);
+        unsigned esum = 0, nnz = 0;
+        if (bx < g.nbx_y && by < g.nby_y) {
+            float v[64];
+            float4* slot = reinterpret_cast<float4*>(&sm.plane[ch][blk][0]);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float4 a = slot[i];
+                v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = a.z; v[4 * i + 3] = a.w;
+            }
+            int16_t* cout = nullptr;
+            if (COEFFS)
+                cout = coeffs + (size_t)unit * coeff_stride +
+                       ((size_t)ch * g.nblk_y + (size_t)by * g.nbx_y + bx) * 64;
+            codec_fast<COEFFS>(v, sm.fq, sm.dq, esum, nnz, cout);
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                slot[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+        flush_stats(esum, nnz, metrics + unit);
+    }
+    __syncthreads();
+    uint8_t* out = recon + (size_t)unit * recon_stride;
+    for (int task = tid; task < F4_TH * (F4_TW / 16); task += F4_NT) {
+        const int r = task / (F4_TW / 16), seg = task % (F4_TW / 16);
+        if (r >= n_rows || seg * 16 >= n_px) continue;
+        const int blk = (r >> 3) * F4_BX + seg * 2, ry = r & 7;
+        float pl[3][16];
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            const float4* p0 = reinterpret_cast<const float4*>(&sm.plane[p][blk][ry * 8]);
+            const float4* p1 = reinterpret_cast<const float4*>(&sm.plane[p][blk + 1][ry * 8]);
+            float4 a = p0[0], b = p0[1], c = p1[0], d = p1[1];
+            pl[p][0] = a.x; pl[p][1] = a.y; pl[p][2] = a.z; pl[p][3] = a.w;
+            pl[p][4] = b.x; pl[p][5] = b.y; pl[p][6] = b.z; pl[p][7] = b.w;
+            pl[p][8] = c.x; pl[p][9] = c.y; pl[p][10] = c.z; pl[p][11] = c.w;
+            pl[p][12] = d.x; pl[p][13] = d.y; pl[p][14] = d.z; pl[p][15] = d.w;
+        }
+        uint32_t bytes[48];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float yv = pl[0][i], cbv = pl[1][i], crv = pl[2][i];
+            const float rf = __saturatef(fmaf(1.402f, crv, yv - 1.402f * k128_255));
+            const float gf = __saturatef(fmaf(-0.344136f, cbv, fmaf(-0.714136f, crv, yv + (0.344136f + 0.714136f) * k128_255)));
+            const float bf = __saturatef(fmaf(1.772f, cbv, yv - 1.772f * k128_255));
+            bytes[3 * i] = trunc_byte(rf);
+            bytes[3 * i + 1] = trunc_byte(gf);
+            bytes[3 * i + 2] = trunc_byte(bf);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)(y0 + r) * g.W + x0 + seg * 16) * 3);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            uint4 o;
+            o.x = pack4(bytes[16 * i + 0], bytes[16 * i + 1], bytes[16 * i + 2], bytes[16 * i + 3]);
+            o.y = pack4(bytes[16 * i + 4], bytes[16 * i + 5], bytes[16 * i + 6], bytes[16 * i + 7]);
+            o.z = pack4(bytes[16 * i + 8], bytes[16 * i + 9], bytes[16 * i + 10], bytes[16 * i + 11]);
+            o.w = pack4(bytes[16 * i + 12], bytes[16 * i + 13], bytes[16 * i + 14], bytes[16 * i + 15]);
+            dst[i] = o;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------
+bool fused_supported(const Geom& g, int prefilter, const void* rgb, size_t rgb_stride,
+                     const void* recon, size_t recon_stride) {
+    if (prefilter && g.sub != 0) return false;        // prefilter: staged kernels (for now)
+    if ((g.W % 16) != 0 || (g.H % 8) != 0) return false;
+    if (g.sub == 2 && (g.H % 16) != 0) return false;   // chroma planes must be whole blocks
+    if (((uintptr_t)rgb | (uintptr_t)recon | rgb_stride | recon_stride) & 15) return false;
+    return true;
+}
+
+size_t fused_chroma_plane_floats(const Geom& g) { return g.sub ? (size_t)2 * g.plane_c : 0; }
+
+template <class K>
+static cudaError_t set_smem(K kernel, size_t bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+cudaError_t launch_fused_chroma(const Geom& g, const uint8_t* rgb, size_t rgb_stride,
+                                float* cplanes, size_t cplane_stride, const QTables* tables,
+                                int table_stride, int16_t* coeffs, size_t coeff_stride,
+                                DevMetrics* metrics, int units, cudaStream_t s) {
+    dim3 grid((g.nbx_c + CA_BX - 1) / CA_BX, (g.nby_c + CA_BY - 1) / CA_BY, units);
+    cudaError_t e;
+#define JDS_LAUNCH_CA(SUBV, CO)                                                                 \
+    do {                                                                                        \
+        e = set_smem(k_fast_chroma<SUBV, CO>, sizeof(ChromaSmem<SUBV>));                         \
+        if (e != cudaSuccess) return e;                                                          \
+        k_fast_chroma<SUBV, CO><<<grid, CA_NT, sizeof(ChromaSmem<SUBV>), s>>>(                   \
+            g, rgb, rgb_stride, cplanes, cplane_stride, tables, table_stride, coeffs,            \
+            coeff_stride, metrics);                                                              \
+    } while (0)
+    if (g.sub == 2) { if (coeffs) JDS_LAUNCH_CA(2, true); else JDS_LAUNCH_CA(2, false); }
+    else { if (coeffs) JDS_LAUNCH_CA(1, true); else JDS_LAUNCH_CA(1, false); }
+#undef JDS_LAUNCH_CA
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fused_luma(const Geom& g, const uint8_t* rgb, size_t rgb_stride,
+                              const float* cplanes, size_t cplane_stride, const QTables* tables,
+                              int table_stride, int16_t* coeffs, size_t coeff_stride,
+                              uint8_t* recon, size_t recon_stride, DevMetrics* metrics, int units,
+                              cudaStream_t s) {
+    cudaError_t e;
+    if (g.sub == 0) {
+        dim3 grid((g.nbx_y + F4_BX - 1) / F4_BX, (g.nby_y + F4_BY - 1) / F4_BY, units);
+        if (coeffs) {
+            e = set_smem(k_fast_444<true>, sizeof(F444Smem));
+            if (e != cudaSuccess) return e;
+            k_fast_444<true><<<grid, F4_NT, sizeof(F444Smem), s>>>(
+                g, rgb, rgb_stride, tables, table_stride, coeffs, coeff_stride, recon, recon_stride, metrics);
+        } else {
+            e = set_smem(k_fast_444<false>, sizeof(F444Smem));
+            if (e != cudaSuccess) return e;
+            k_fast_444<false><<<grid, F4_NT, sizeof(F444Smem), s>>>(
+                g, rgb, rgb_stride, tables, table_stride, coeffs, coeff_stride, recon, recon_stride, metrics);
+        }
+        return cudaGetLastError();
+    }
+    dim3 grid((g.nbx_y + LU_BX - 1) / LU_BX, (g.nby_y + LU_BY - 1) / LU_BY, units);
+#define JDS_LAUNCH_LU(SUBV, CO)                                                                 \
+    do {                                                                                        \
+        e = set_smem(k_fast_luma<SUBV, CO>, sizeof(LumaSmem<SUBV>));                             \
+        if (e != cudaSuccess) return e;                                                          \
+        k_fast_luma<SUBV, CO><<<grid, LU_NT, sizeof(LumaSmem<SUBV>), s>>>(                       \
+            g, rgb, rgb_stride, cplanes, cplane_stride, tables, table_stride, coeffs,            \
+            coeff_stride, recon, recon_stride, metrics);                                         \
+    } while (0)
+    if (g.sub == 2) { if (coeffs) JDS_LAUNCH_LU(2, true); else JDS_LAUNCH_LU(2, false); }
+    else { if (coeffs) JDS_LAUNCH_LU(1, true); else JDS_LAUNCH_LU(1, false); }
+#undef JDS_LAUNCH_LU
+    return cudaGetLastError();
+}
+
+}  // namespace jds

@@ -17,6 +17,26 @@ void launch_inverse(bool exact, const Geom& g, const uint8_t* rgb, size_t rgb_st
                     DevMetrics* metrics, int units, cudaStream_t s);
 void launch_ssim(bool exact, int H, int W, const uint8_t* a, size_t a_stride, const uint8_t* b,
                  size_t b_stride, DevMetrics* metrics, int units, cudaStream_t s);
+// strip-streaming SSIM / SSE kernel (jds_ssim.cu); needs W % 16 == 0 and 16-byte aligned
+// image bases / unit strides (TMA bulk copies)
+bool ssim_strip_supported(int H, int W, const void* a, size_t a_stride, const void* b,
+                          size_t b_stride);
+cudaError_t launch_ssim_strip(int H, int W, const uint8_t* a, size_t a_stride, const uint8_t* b,
+                              size_t b_stride, DevMetrics* metrics, int units, bool want_ssim,
+                              bool want_sse, int sm_count, cudaStream_t s);
+// fused fast-mode codec kernels (jds_fused.cu)
+bool fused_supported(const Geom& g, int prefilter, const void* rgb, size_t rgb_stride,
+                     const void* recon, size_t recon_stride);
+size_t fused_chroma_plane_floats(const Geom& g);
+cudaError_t launch_fused_chroma(const Geom& g, const uint8_t* rgb, size_t rgb_stride,
+                                float* cplanes, size_t cplane_stride, const QTables* tables,
+                                int table_stride, int16_t* coeffs, size_t coeff_stride,
+                                DevMetrics* metrics, int units, cudaStream_t s);
+cudaError_t launch_fused_luma(const Geom& g, const uint8_t* rgb, size_t rgb_stride,
+                              const float* cplanes, size_t cplane_stride, const QTables* tables,
+                              int table_stride, int16_t* coeffs, size_t coeff_stride,
+                              uint8_t* recon, size_t recon_stride, DevMetrics* metrics, int units,
+                              cudaStream_t s);
 void launch_selected_block(const Geom& g, const uint8_t* rgb, int bx, int by,
                            const QTables* tables, void* out, cudaStream_t s);
 size_t selected_out_bytes();

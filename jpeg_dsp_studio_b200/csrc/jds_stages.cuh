@@ -132,7 +132,7 @@ struct BlockCodec<Exact> {
             q[i] = (int16_t)qi;
             bits += coeff_bits(qi);
             nnz += (qi != 0);
-            v[i] = P::mul(qv, tb.q[i]);
+            v[i] = P::mul((double)qi, tb.q[i]);     // int16 -> fp64: never -0.0 (quantizer.py:29)
             if (deq_out) deq_out[i] = v[i];
         }
         st.bits = bits;
