@@ -6,39 +6,50 @@
 // of squared differences for PSNR (utils/metrics.py:11,20).
 //
 // Design (DESIGN.md "k_ssim_strip"):
-//   * a CTA owns a vertical strip of 128 window columns (134 pixel columns) and walks
+//   * a CTA owns a vertical strip of 64 window columns (70 pixel columns) and walks
 //     down it 7 rows at a time; nothing is recomputed vertically.
 //   * rows arrive by TMA bulk copies (cp.async.bulk + mbarrier), double buffered.
-//   * pass 1 (horizontal): a thread owns (row, channel, 16-window segment) and forms
-//     the 7-tap window sums of x, y, x^2+y^2, xy by running prefix differences in
-//     registers; results go to shared memory as one float4 per (row, channel, column).
-//   * pass 2 (vertical): a thread owns (column, channel), keeps the last 7 horizontal
+//   * the four channels are processed as two PAIRS - (R,G) and (B,Y) - and every
+//     floating-point operation is a packed f32x2 instruction (FADD2/FMUL2/FFMA2, new on
+//     sm_100): one issue slot does the work for both channels of the pair.
+//   * prep: bytes -> centred (x-128) fp32, channel pairs interleaved, plus BT.601 Y.
+//   * pass 1 (horizontal): a thread owns (row, pair, 8-window segment) and forms the
+//     7-tap window sums of x, y, x^2+y^2, xy by running prefix differences in
+//     registers; results go to shared memory (32 B per row, pair, column).
+//   * pass 2 (vertical): a thread owns (column, pair), keeps the last 7 horizontal
 //     sums in a register ring, slides the 7-row sum and evaluates the SSIM formula.
-//   * samples are centred (x-128) so fp32 sums of the integer channels are exact and
-//     the fp32 Y sums keep their low bits; the Y accumulators are rebuilt from the
-//     ring every chunk so rounding cannot drift down a strip.
+//   * centring makes the fp32 sums of the integer channels exact and keeps the low
+//     bits of the Y sums; the Y accumulators are rebuilt from the ring every chunk so
+//     rounding cannot drift down a strip.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "jds_kernels.cuh"
 
 namespace jds {
 
-constexpr int S_OW = 128;            // window columns per strip
-constexpr int S_LW = 144;            // pixel columns loaded per strip (multiple of 16)
+constexpr int S_OW = 64;             // window columns per strip
+constexpr int S_LW = 80;             // pixel columns loaded per strip (multiple of 16)
 constexpr int S_ROWB = S_LW * 3;     // bytes per loaded row
 constexpr int S_R = 7;               // rows per chunk == window height
-constexpr int S_NT = 512;            // threads per CTA
-constexpr int S_SEG = 16;            // windows per pass-1 task
+constexpr int S_NT = 128;            // threads per CTA = 64 columns x 2 channel pairs
+constexpr int S_SEG = 8;             // windows per pass-1 task
 constexpr int S_NSEG = S_OW / S_SEG; // 8
+
+constexpr int S_FPITCH = S_LW + 2;   // float2 row pitch of fpl: rows land 16 B apart in the banks
+constexpr int S_HPITCH = 2 * S_OW + 1; // float4 row pitch of hbuf: likewise
+
+struct HSum {                        // window sums of one (row, pair, column)
+    float2 sx, sy, sq, sc;           // .x = first channel of the pair, .y = second
+};
 
 struct SsimSmem {
     alignas(128) uint8_t raw[2][2][S_R][S_ROWB];   // [buffer][image][row][byte]
-    alignas(16) float ybuf[2][S_R][S_LW];          // centred Y of both images
-    alignas(16) float4 hbuf[S_R][4][S_OW];         // horizontal window sums (swizzled)
+    alignas(16) float2 fpl[2][2][S_R][S_FPITCH];   // centred fp32 [image][pair][row][col]
+    alignas(16) float4 hxy[S_R][S_HPITCH];         // horizontal sums (sx, sy) [row][pair*64+col]
+    alignas(16) float4 hqc[S_R][S_HPITCH];         // horizontal sums (sq, sc)
     alignas(8) unsigned long long bar[2];
-    double red_ssim[4][16];
-    double red_ssey[16];
-    unsigned long long red_sse[16];
+    double red_ssim[4][2];
+    double red_sse[4][4];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -74,7 +85,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
         : "memory");
 }
 
-__device__ __forceinline__ int hswz(int col) { return col ^ ((col >> 4) & 7); }
+__device__ __forceinline__ int hswz(int col) { return col ^ ((col >> 3) & 7); }
 
 // byte `b` (0..3) of `w` as (value - 128) in fp32: 0x4B0000vv is 2^23 + vv
 template <int B>
@@ -82,101 +93,30 @@ __device__ __forceinline__ float byte_centered(uint32_t w) {
     return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440 | B)) - 8388736.0f;
 }
 
-// SSIM of one window from centred sums over its 49 samples
-__device__ __forceinline__ float ssim_window(float sx, float sy, float sq, float sxy) {
-    constexpr float inv = 1.0f / 49.0f;
-    constexpr float cn = 49.0f / 48.0f;
-    constexpr float C1 = 6.5025f, C2 = 58.5225f;
-    const float mx = sx * inv, my = sy * inv;
-    const float t = mx * my;
-    const float A2 = fmaf(sxy, 2.0f * cn * inv, fmaf(t, -2.0f * cn, C2));
-    const float u = fmaf(mx, mx, my * my);
-    const float B2 = fmaf(sq, cn * inv, fmaf(u, -cn, C2));
-    const float ux = mx + 128.0f, uy = my + 128.0f;
-    const float A1 = fmaf(ux * uy, 2.0f, C1);
-    const float B1 = fmaf(ux, ux, fmaf(uy, uy, C1));
-    return __fdividef(A1 * A2, B1 * B2);
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __ffma2_rn(b, f2(-1.0f), a); }
+
+// 0.5 * SSIM of one window for both channels of a pair, from the centred sums over its
+// 49 samples:  S = (2 ux uy + C1)(2 vxy + C2) / ((ux^2 + uy^2 + C1)(vx + vy + C2)),
+// v = 49/48 (E[ab]-E[a]E[b]), written on the raw sums (N = 49, Ux = N ux):
+//   S = 2 A1 A2 / (B1 B2),  A1 = 2 Ux Uy + C1 N^2,  B1 = Ux^2 + Uy^2 + C1 N^2,
+//   A2 = N Sxy - Sx Sy + C2 N (N-1) / 2,  B2 = N Sq - Sx^2 - Sy^2 + C2 N (N-1)
+__device__ __forceinline__ float2 ssim_window_half2(float2 sx, float2 sy, float2 sq, float2 sc) {
+    constexpr float N = 49.0f;
+    constexpr float C1N2 = 6.5025f * 2401.0f;
+    constexpr float K2 = 58.5225f * 49.0f * 48.0f;
+    const float2 Ux = __fadd2_rn(sx, f2(128.0f * N)), Uy = __fadd2_rn(sy, f2(128.0f * N));
+    const float2 A1 = __ffma2_rn(__fmul2_rn(Ux, Uy), f2(2.0f), f2(C1N2));
+    const float2 B1 = __ffma2_rn(Ux, Ux, __ffma2_rn(Uy, Uy, f2(C1N2)));
+    const float2 A2 = __ffma2_rn(sc, f2(N), __ffma2_rn(sx, sub2(f2(0.0f), sy), f2(0.5f * K2)));
+    const float2 u = __ffma2_rn(sx, sx, __fmul2_rn(sy, sy));
+    const float2 B2 = __ffma2_rn(sq, f2(N), sub2(f2(K2), u));
+    const float2 num = __fmul2_rn(A1, A2), den = __fmul2_rn(B1, B2);
+    return __fmul2_rn(num, f2(__fdividef(1.0f, den.x), __fdividef(1.0f, den.y)));
 }
 
-// ---- pass 1 for one (row, segment) of channel CH ---------------------------------
-template <int CH>
-__device__ __forceinline__ void pass1_task(SsimSmem& sm, int buf, int r, int seg, int valid_px,
-                                           float& sse_out) {
-    float px[S_SEG + 6], py[S_SEG + 6];
-    if (CH < 3) {
-        const uint4* qa = reinterpret_cast<const uint4*>(&sm.raw[buf][0][r][48 * seg]);
-        const uint4* qb = reinterpret_cast<const uint4*>(&sm.raw[buf][1][r][48 * seg]);
-        uint32_t wa[20], wb[20];
-#pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            uint4 a = qa[i], b = qb[i];
-            wa[4 * i] = a.x; wa[4 * i + 1] = a.y; wa[4 * i + 2] = a.z; wa[4 * i + 3] = a.w;
-            wb[4 * i] = b.x; wb[4 * i + 1] = b.y; wb[4 * i + 2] = b.z; wb[4 * i + 3] = b.w;
-        }
-#pragma unroll
-        for (int i = 0; i < S_SEG + 6; ++i) {
-            constexpr int dummy = 0;
-            (void)dummy;
-            const int b = 3 * i + CH;
-            const uint32_t va = wa[b >> 2], vb = wb[b >> 2];
-            switch (b & 3) {
-                case 0: px[i] = byte_centered<0>(va); py[i] = byte_centered<0>(vb); break;
-                case 1: px[i] = byte_centered<1>(va); py[i] = byte_centered<1>(vb); break;
-                case 2: px[i] = byte_centered<2>(va); py[i] = byte_centered<2>(vb); break;
-                default: px[i] = byte_centered<3>(va); py[i] = byte_centered<3>(vb); break;
-            }
-        }
-    } else {
-        const float4* qa = reinterpret_cast<const float4*>(&sm.ybuf[0][r][S_SEG * seg]);
-        const float4* qb = reinterpret_cast<const float4*>(&sm.ybuf[1][r][S_SEG * seg]);
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            float4 a = qa[i], b = qb[i];
-            if (4 * i + 0 < S_SEG + 6) { px[4 * i + 0] = a.x; py[4 * i + 0] = b.x; }
-            if (4 * i + 1 < S_SEG + 6) { px[4 * i + 1] = a.y; py[4 * i + 1] = b.y; }
-            if (4 * i + 2 < S_SEG + 6) { px[4 * i + 2] = a.z; py[4 * i + 2] = b.z; }
-            if (4 * i + 3 < S_SEG + 6) { px[4 * i + 3] = a.w; py[4 * i + 3] = b.w; }
-        }
-    }
-    // squared error of the pixels this task owns (its first 16 columns)
-    float sse = 0.f;
-    const int c0 = S_SEG * seg;
-    if (c0 + S_SEG <= valid_px) {
-#pragma unroll
-        for (int i = 0; i < S_SEG; ++i) {
-            const float d = px[i] - py[i];
-            sse = fmaf(d, d, sse);
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < S_SEG; ++i) {
-            const float d = (c0 + i < valid_px) ? px[i] - py[i] : 0.f;
-            sse = fmaf(d, d, sse);
-        }
-    }
-    sse_out += sse;
-    // running prefix sums; window j = prefix[j+7] - prefix[j]
-    float Px[S_SEG + 7], Py[S_SEG + 7], Pq[S_SEG + 7], Pc[S_SEG + 7];
-    Px[0] = Py[0] = Pq[0] = Pc[0] = 0.f;
-#pragma unroll
-    for (int i = 0; i < S_SEG + 6; ++i) {
-        Px[i + 1] = Px[i] + px[i];
-        Py[i + 1] = Py[i] + py[i];
-        Pq[i + 1] = fmaf(px[i], px[i], fmaf(py[i], py[i], Pq[i]));
-        Pc[i + 1] = fmaf(px[i], py[i], Pc[i]);
-    }
-#pragma unroll
-    for (int j = 0; j < S_SEG; ++j) {
-        float4 h;
-        h.x = Px[j + 7] - Px[j];
-        h.y = Py[j + 7] - Py[j];
-        h.z = Pq[j + 7] - Pq[j];
-        h.w = Pc[j + 7] - Pc[j];
-        sm.hbuf[r][CH][hswz(c0 + j)] = h;
-    }
-}
-
-__global__ void __launch_bounds__(S_NT, 1)
+__global__ void __launch_bounds__(S_NT, 3)
 k_ssim_strip(int H, int W, int seg_rows, const uint8_t* __restrict__ a_img, size_t a_stride,
              const uint8_t* __restrict__ b_img, size_t b_stride, DevMetrics* __restrict__ metrics,
              int want_ssim, int want_sse) {
@@ -187,7 +127,7 @@ k_ssim_strip(int H, int W, int seg_rows, const uint8_t* __restrict__ a_img, size
     const uint8_t* A = a_img + (size_t)unit * a_stride;
     const uint8_t* B = b_img + (size_t)unit * b_stride;
     const int x0 = blockIdx.x * S_OW;
-    // rows: this CTA owns pixel rows [py0, py1) for the squared error, and the window
+    // rows: this CTA owns pixel rows [py0, py1) for the squared error and the window
     // rows [py0, min(py1, H-6)) for SSIM; it reads pixel rows [py0, min(py1 + 6, H))
     const int py0 = blockIdx.y * seg_rows;
     const int py1 = min(py0 + seg_rows, H);
@@ -207,7 +147,7 @@ k_ssim_strip(int H, int W, int seg_rows, const uint8_t* __restrict__ a_img, size
     __syncthreads();
 
     auto issue = [&](int chunk) {
-        // one warp issues the chunk's bulk copies (14 rows), lane i -> row i
+        // one warp issues the chunk's bulk copies (2 images x 7 rows), lane i -> row i
         const int buf = chunk & 1;
         const int y0 = py0 + chunk * S_R;
         const int nr = min(S_R, in_end - y0);
@@ -221,118 +161,215 @@ k_ssim_strip(int H, int W, int seg_rows, const uint8_t* __restrict__ a_img, size
             }
         }
     };
-    if (tid < 32) issue(0);
+    if (tid < 32) {
+        issue(0);
+        if (n_chunks > 1) issue(1);
+    }
 
-    // pass-2 state: thread = (column, channel)
+    // pass-2 role: thread = (window column, channel pair)
     const int col = tid & (S_OW - 1);
-    const int ch = tid >> 7;
-    float4 ring[S_R];
+    const int pair = tid >> 6;                      // warps 0,1: (R,G); warps 2,3: (B,Y)
+    const int hidx = pair * S_OW + col;
+    HSum ring[S_R];
 #pragma unroll
-    for (int i = 0; i < S_R; ++i) ring[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    double ssim_total = 0.0;
-    const bool col_ok = col < nwin_x;
-    // pass-1 state: warps 0..7, two warps per channel, 56 tasks per channel
-    const int p1_ch = tid >> 6;
-    const int p1_task = tid & 63;
-    const bool p1_active = tid < 256 && p1_task < S_R * S_NSEG;
-    const int p1_row = p1_task / S_NSEG, p1_seg = p1_task % S_NSEG;
-    double sse_total = 0.0;
+    for (int i = 0; i < S_R; ++i) ring[i].sx = ring[i].sy = ring[i].sq = ring[i].sc = f2(0.f);
+    HSum acc;
+    acc.sx = acc.sy = acc.sq = acc.sc = f2(0.f);
+    double ssim_a = 0.0, ssim_b = 0.0;
+    const bool col_ok = want_ssim && col < nwin_x;
+    // pass-1 role: thread = (row, segment, pair), 112 of the 128 threads
+    // (row fastest: the padded row pitches then spread a quarter-warp over the banks)
+    const int p1_row = tid % S_R;
+    const int p1_seg = (tid / S_R) & (S_NSEG - 1);
+    const int p1_pair = tid / (S_NSEG * S_R);
+    const bool p1_active = tid < S_NSEG * S_R * 2;
+    const int p1_c0 = S_SEG * p1_seg;
+    double sse_a = 0.0, sse_b = 0.0;                // squared error of the pair's channels
+
+    // prep: bytes -> centred fp32, pairs (R,G) and (B,Y) interleaved; task = 4 pixels
+    auto prep = [&](int chunk) {
+        const int buf = chunk & 1;
+        const int nrp = min(S_R, in_end - (py0 + chunk * S_R));
+        mbar_wait(&sm.bar[buf], (uint32_t)((chunk >> 1) & 1));
+        for (int task = tid; task < 2 * S_R * (S_LW / 4); task += S_NT) {
+            const int img = task / (S_R * (S_LW / 4));
+            const int rem = task % (S_R * (S_LW / 4));
+            const int r = rem / (S_LW / 4), g4 = rem % (S_LW / 4);
+            if (r < nrp) {
+                const uint32_t* w = reinterpret_cast<const uint32_t*>(&sm.raw[buf][img][r][12 * g4]);
+                const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+                const float R0 = byte_centered<0>(w0), G0 = byte_centered<1>(w0), B0 = byte_centered<2>(w0);
+                const float R1 = byte_centered<3>(w0), G1 = byte_centered<0>(w1), B1 = byte_centered<1>(w1);
+                const float R2 = byte_centered<2>(w1), G2 = byte_centered<3>(w1), B2 = byte_centered<0>(w2);
+                const float R3 = byte_centered<1>(w2), G3 = byte_centered<2>(w2), B3 = byte_centered<3>(w2);
+                const float Y0 = fmaf(0.299f, R0, fmaf(0.587f, G0, 0.114f * B0));
+                const float Y1 = fmaf(0.299f, R1, fmaf(0.587f, G1, 0.114f * B1));
+                const float Y2 = fmaf(0.299f, R2, fmaf(0.587f, G2, 0.114f * B2));
+                const float Y3 = fmaf(0.299f, R3, fmaf(0.587f, G3, 0.114f * B3));
+                float4* d0 = reinterpret_cast<float4*>(&sm.fpl[img][0][r][4 * g4]);
+                float4* d1 = reinterpret_cast<float4*>(&sm.fpl[img][1][r][4 * g4]);
+                d0[0] = make_float4(R0, G0, R1, G1);
+                d0[1] = make_float4(R2, G2, R3, G3);
+                d1[0] = make_float4(B0, Y0, B1, Y1);
+                d1[1] = make_float4(B2, Y2, B3, Y3);
+            }
+        }
+    };
+    prep(0);
+    __syncthreads();
+
+    // one vertical step of pass 2: take row r's horizontal sums, emit (optionally), drop the
+    // row that leaves the 7-row window
+#define JDS_P2_STEP(r, EMIT)                                                             \
+    {                                                                                    \
+        const float4 h0 = sm.hxy[r][hidx], h1 = sm.hqc[r][hidx];                         \
+        HSum h;                                                                          \
+        h.sx = f2(h0.x, h0.y); h.sy = f2(h0.z, h0.w);                                    \
+        h.sq = f2(h1.x, h1.y); h.sc = f2(h1.z, h1.w);                                    \
+        ring[r] = h;                                                                     \
+        acc.sx = __fadd2_rn(acc.sx, h.sx);                                               \
+        acc.sy = __fadd2_rn(acc.sy, h.sy);                                               \
+        acc.sq = __fadd2_rn(acc.sq, h.sq);                                               \
+        acc.sc = __fadd2_rn(acc.sc, h.sc);                                               \
+        if (EMIT) ssum = __fadd2_rn(ssum, ssim_window_half2(acc.sx, acc.sy, acc.sq, acc.sc)); \
+        const HSum o = ring[(r + 1) % S_R];                                              \
+        acc.sx = sub2(acc.sx, o.sx);                                                     \
+        acc.sy = sub2(acc.sy, o.sy);                                                     \
+        acc.sq = sub2(acc.sq, o.sq);                                                     \
+        acc.sc = sub2(acc.sc, o.sc);                                                     \
+    }
 
     for (int c = 0; c < n_chunks; ++c) {
-        const int buf = c & 1;
-        if (tid < 32 && c + 1 < n_chunks) issue(c + 1);
-        mbar_wait(&sm.bar[buf], (uint32_t)((c >> 1) & 1));
+        // raw[c & 1] (chunk c) was consumed by prep(c) before the last barrier: refill it
+        if (tid < 32 && c + 2 < n_chunks) issue(c + 2);
         const int y0 = py0 + c * S_R;
         const int nr = min(S_R, in_end - y0);
 
-        // ---- centred Y of both images: one task = 4 pixels -------------------------
-        if (tid < 2 * S_R * (S_LW / 4)) {
-            const int img = tid / (S_R * (S_LW / 4));
-            const int rem = tid % (S_R * (S_LW / 4));
-            const int r = rem / (S_LW / 4), g4 = rem % (S_LW / 4);
-            if (r < nr) {
-                const uint32_t* w = reinterpret_cast<const uint32_t*>(&sm.raw[buf][img][r][12 * g4]);
-                const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
-                float4 yv;
-                yv.x = fmaf(0.299f, byte_centered<0>(w0), fmaf(0.587f, byte_centered<1>(w0), 0.114f * byte_centered<2>(w0)));
-                yv.y = fmaf(0.299f, byte_centered<3>(w0), fmaf(0.587f, byte_centered<0>(w1), 0.114f * byte_centered<1>(w1)));
-                yv.z = fmaf(0.299f, byte_centered<2>(w1), fmaf(0.587f, byte_centered<3>(w1), 0.114f * byte_centered<0>(w2)));
-                yv.w = fmaf(0.299f, byte_centered<1>(w2), fmaf(0.587f, byte_centered<2>(w2), 0.114f * byte_centered<3>(w2)));
-                *reinterpret_cast<float4*>(&sm.ybuf[img][r][4 * g4]) = yv;
-            }
-        }
-        __syncthreads();
-
-        // ---- pass 1: horizontal window sums --------------------------------------
+        // ---- pass 1: horizontal 7-tap sums of x, y, x^2+y^2, xy (sliding window) ---------
         if (p1_active && p1_row < nr) {
-            // squared error only for rows this CTA owns (not the 6-row overlap)
-            float sse = 0.f;
-            const bool own_row = (y0 + p1_row) < py1;
-            const int vpx = own_row ? own_px : 0;
-            switch (p1_ch) {
-                case 0: pass1_task<0>(sm, buf, p1_row, p1_seg, vpx, sse); break;
-                case 1: pass1_task<1>(sm, buf, p1_row, p1_seg, vpx, sse); break;
-                case 2: pass1_task<2>(sm, buf, p1_row, p1_seg, vpx, sse); break;
-                default: pass1_task<3>(sm, buf, p1_row, p1_seg, vpx, sse); break;
+            const float4* qa = reinterpret_cast<const float4*>(&sm.fpl[0][p1_pair][p1_row][p1_c0]);
+            const float4* qb = reinterpret_cast<const float4*>(&sm.fpl[1][p1_pair][p1_row][p1_c0]);
+            float2 xs[S_SEG + 6], ys[S_SEG + 6];
+#pragma unroll
+            for (int i2 = 0; i2 < (S_SEG + 6) / 2; ++i2) {
+                const float4 a = qa[i2], b = qb[i2];
+                xs[2 * i2] = f2(a.x, a.y); xs[2 * i2 + 1] = f2(a.z, a.w);
+                ys[2 * i2] = f2(b.x, b.y); ys[2 * i2 + 1] = f2(b.z, b.w);
             }
-            sse_total += (double)sse;
+            // squared error of the 8 pixels this task owns (exact for the integer channels)
+            if ((y0 + p1_row) < py1) {
+                float2 sse = f2(0.f);
+                if (p1_c0 + S_SEG <= own_px) {
+#pragma unroll
+                    for (int i = 0; i < S_SEG; ++i) {
+                        const float2 d = sub2(xs[i], ys[i]);
+                        sse = __ffma2_rn(d, d, sse);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < S_SEG; ++i)
+                        if (p1_c0 + i < own_px) {
+                            const float2 d = sub2(xs[i], ys[i]);
+                            sse = __ffma2_rn(d, d, sse);
+                        }
+                }
+                sse_a += (double)sse.x;
+                sse_b += (double)sse.y;
+            }
+            float2 wx = f2(0.f), wy = f2(0.f), wq = f2(0.f), wc = f2(0.f);
+#pragma unroll
+            for (int i = 0; i < S_SEG + 6; ++i) {
+                wx = __fadd2_rn(wx, xs[i]);
+                wy = __fadd2_rn(wy, ys[i]);
+                wq = __ffma2_rn(xs[i], xs[i], __ffma2_rn(ys[i], ys[i], wq));
+                wc = __ffma2_rn(xs[i], ys[i], wc);
+                if (i >= 6) {
+                    const int j = i - 6;
+                    sm.hxy[p1_row][p1_pair * S_OW + p1_c0 + j] = make_float4(wx.x, wx.y, wy.x, wy.y);
+                    sm.hqc[p1_row][p1_pair * S_OW + p1_c0 + j] = make_float4(wq.x, wq.y, wc.x, wc.y);
+                    const float2 ox = xs[j], oy = ys[j];
+                    const float2 nox = sub2(f2(0.f), ox), noy = sub2(f2(0.f), oy);
+                    wx = __fadd2_rn(wx, nox);
+                    wy = __fadd2_rn(wy, noy);
+                    wq = __ffma2_rn(nox, ox, __ffma2_rn(noy, oy, wq));
+                    wc = __ffma2_rn(nox, oy, wc);
+                }
+            }
         }
         __syncthreads();
 
-        // ---- pass 2: vertical sliding sum + SSIM ------------------------------------
-        if (want_ssim) {
-            if (ch == 3) {
-                // rebuild the fp32 accumulators from the ring: no drift down the strip
-                acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        // ---- pass 2: vertical sliding sum + SSIM; then prep of the next chunk -------------
+        {
+            if (pair == 1) {
+                // rebuild the accumulators from the ring: the Y sums are not integers and
+                // must not drift down the strip (warp-uniform branch)
+                acc.sx = acc.sy = acc.sq = acc.sc = f2(0.f);
 #pragma unroll
                 for (int i = 1; i < S_R; ++i) {
-                    acc.x += ring[i].x; acc.y += ring[i].y; acc.z += ring[i].z; acc.w += ring[i].w;
+                    acc.sx = __fadd2_rn(acc.sx, ring[i].sx);
+                    acc.sy = __fadd2_rn(acc.sy, ring[i].sy);
+                    acc.sq = __fadd2_rn(acc.sq, ring[i].sq);
+                    acc.sc = __fadd2_rn(acc.sc, ring[i].sc);
                 }
             }
-            float ssum = 0.f;
+            // rows r of this chunk in [e0, e1) complete a window row that this CTA owns
+            const int e0 = max(0, 6 - c * S_R);
+            const int e1 = want_ssim ? min(nr, py1 + 6 - y0) : 0;
+            float2 ssum = f2(0.f);
+            if (nr == S_R && e0 == 0 && e1 == S_R) {
+                // steady state: all seven rows emit; straight-line code, no branches
+                JDS_P2_STEP(0, true) JDS_P2_STEP(1, true) JDS_P2_STEP(2, true) JDS_P2_STEP(3, true)
+                JDS_P2_STEP(4, true) JDS_P2_STEP(5, true) JDS_P2_STEP(6, true)
+            } else {
 #pragma unroll
-            for (int r = 0; r < S_R; ++r) {
-                if (r < nr) {
-                    const float4 h = sm.hbuf[r][ch][hswz(col)];
-                    ring[r] = h;
-                    acc.x += h.x; acc.y += h.y; acc.z += h.z; acc.w += h.w;
-                    const int step = c * S_R + r;            // rows consumed so far - 1
-                    const int wy = py0 + step - 6;           // window row that just completed
-                    if (step >= 6 && wy < py1 && col_ok)
-                        ssum += ssim_window(acc.x, acc.y, acc.z, acc.w);
-                    const float4 o = ring[(r + 1) % S_R];
-                    acc.x -= o.x; acc.y -= o.y; acc.z -= o.z; acc.w -= o.w;
-                }
+                for (int r = 0; r < S_R; ++r)
+                    if (r < nr) JDS_P2_STEP(r, (r >= e0 && r < e1))
             }
-            ssim_total += (double)ssum;
+            if (col_ok) {
+                ssim_a += (double)ssum.x;
+                ssim_b += (double)ssum.y;
+            }
         }
+        if (c + 1 < n_chunks) prep(c + 1);
         __syncthreads();
     }
+#undef JDS_P2_STEP
 
     // ---- reductions ---------------------------------------------------------------
     const int lane = tid & 31, warp = tid >> 5;
+    // pass-1 pair varies inside a warp (56 tasks per pair): reduce per pair
+    double e[4];
+    e[0] = (p1_active && p1_pair == 0) ? sse_a : 0.0;
+    e[1] = (p1_active && p1_pair == 0) ? sse_b : 0.0;
+    e[2] = (p1_active && p1_pair == 1) ? sse_a : 0.0;
+    e[3] = (p1_active && p1_pair == 1) ? sse_b : 0.0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        ssim_total += __shfl_down_sync(0xffffffffu, ssim_total, o);
-        sse_total += __shfl_down_sync(0xffffffffu, sse_total, o);
+        ssim_a += __shfl_down_sync(0xffffffffu, ssim_a, o);
+        ssim_b += __shfl_down_sync(0xffffffffu, ssim_b, o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) e[k] += __shfl_down_sync(0xffffffffu, e[k], o);
     }
     if (lane == 0) {
-        sm.red_ssim[0][warp] = ssim_total;     // warp -> channel = warp / 4
-        sm.red_ssey[warp] = sse_total;         // pass-1 warps: channel = warp / 2 (warps 0..7)
+        sm.red_ssim[warp][0] = ssim_a;              // pass-2 pair = warp / 2
+        sm.red_ssim[warp][1] = ssim_b;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) sm.red_sse[warp][k] = e[k];
     }
     __syncthreads();
-    if (tid < 4) {
-        double s = 0.0;
-        for (int w = 0; w < 4; ++w) s += sm.red_ssim[0][tid * 4 + w];
-        if (want_ssim) atomicAdd(&metrics[unit].ssim_sum[tid], s);
+    if (tid < 4 && want_ssim) {
+        // channel tid: pair = tid / 2 (warps 2*pair, 2*pair+1), half = tid % 2
+        const int pr = tid >> 1, hf = tid & 1;
+        atomicAdd(&metrics[unit].ssim_sum[tid],
+                  2.0 * (sm.red_ssim[2 * pr][hf] + sm.red_ssim[2 * pr + 1][hf]));
     }
     if (tid == 32 && want_sse) {
+        double t[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int w = 0; w < 4; ++w)
+            for (int k = 0; k < 4; ++k) t[k] += sm.red_sse[w][k];
         // integer channels: every partial is an exact integer below 2^53
-        double rgb = 0.0;
-        for (int w = 0; w < 6; ++w) rgb += sm.red_ssey[w];
-        atomicAdd(&metrics[unit].sse_rgb, (unsigned long long)(rgb + 0.5));
-        atomicAdd(&metrics[unit].sse_y, sm.red_ssey[6] + sm.red_ssey[7]);
+        atomicAdd(&metrics[unit].sse_rgb, (unsigned long long)(t[0] + t[1] + t[2] + 0.5));
+        atomicAdd(&metrics[unit].sse_y, t[3]);
     }
 }
 
@@ -355,9 +392,9 @@ cudaError_t launch_ssim_strip(int H, int W, const uint8_t* a, size_t a_stride, c
         if (e != cudaSuccess) return e;
     }
     const int strips = (W + S_OW - 1) / S_OW;
-    // vertical segments: enough CTAs to fill the machine (~2 per SM x 2 waves), but at
+    // vertical segments: enough CTAs to fill the machine (3 per SM x ~3 waves), but at
     // least 126 rows each so the 6-row overlap stays below 5 %
-    int want_ctas = sm_count * 4;
+    int want_ctas = sm_count * 12;
     int segs = (want_ctas + strips * units - 1) / (strips * units);
     if (segs < 1) segs = 1;
     int seg_rows = (H + segs - 1) / segs;
