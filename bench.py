@@ -205,6 +205,8 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
+    # one launch per step: let the whole batch fit the scratch budget of the context
+    os.environ.setdefault("JDS_SCRATCH_MB", "8192")
     import jpeg_dsp_studio_b200 as J
     eng = J.Engine(local)
     stream = torch.cuda.current_stream(dev)

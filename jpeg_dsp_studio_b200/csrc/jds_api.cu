@@ -54,7 +54,12 @@ struct jds_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    cudaEvent_t evs[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    static constexpr int kTimedChunks = 32;             // chunks per call with per-stage events
+    cudaEvent_t evs[5 * kTimedChunks] = {};
+    cudaStream_t s_in = nullptr, s_out = nullptr;      // copy streams of the pipelined host path
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr},
+                ev_out[2] = {nullptr, nullptr};
+    int plan_chunk = 1;
     double stage_ms[4] = {0, 0, 0, 0};   // forward, codec, inverse, ssim (accumulated)
     uint64_t stage_launches[4] = {0, 0, 0, 0};
     DevBuf planes, in, recon, coeffs, errs, metrics, tables, selected;
@@ -125,7 +130,14 @@ extern "C" int jds_ctx_create(int device, jds_ctx** out) {
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
-    for (int i = 0; i < 5 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->evs[i]);
+    for (int i = 0; i < 5 * jds_ctx::kTimedChunks && e == cudaSuccess; ++i) e = cudaEventCreate(&c->evs[i]);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_comp[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming);
+    }
     if (e != cudaSuccess) {
         delete c;
         return fail(JDS_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(e));
@@ -155,8 +167,15 @@ extern "C" int jds_ctx_destroy(jds_ctx* c) {
     if (c->h_selected) cudaFreeHost(c->h_selected);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
-    for (int i = 0; i < 5; ++i)
+    for (int i = 0; i < 5 * jds_ctx::kTimedChunks; ++i)
         if (c->evs[i]) cudaEventDestroy(c->evs[i]);
+    for (int i = 0; i < 2; ++i) {
+        if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
+        if (c->ev_comp[i]) cudaEventDestroy(c->ev_comp[i]);
+        if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
+    }
+    if (c->s_in) cudaStreamDestroy(c->s_in);
+    if (c->s_out) cudaStreamDestroy(c->s_out);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return JDS_OK;
@@ -270,6 +289,108 @@ struct UnitJob {
     jds_metrics* metrics;
 };
 
+// Kernels of one chunk of `n` units on the compute stream.  Returns which stages ran.
+struct ChunkPtrs {
+    const uint8_t* d_rgb;
+    size_t rgb_stride;
+    uint8_t* d_recon;
+    int16_t* d_coeffs;
+    double* d_ey;
+    double* d_ergb;
+    const QTables* d_tables;
+    DevMetrics* d_metrics;
+    bool first_chunk;
+};
+
+static int launch_chunk(jds_ctx* c, const UnitJob& J, const ChunkPtrs& P, int n,
+                        cudaEvent_t* evs /* 5 events or NULL */, bool ran[4]) {
+    const bool timed = evs != nullptr;
+    const Geom& g = J.g;
+    const jds_params* p = J.p;
+    const bool exact = p->precision == JDS_EXACT;
+    const size_t esz = exact ? sizeof(double) : sizeof(float);
+    const size_t frame_bytes = (size_t)g.H * g.W * 3;
+    const size_t planes_elems = (size_t)(g.plane_y + 2 * g.plane_c);
+    const size_t ncoef = 64ull * (size_t)(g.nblk_y + 2 * g.nblk_c);
+    const bool want_hist = (p->outputs & JDS_OUT_HIST) != 0;
+    const bool want_ssim = (p->outputs & JDS_OUT_SSIM) != 0;
+    cudaStream_t s = c->stream;
+    const int tstride = J.qualities ? 1 : 0;
+    const int fwd_units = J.shared_input ? 1 : c->plan_chunk;
+    char* planes = (char*)c->planes.p;
+    void* fwd = planes;
+    void* rec = planes + planes_elems * esz * (size_t)fwd_units;
+    const size_t fwd_stride = J.shared_input ? 0 : planes_elems;
+    const size_t rec_stride = planes_elems;
+
+    if (timed) JDS_CUDA(cudaEventRecord(evs[0], s));
+    // fast mode on block-aligned frames runs the fused kernels (jds_fused.cu); exact
+    // mode, prefiltered / ragged frames and the GUI-only outputs (histogram, error
+    // maps) run the staged kernels (jds_kernels.cu)
+    const bool fused = !exact && !c->no_fused && !want_hist && !P.d_ey && !P.d_ergb &&
+                       fused_supported(g, p->prefilter, P.d_rgb, P.rgb_stride, P.d_recon, frame_bytes) &&
+                       ssim_strip_supported(g.H, g.W, P.d_rgb, P.rgb_stride, P.d_recon, frame_bytes);
+    if (fused) {
+        float* cpl = (float*)c->planes.p;
+        const size_t cpl_stride = fused_chroma_plane_floats(g);
+        ran[0] = g.sub != 0;
+        if (ran[0]) {
+            JDS_CUDA(launch_fused_chroma(g, P.d_rgb, P.rgb_stride, cpl, cpl_stride, P.d_tables,
+                                         tstride, P.d_coeffs, ncoef, P.d_metrics, n, s));
+            c->launches++;
+        }
+        if (timed) JDS_CUDA(cudaEventRecord(evs[1], s));
+        JDS_CUDA(launch_fused_luma(g, P.d_rgb, P.rgb_stride, cpl, cpl_stride, P.d_tables, tstride,
+                                   P.d_coeffs, ncoef, P.d_recon, frame_bytes, P.d_metrics, n, s));
+        c->launches++;
+        if (timed) {
+            JDS_CUDA(cudaEventRecord(evs[2], s));
+            JDS_CUDA(cudaEventRecord(evs[3], s));
+        }
+        ran[1] = true;
+        ran[2] = false;
+        ran[3] = true;      // squared errors always come from the strip kernel here
+        JDS_CUDA(launch_ssim_strip(g.H, g.W, P.d_rgb, P.rgb_stride, P.d_recon, frame_bytes,
+                                   P.d_metrics, n, want_ssim, true, c->sm_count, s));
+        c->launches++;
+    } else {
+        ran[0] = !J.shared_input || P.first_chunk;
+        ran[1] = ran[2] = true;
+        if (ran[0]) {
+            launch_forward(exact, g, p->prefilter, P.d_rgb, P.rgb_stride, fwd, fwd_stride,
+                           J.shared_input ? 1 : n, s);
+            c->launches++;
+        }
+        if (timed) JDS_CUDA(cudaEventRecord(evs[1], s));
+        launch_codec(exact, g, fwd, fwd_stride, rec, rec_stride, P.d_tables, tstride, P.d_coeffs,
+                     ncoef, want_hist, P.d_metrics, n, s);
+        if (timed) JDS_CUDA(cudaEventRecord(evs[2], s));
+        launch_inverse(exact, g, P.d_rgb, P.rgb_stride, fwd, fwd_stride, rec, rec_stride, P.d_recon,
+                       frame_bytes, P.d_ey, P.d_ergb, P.d_metrics, n, s);
+        if (timed) JDS_CUDA(cudaEventRecord(evs[3], s));
+        c->launches += 2;
+        ran[3] = want_ssim && g.H >= 7 && g.W >= 7;
+        if (ran[3]) {
+            if (!c->legacy_ssim &&
+                ssim_strip_supported(g.H, g.W, P.d_rgb, P.rgb_stride, P.d_recon, frame_bytes)) {
+                JDS_CUDA(launch_ssim_strip(g.H, g.W, P.d_rgb, P.rgb_stride, P.d_recon, frame_bytes,
+                                           P.d_metrics, n, true, false, c->sm_count, s));
+            } else {
+                launch_ssim(exact, g.H, g.W, P.d_rgb, P.rgb_stride, P.d_recon, frame_bytes,
+                            P.d_metrics, n, s);
+            }
+            c->launches++;
+        }
+    }
+    if (timed) JDS_CUDA(cudaEventRecord(evs[4], s));
+    JDS_CUDA(cudaGetLastError());
+    return JDS_OK;
+}
+
+// The whole job: chunks of units flow through three streams - host->device copies,
+// kernels, device->host copies - with double-buffered staging, so that with host
+// buffers the PCIe transfers of neighbouring chunks overlap the kernels and each other
+// (full duplex).  With device buffers the copy streams stay idle.
 static int run_job(jds_ctx* c, const UnitJob& J) {
     const Geom& g = J.g;
     const jds_params* p = J.p;
@@ -279,197 +400,179 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
     const size_t planes_elems = (size_t)(g.plane_y + 2 * g.plane_c);
     const size_t ncoef = 64ull * (size_t)(g.nblk_y + 2 * g.nblk_c);
     const bool want_coeffs = (p->outputs & JDS_OUT_COEFFS) && J.coeffs;
-    const bool want_hist = (p->outputs & JDS_OUT_HIST) != 0;
     const bool want_ssim = (p->outputs & JDS_OUT_SSIM) != 0;
     const bool want_recon = (p->outputs & JDS_OUT_RECON) && J.recon;
     const bool want_ey = (p->outputs & JDS_OUT_ERR_Y) && J.err_y;
     const bool want_ergb = (p->outputs & JDS_OUT_ERR_RGB) && J.err_rgb;
     if ((want_ey || want_ergb) && J.units != 1)
         return fail(JDS_ERR_INVALID, "error maps are single-frame outputs");
+    const bool in_host = J.rgb_loc == JDS_HOST;
+    const bool out_host = J.out_loc == JDS_HOST;
 
     JDS_CUDA(cudaSetDevice(c->device));
 
-    // units per chunk from the scratch budget
-    const size_t per_unit = planes_elems * esz * (J.shared_input ? 1 : 2) + frame_bytes +
+    // units per chunk: bounded by the scratch budget; with host buffers also small enough
+    // that there are several chunks to overlap
+    const size_t per_unit = planes_elems * esz * (J.shared_input ? 1 : 2) + frame_bytes * 2 +
                             (want_coeffs ? ncoef * 2 : 0);
     int chunk = (int)(c->scratch_budget / (per_unit ? per_unit : 1));
     if (chunk < 1) chunk = 1;
     if (chunk > J.units) chunk = J.units;
     if (chunk > 65535) chunk = 65535;
+    const bool pipelined = (in_host || (out_host && (want_recon || want_coeffs))) && J.units > 1;
+    if (pipelined) {
+        // many small chunks hide the pipeline fill / drain (one copy each way), but keep
+        // every copy >= 8 MB so PCIe stays efficient
+        int target = (J.units + 15) / 16;
+        const size_t floor_bytes = (size_t)8 << 20;
+        const int min_units = (int)((floor_bytes + frame_bytes - 1) / frame_bytes);
+        if (target < min_units) target = min_units;
+        if (target < 1) target = 1;
+        if (chunk > target) chunk = target;
+    }
+    c->plan_chunk = chunk;
+    const int nbuf = pipelined ? 2 : 1;
 
     int rc;
     const int fwd_units = J.shared_input ? 1 : chunk;
     if ((rc = ensure(c, c->planes, planes_elems * esz * (size_t)(fwd_units + chunk)))) return rc;
-    if ((rc = ensure(c, c->metrics, sizeof(DevMetrics) * (size_t)chunk))) return rc;
-    if ((rc = ensure(c, c->tables, sizeof(QTables) * (size_t)chunk))) return rc;
-    if ((rc = ensure_pinned(&c->h_metrics, &c->h_metrics_bytes, sizeof(DevMetrics) * (size_t)chunk)))
+    if ((rc = ensure(c, c->metrics, sizeof(DevMetrics) * (size_t)J.units))) return rc;
+    const int n_tables_total = J.qualities ? J.units : 1;
+    if ((rc = ensure(c, c->tables, sizeof(QTables) * (size_t)n_tables_total))) return rc;
+    if ((rc = ensure_pinned(&c->h_metrics, &c->h_metrics_bytes, sizeof(DevMetrics) * (size_t)J.units)))
         return rc;
-    if ((rc = ensure_pinned(&c->h_tables, &c->h_tables_bytes, sizeof(QTables) * (size_t)chunk)))
+    if ((rc = ensure_pinned(&c->h_tables, &c->h_tables_bytes, sizeof(QTables) * (size_t)n_tables_total)))
         return rc;
-    const bool in_host = J.rgb_loc == JDS_HOST;
-    const bool out_host = J.out_loc == JDS_HOST;
-    if (in_host && (rc = ensure(c, c->in, frame_bytes * (size_t)fwd_units))) return rc;
-    if ((!want_recon || out_host) && (rc = ensure(c, c->recon, frame_bytes * (size_t)chunk)))
-        return rc;
-    if (want_coeffs && out_host && (rc = ensure(c, c->coeffs, ncoef * 2 * (size_t)chunk))) return rc;
-    if ((want_ey || want_ergb) && out_host &&
-        (rc = ensure(c, c->errs, (size_t)g.H * g.W * 8 * 2)))
+    const size_t in_slot = frame_bytes * (size_t)fwd_units;
+    const size_t recon_slot = frame_bytes * (size_t)chunk;
+    const size_t coeff_slot = ncoef * 2 * (size_t)chunk;
+    if (in_host && (rc = ensure(c, c->in, in_slot * (J.shared_input ? 1 : nbuf)))) return rc;
+    if ((!want_recon || out_host) && (rc = ensure(c, c->recon, recon_slot * nbuf))) return rc;
+    if (want_coeffs && out_host && (rc = ensure(c, c->coeffs, coeff_slot * nbuf))) return rc;
+    if ((want_ey || want_ergb) && out_host && (rc = ensure(c, c->errs, (size_t)g.H * g.W * 8 * 2)))
         return rc;
 
-    char* planes = (char*)c->planes.p;
-    void* fwd = planes;
-    void* rec = planes + planes_elems * esz * (size_t)fwd_units;
-    const size_t fwd_stride = J.shared_input ? 0 : planes_elems;
-    const size_t rec_stride = planes_elems;
     DevMetrics* d_metrics = (DevMetrics*)c->metrics.p;
     QTables* d_tables = (QTables*)c->tables.p;
     QTables* h_tables = (QTables*)c->h_tables;
     DevMetrics* h_metrics = (DevMetrics*)c->h_metrics;
     cudaStream_t s = c->stream;
+    cudaStream_t s_in = pipelined ? c->s_in : s;
+    cudaStream_t s_out = pipelined ? c->s_out : s;
 
-    for (int u0 = 0; u0 < J.units; u0 += chunk) {
+    // quantiser tables of every unit, metric accumulators
+    for (int i = 0; i < n_tables_total; ++i)
+        fill_tables(J.qualities ? J.qualities[i] : p->quality, &h_tables[i]);
+    JDS_CUDA(cudaMemcpyAsync(d_tables, h_tables, sizeof(QTables) * n_tables_total,
+                             cudaMemcpyHostToDevice, s));
+    JDS_CUDA(cudaMemsetAsync(d_metrics, 0, sizeof(DevMetrics) * J.units, s));
+    if (J.shared_input && in_host)
+        JDS_CUDA(cudaMemcpyAsync(c->in.p, J.rgb, frame_bytes, cudaMemcpyHostToDevice, s));
+    JDS_CUDA(cudaEventRecord(c->ev0, s));
+
+    int chunk_idx = 0;
+    bool timed_ran[jds_ctx::kTimedChunks][4];
+    int n_timed = 0;
+    for (int u0 = 0; u0 < J.units; u0 += chunk, ++chunk_idx) {
         const int n = (J.units - u0 < chunk) ? (J.units - u0) : chunk;
-        // --- quantiser tables ---
-        const int n_tables = J.qualities ? n : 1;
-        for (int i = 0; i < n_tables; ++i)
-            fill_tables(J.qualities ? J.qualities[u0 + i] : p->quality, &h_tables[i]);
-        JDS_CUDA(cudaMemcpyAsync(d_tables, h_tables, sizeof(QTables) * n_tables,
-                                 cudaMemcpyHostToDevice, s));
+        const int b = chunk_idx % nbuf;
+        ChunkPtrs P;
+        P.first_chunk = (u0 == 0);
+        P.d_tables = d_tables + (J.qualities ? u0 : 0);
+        P.d_metrics = d_metrics + u0;
         // --- inputs ---
-        const uint8_t* d_rgb;
-        size_t rgb_stride = J.shared_input ? 0 : frame_bytes;
-        if (in_host) {
-            if (!J.shared_input || u0 == 0) {
-                const size_t nin = J.shared_input ? 1 : (size_t)n;
-                const uint8_t* src = J.rgb + (J.shared_input ? 0 : (size_t)u0 * frame_bytes);
-                JDS_CUDA(cudaMemcpyAsync(c->in.p, src, frame_bytes * nin,
-                                         cudaMemcpyHostToDevice, s));
+        P.rgb_stride = J.shared_input ? 0 : frame_bytes;
+        if (J.shared_input) {
+            P.d_rgb = in_host ? (const uint8_t*)c->in.p : J.rgb;
+        } else if (in_host) {
+            uint8_t* slot = (uint8_t*)c->in.p + (size_t)b * in_slot;
+            if (pipelined && chunk_idx >= nbuf)      // slot last read by the kernels of chunk-2
+                JDS_CUDA(cudaStreamWaitEvent(s_in, c->ev_comp[b], 0));
+            JDS_CUDA(cudaMemcpyAsync(slot, J.rgb + (size_t)u0 * frame_bytes, frame_bytes * (size_t)n,
+                                     cudaMemcpyHostToDevice, s_in));
+            if (pipelined) {
+                JDS_CUDA(cudaEventRecord(c->ev_in[b], s_in));
+                JDS_CUDA(cudaStreamWaitEvent(s, c->ev_in[b], 0));
             }
-            d_rgb = (const uint8_t*)c->in.p;
+            P.d_rgb = slot;
         } else {
-            d_rgb = J.rgb + (J.shared_input ? 0 : (size_t)u0 * frame_bytes);
+            P.d_rgb = J.rgb + (size_t)u0 * frame_bytes;
         }
         // --- outputs ---
-        uint8_t* d_recon = (want_recon && !out_host) ? J.recon + (size_t)u0 * frame_bytes
-                                                     : (uint8_t*)c->recon.p;
-        int16_t* d_coeffs = nullptr;
+        P.d_recon = (want_recon && !out_host) ? J.recon + (size_t)u0 * frame_bytes
+                                              : (uint8_t*)c->recon.p + (size_t)b * recon_slot;
+        P.d_coeffs = nullptr;
         if (want_coeffs)
-            d_coeffs = out_host ? (int16_t*)c->coeffs.p : J.coeffs + (size_t)u0 * ncoef;
-        double* d_ey = nullptr;
-        double* d_ergb = nullptr;
-        if (want_ey) d_ey = out_host ? (double*)c->errs.p : J.err_y;
-        if (want_ergb) d_ergb = out_host ? (double*)c->errs.p + (size_t)g.H * g.W : J.err_rgb;
+            P.d_coeffs = out_host ? (int16_t*)((char*)c->coeffs.p + (size_t)b * coeff_slot)
+                                  : J.coeffs + (size_t)u0 * ncoef;
+        P.d_ey = want_ey ? (out_host ? (double*)c->errs.p : J.err_y) : nullptr;
+        P.d_ergb = want_ergb ? (out_host ? (double*)c->errs.p + (size_t)g.H * g.W : J.err_rgb) : nullptr;
+        if (pipelined && chunk_idx >= nbuf)          // staging slot still being copied out?
+            JDS_CUDA(cudaStreamWaitEvent(s, c->ev_out[b], 0));
 
-        JDS_CUDA(cudaMemsetAsync(d_metrics, 0, sizeof(DevMetrics) * n, s));
-        JDS_CUDA(cudaEventRecord(c->ev0, s));
-        JDS_CUDA(cudaEventRecord(c->evs[0], s));
-        // fast mode on block-aligned frames runs the fused kernels (jds_fused.cu); exact
-        // mode, prefiltered / ragged frames and the GUI-only outputs (histogram, error
-        // maps) run the staged kernels (jds_kernels.cu)
-        const bool fused = !exact && !c->no_fused && !want_hist && !want_ey && !want_ergb &&
-                           fused_supported(g, p->prefilter, d_rgb, rgb_stride, d_recon, frame_bytes) &&
-                           ssim_strip_supported(g.H, g.W, d_rgb, rgb_stride, d_recon, frame_bytes);
-        bool do_fwd, do_inv, do_ssim;
-        if (fused) {
-            float* cpl = (float*)c->planes.p;
-            const size_t cpl_stride = fused_chroma_plane_floats(g);
-            do_fwd = g.sub != 0;
-            if (do_fwd) {
-                JDS_CUDA(launch_fused_chroma(g, d_rgb, rgb_stride, cpl, cpl_stride, d_tables,
-                                             J.qualities ? 1 : 0, d_coeffs, ncoef, d_metrics, n, s));
-                c->launches++;
-            }
-            JDS_CUDA(cudaEventRecord(c->evs[1], s));
-            JDS_CUDA(launch_fused_luma(g, d_rgb, rgb_stride, cpl, cpl_stride, d_tables,
-                                       J.qualities ? 1 : 0, d_coeffs, ncoef, d_recon, frame_bytes,
-                                       d_metrics, n, s));
-            c->launches++;
-            JDS_CUDA(cudaEventRecord(c->evs[2], s));
-            JDS_CUDA(cudaEventRecord(c->evs[3], s));
-            do_inv = false;
-            do_ssim = true;     // squared errors always come from the strip kernel here
-            JDS_CUDA(launch_ssim_strip(g.H, g.W, d_rgb, rgb_stride, d_recon, frame_bytes, d_metrics,
-                                       n, want_ssim, true, c->sm_count, s));
-            c->launches++;
-        } else {
-            do_fwd = !J.shared_input || u0 == 0;
-            do_inv = true;
-            if (do_fwd) {
-                launch_forward(exact, g, p->prefilter, d_rgb, rgb_stride, fwd, fwd_stride,
-                               J.shared_input ? 1 : n, s);
-                c->launches++;
-            }
-            JDS_CUDA(cudaEventRecord(c->evs[1], s));
-            launch_codec(exact, g, fwd, fwd_stride, rec, rec_stride, d_tables,
-                         J.qualities ? 1 : 0, d_coeffs, ncoef, want_hist, d_metrics, n, s);
-            JDS_CUDA(cudaEventRecord(c->evs[2], s));
-            launch_inverse(exact, g, d_rgb, rgb_stride, fwd, fwd_stride, rec, rec_stride, d_recon,
-                           frame_bytes, d_ey, d_ergb, d_metrics, n, s);
-            JDS_CUDA(cudaEventRecord(c->evs[3], s));
-            c->launches += 2;
-            do_ssim = want_ssim && g.H >= 7 && g.W >= 7;
-            if (do_ssim) {
-                if (!c->legacy_ssim &&
-                    ssim_strip_supported(g.H, g.W, d_rgb, rgb_stride, d_recon, frame_bytes)) {
-                    JDS_CUDA(launch_ssim_strip(g.H, g.W, d_rgb, rgb_stride, d_recon, frame_bytes,
-                                               d_metrics, n, true, false, c->sm_count, s));
-                } else {
-                    launch_ssim(exact, g.H, g.W, d_rgb, rgb_stride, d_recon, frame_bytes,
-                                d_metrics, n, s);
-                }
-                c->launches++;
-            }
+        // per-stage events for the first kTimedChunks chunks of the call
+        cudaEvent_t* evs = chunk_idx < jds_ctx::kTimedChunks ? &c->evs[5 * chunk_idx] : nullptr;
+        bool ran[4];
+        if ((rc = launch_chunk(c, J, P, n, evs, ran))) return rc;
+        if (evs) {
+            n_timed = chunk_idx + 1;
+            for (int k = 0; k < 4; ++k) timed_ran[chunk_idx][k] = ran[k];
         }
-        JDS_CUDA(cudaEventRecord(c->evs[4], s));
-        JDS_CUDA(cudaEventRecord(c->ev1, s));
-        JDS_CUDA(cudaGetLastError());
+        if (pipelined) {
+            JDS_CUDA(cudaEventRecord(c->ev_comp[b], s));
+            JDS_CUDA(cudaStreamWaitEvent(s_out, c->ev_comp[b], 0));
+        }
         // --- results back ---
-        JDS_CUDA(cudaMemcpyAsync(h_metrics, d_metrics, sizeof(DevMetrics) * n,
-                                 cudaMemcpyDeviceToHost, s));
         if (out_host) {
             if (want_recon)
-                JDS_CUDA(cudaMemcpyAsync(J.recon + (size_t)u0 * frame_bytes, d_recon,
-                                         frame_bytes * n, cudaMemcpyDeviceToHost, s));
+                JDS_CUDA(cudaMemcpyAsync(J.recon + (size_t)u0 * frame_bytes, P.d_recon,
+                                         frame_bytes * (size_t)n, cudaMemcpyDeviceToHost, s_out));
             if (want_coeffs)
-                JDS_CUDA(cudaMemcpyAsync(J.coeffs + (size_t)u0 * ncoef, d_coeffs,
-                                         ncoef * 2 * (size_t)n, cudaMemcpyDeviceToHost, s));
+                JDS_CUDA(cudaMemcpyAsync(J.coeffs + (size_t)u0 * ncoef, P.d_coeffs,
+                                         ncoef * 2 * (size_t)n, cudaMemcpyDeviceToHost, s_out));
             if (want_ey)
-                JDS_CUDA(cudaMemcpyAsync(J.err_y, d_ey, (size_t)g.H * g.W * 8,
-                                         cudaMemcpyDeviceToHost, s));
+                JDS_CUDA(cudaMemcpyAsync(J.err_y, P.d_ey, (size_t)g.H * g.W * 8,
+                                         cudaMemcpyDeviceToHost, s_out));
             if (want_ergb)
-                JDS_CUDA(cudaMemcpyAsync(J.err_rgb, d_ergb, (size_t)g.H * g.W * 8,
-                                         cudaMemcpyDeviceToHost, s));
+                JDS_CUDA(cudaMemcpyAsync(J.err_rgb, P.d_ergb, (size_t)g.H * g.W * 8,
+                                         cudaMemcpyDeviceToHost, s_out));
+            if (pipelined) JDS_CUDA(cudaEventRecord(c->ev_out[b], s_out));
         }
-        JDS_CUDA(cudaStreamSynchronize(s));
-        float ms = 0.f;
-        JDS_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-        {
-            const bool ran[4] = {do_fwd, true, do_inv, do_ssim};
-            for (int k = 0; k < 4; ++k) {
-                float t = 0.f;
-                JDS_CUDA(cudaEventElapsedTime(&t, c->evs[k], c->evs[k + 1]));
-                if (ran[k]) {
-                    c->stage_ms[k] += t;
-                    c->stage_launches[k] += 1;
-                }
+    }
+    JDS_CUDA(cudaEventRecord(c->ev1, s));
+    JDS_CUDA(cudaMemcpyAsync(h_metrics, d_metrics, sizeof(DevMetrics) * J.units,
+                             cudaMemcpyDeviceToHost, s));
+    if (pipelined) {
+        JDS_CUDA(cudaStreamSynchronize(s_in));
+        JDS_CUDA(cudaStreamSynchronize(s_out));
+    }
+    JDS_CUDA(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    JDS_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    for (int ci = 0; ci < n_timed; ++ci)
+        for (int k = 0; k < 4; ++k) {
+            float t = 0.f;
+            JDS_CUDA(cudaEventElapsedTime(&t, c->evs[5 * ci + k], c->evs[5 * ci + k + 1]));
+            if (timed_ran[ci][k]) {
+                c->stage_ms[k] += t;
+                c->stage_launches[k] += 1;
             }
         }
-        for (int i = 0; i < n; ++i) {
-            jds_metrics* m = &J.metrics[u0 + i];
-            const DevMetrics& d = h_metrics[i];
-            memset(m, 0, sizeof *m);
-            m->sse_rgb = d.sse_rgb;
-            m->sse_y = d.sse_y;
-            for (int k = 0; k < 4; ++k) m->ssim_sum[k] = d.ssim_sum[k];
-            m->ssim_count = (want_ssim && g.H >= 7 && g.W >= 7)
-                                ? (uint64_t)(g.H - 6) * (uint64_t)(g.W - 6) : 0;
-            m->coeff_bits = d.coeff_bits;
-            m->nnz = d.nnz;
-            m->total_coeffs = ncoef;
-            m->luma_blocks = (uint64_t)g.nblk_y;
-            for (int k = 0; k < 50; ++k) m->hist50[k] = (int64_t)d.hist[k];
-            m->gpu_ms = (double)ms / n;
-        }
+    for (int i = 0; i < J.units; ++i) {
+        jds_metrics* m = &J.metrics[i];
+        const DevMetrics& d = h_metrics[i];
+        memset(m, 0, sizeof *m);
+        m->sse_rgb = d.sse_rgb;
+        m->sse_y = d.sse_y;
+        for (int k = 0; k < 4; ++k) m->ssim_sum[k] = d.ssim_sum[k];
+        m->ssim_count = (want_ssim && g.H >= 7 && g.W >= 7)
+                            ? (uint64_t)(g.H - 6) * (uint64_t)(g.W - 6) : 0;
+        m->coeff_bits = d.coeff_bits;
+        m->nnz = d.nnz;
+        m->total_coeffs = ncoef;
+        m->luma_blocks = (uint64_t)g.nblk_y;
+        for (int k = 0; k < 50; ++k) m->hist50[k] = (int64_t)d.hist[k];
+        m->gpu_ms = (double)ms / J.units;
     }
     return JDS_OK;
 }
