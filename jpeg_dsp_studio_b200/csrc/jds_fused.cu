@@ -203,16 +203,13 @@ __device__ __forceinline__ uint32_t pack4(uint32_t a, uint32_t b, uint32_t c, ui
 // tile = 16 x 4 chroma blocks per channel; thread t: channel t/64, block t%64
 // ------------------------------------------------------------------------------
 constexpr int CA_BX = 16, CA_BY = 4, CA_NT = 128;
-constexpr int CA_ROWB = CA_BX * 16 * 3;          // 768 bytes of RGB per tile row
 
 template <int SUB>
 struct ChromaSmem {
     static constexpr int ROWS = CA_BY * 8 * (SUB == 2 ? 2 : 1);
-    alignas(128) uint8_t raw[ROWS][CA_ROWB];
     alignas(16) float plane[2][CA_BX * CA_BY][BLK_STRIDE];
     alignas(16) float fq[64];
     alignas(16) float dq[64];
-    alignas(8) unsigned long long bar;
 };
 
 template <int SUB, bool COEFFS>
@@ -232,21 +229,8 @@ k_fast_chroma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
     const int x0 = bx0 * 16, y0 = by0 * 8 * VS;                      // luma pixel origin
     const int n_rows = min(ROWS, g.H - y0);
     const int n_px = min(CA_BX * 16, g.W - x0);
-    const uint32_t row_bytes = (uint32_t)n_px * 3u;
 
-    if (tid == 0) {
-        f_mbar_init(&sm.bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (tid < 32) {
-        if (tid == 0) f_mbar_expect_tx(&sm.bar, row_bytes * (uint32_t)n_rows);
-        __syncwarp();
-        for (int r = tid; r < n_rows; r += 32)
-            f_bulk_g2s(&sm.raw[r][0], in + ((size_t)(y0 + r) * g.W + x0) * 3, row_bytes, &sm.bar);
-    }
     load_tables(tables + (size_t)unit * table_stride, sm.fq, sm.dq, tid, CA_NT);
-    f_mbar_wait(&sm.bar, 0);
 
     // ---- decimation: a task = one chroma row x 8 chroma samples (16 luma pixels) ----
     // channel sums over the 2x1 / 2x2 footprint with IDP4A on the interleaved bytes,
@@ -259,10 +243,13 @@ k_fast_chroma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
             uint32_t w[VS][12];
 #pragma unroll
             for (int v = 0; v < VS; ++v) {
-                const uint4* q = reinterpret_cast<const uint4*>(&sm.raw[cr * VS + v][seg * 48]);
+                // 48 contiguous bytes per thread, consecutive threads contiguous: the three
+                // 16-byte loads of a warp cover whole 128-byte lines between them
+                const uint4* q = reinterpret_cast<const uint4*>(
+                    in + ((size_t)(y0 + cr * VS + v) * g.W + x0 + seg * 16) * 3);
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
-                    const uint4 a = q[i];
+                    const uint4 a = __ldg(q + i);
                     w[v][4 * i] = a.x; w[v][4 * i + 1] = a.y; w[v][4 * i + 2] = a.z; w[v][4 * i + 3] = a.w;
                 }
             }
@@ -338,18 +325,16 @@ k_fast_chroma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
 // ------------------------------------------------------------------------------
 constexpr int LU_BX = 32, LU_BY = 4, LU_NT = 128;
 constexpr int LU_TW = LU_BX * 8, LU_TH = LU_BY * 8;      // 256 x 32
-constexpr int LU_ROWB = LU_TW * 3;                       // 768
 constexpr int CT_COLS = LU_TW / 2 + 8;                   // 136 chroma columns staged
 
 template <int SUB>
 struct LumaSmem {
     static constexpr int CT_ROWS = (SUB == 2) ? LU_TH / 2 + 2 : LU_TH;
-    alignas(128) uint8_t raw[LU_TH][LU_ROWB];
     alignas(16) float plane[LU_BX * LU_BY][BLK_STRIDE];
     alignas(128) float ctile[2][CT_ROWS][CT_COLS];
     alignas(16) float fq[64];
     alignas(16) float dq[64];
-    alignas(8) unsigned long long bar[2];
+    alignas(8) unsigned long long bar;
 };
 
 // 16 horizontally upsampled chroma samples from staged samples c[0..15], where c[4+k]
@@ -387,14 +372,12 @@ k_fast_luma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
             uint8_t* __restrict__ recon, size_t recon_stride, DevMetrics* __restrict__ metrics) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     LumaSmem<SUB>& sm = *reinterpret_cast<LumaSmem<SUB>*>(smem_raw);
-    constexpr int CT_ROWS = LumaSmem<SUB>::CT_ROWS;
     const int tid = threadIdx.x;
     const int unit = blockIdx.z;
     const uint8_t* in = rgb + (size_t)unit * rgb_stride;
     const int x0 = blockIdx.x * LU_TW, y0 = blockIdx.y * LU_TH;
     const int n_rows = min(LU_TH, g.H - y0);
     const int n_px = min(LU_TW, g.W - x0);
-    const uint32_t row_bytes = (uint32_t)n_px * 3u;
 
     // chroma tile geometry: columns [ccol0, ccol0 + ncc), rows [crow0, crow0 + ncr)
     const int cx0 = x0 >> 1;
@@ -407,41 +390,37 @@ k_fast_luma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
     const int crow1 = (SUB == 2) ? min(cy0 + (n_rows >> 1) + 1, g.hc) : min(cy0 + n_rows, g.hc);
 
     if (tid == 0) {
-        f_mbar_init(&sm.bar[0], 1);
-        f_mbar_init(&sm.bar[1], 1);
+        f_mbar_init(&sm.bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     if (tid < 32) {
-        if (tid == 0) {
-            f_mbar_expect_tx(&sm.bar[0], row_bytes * (uint32_t)n_rows);
-            f_mbar_expect_tx(&sm.bar[1], (uint32_t)(ccol1 - ccol0) * 4u * 2u * (uint32_t)(crow1 - crow0));
-        }
+        // reconstructed chroma (written by k_fast_chroma earlier in this stream): TMA bulk
+        // copies, one row per lane, overlapped with the luma work below
+        if (tid == 0)
+            f_mbar_expect_tx(&sm.bar, (uint32_t)(ccol1 - ccol0) * 4u * 2u * (uint32_t)(crow1 - crow0));
         __syncwarp();
-        for (int r = tid; r < n_rows; r += 32)
-            f_bulk_g2s(&sm.raw[r][0], in + ((size_t)(y0 + r) * g.W + x0) * 3, row_bytes, &sm.bar[0]);
-        // reconstructed chroma (written by k_fast_chroma earlier in this stream)
         const float* cp = cplanes + (size_t)unit * cplane_stride;
         const int ncr = crow1 - crow0;
         for (int i = tid; i < 2 * ncr; i += 32) {
             const int chn = i / ncr, r = crow0 + i % ncr;
             f_bulk_g2s(&sm.ctile[chn][r - crow_lo][ccol0 - ccol_lo],
                        cp + (size_t)chn * g.plane_c + (size_t)r * g.wcp + ccol0,
-                       (uint32_t)(ccol1 - ccol0) * 4u, &sm.bar[1]);
+                       (uint32_t)(ccol1 - ccol0) * 4u, &sm.bar);
         }
     }
     load_tables(tables + (size_t)unit * table_stride, sm.fq, sm.dq, tid, LU_NT);
-    f_mbar_wait(&sm.bar[0], 0);
 
     // ---- RGB -> level-shifted Y, block layout: a task = one row x 16 pixels ----------
     for (int task = tid; task < LU_TH * (LU_TW / 16); task += LU_NT) {
         const int r = task / (LU_TW / 16), seg = task % (LU_TW / 16);
         if (r < n_rows && seg * 16 < n_px) {
-            const uint4* q = reinterpret_cast<const uint4*>(&sm.raw[r][seg * 48]);
+            const uint4* q = reinterpret_cast<const uint4*>(
+                in + ((size_t)(y0 + r) * g.W + x0 + seg * 16) * 3);
             uint32_t w[12];
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                const uint4 a = q[i];
+                const uint4 a = __ldg(q + i);
                 w[4 * i] = a.x; w[4 * i + 1] = a.y; w[4 * i + 2] = a.z; w[4 * i + 3] = a.w;
             }
             float yv[16];
@@ -487,7 +466,7 @@ k_fast_luma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
         flush_stats(esum, nnz, metrics + unit);
     }
     __syncthreads();
-    f_mbar_wait(&sm.bar[1], 0);
+    f_mbar_wait(&sm.bar, 0);
 
     // ---- compose: a task = 2 rows (SUB 2) or 1 row (SUB 1) x 16 pixels ---------------
     constexpr int RPT = (SUB == 2) ? 2 : 1;                   // rows per task
