@@ -1,0 +1,153 @@
+"""Multi-GPU sharding of sweeps and batches (BASELINE.json configs 4 and 5).
+
+One process per GPU (``torchrun``); units - quality points of a sweep, frames of a
+batch - are independent, so they shard round-robin (unit k -> rank k mod world,
+SURVEY.md §8e) with NO data-path collective.  The only exchange is the metric
+records: one ``all_gather`` per sweep (every rank ends up with the whole
+rate-distortion table) or one ``all_reduce`` per batch (aggregate partials), over
+NCCL on GPUs (gloo in the CPU tests).  Integer partials (SSE_rgb, bits, nnz) are
+summed exactly: fp64 holds integers up to 2^53.
+"""
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+#: fields of one unit's record, in the order they travel
+RECORD_FIELDS = ("unit", "quality", "sse_rgb", "sse_y", "ssim_r", "ssim_g", "ssim_b", "ssim_y",
+                 "ssim_count", "coeff_bits", "nnz", "total_coeffs", "luma_blocks")
+
+
+def shard_indices(n_units: int, rank: int, world: int) -> List[int]:
+    """Units owned by ``rank``: k with k mod world == rank."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    return list(range(rank, n_units, world))
+
+
+def record_from_metrics(unit: int, quality: int, m) -> np.ndarray:
+    """One fp64 row from a ``jds_metrics`` struct (or anything with the same fields)."""
+    return np.array([unit, quality, float(m.sse_rgb), float(m.sse_y), float(m.ssim_sum[0]),
+                     float(m.ssim_sum[1]), float(m.ssim_sum[2]), float(m.ssim_sum[3]),
+                     float(m.ssim_count), float(m.coeff_bits), float(m.nnz),
+                     float(m.total_coeffs), float(m.luma_blocks)], dtype=np.float64)
+
+
+def scalars_from_record(rec: np.ndarray, height: int, width: int) -> dict:
+    """The reference's result floats from a gathered record (utils/metrics.py formulas)."""
+    from .utils.metrics import psnr_from_sse
+    f = dict(zip(RECORD_FIELDS, rec.tolist()))
+    n_px = height * width
+    bits = 2 * int(f["luma_blocks"]) + int(f["coeff_bits"])
+    cnt = f["ssim_count"]
+    out = {
+        "quality": int(f["quality"]),
+        "psnr_rgb": psnr_from_sse(f["sse_rgb"], 3 * n_px),
+        "psnr_y": psnr_from_sse(f["sse_y"], n_px),
+        "ssim_rgb": float(np.mean([f["ssim_r"], f["ssim_g"], f["ssim_b"]]) / cnt) if cnt else float("nan"),
+        "ssim_y": float(f["ssim_y"] / cnt) if cnt else float("nan"),
+        "estimated_bits": bits,
+        "bpp": float(bits / n_px),
+        "compression_ratio": float(n_px * 24 / max(bits, 1)),
+        "nonzero_count": int(f["nnz"]),
+        "total_coeffs": int(f["total_coeffs"]),
+    }
+    return out
+
+
+def _dist():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist
+    return None
+
+
+def gather_records(local: np.ndarray, n_units: int, device=None) -> np.ndarray:
+    """All-gather of per-unit records: every rank returns the (n_units, F) table ordered
+    by unit.  ``local``: (n_local, F) rows whose first column is the unit index."""
+    dist = _dist()
+    nf = len(RECORD_FIELDS)
+    local = np.asarray(local, dtype=np.float64).reshape(-1, nf)
+    if dist is None or dist.get_world_size() == 1:
+        table = local
+    else:
+        import torch
+        world = dist.get_world_size()
+        cap = (n_units + world - 1) // world                 # rows per rank, padded
+        buf = torch.full((cap, nf), -1.0, dtype=torch.float64, device=device)
+        if len(local):
+            buf[:len(local)] = torch.from_numpy(local).to(buf.device)
+        out = torch.empty((world * cap, nf), dtype=torch.float64, device=device)
+        dist.all_gather_into_tensor(out, buf)
+        table = out.cpu().numpy()
+        table = table[table[:, 0] >= 0]
+    order = np.argsort(table[:, 0], kind="stable")
+    table = table[order]
+    if len(table) != n_units or not np.array_equal(table[:, 0], np.arange(n_units)):
+        raise RuntimeError("sharded units do not cover 0..n_units-1 exactly once")
+    return table
+
+
+def reduce_partials(local_sum: np.ndarray, device=None) -> np.ndarray:
+    """All-reduce (sum) of aggregate partials; integer-valued entries stay exact < 2^53."""
+    dist = _dist()
+    v = np.asarray(local_sum, dtype=np.float64)
+    if dist is None or dist.get_world_size() == 1:
+        return v.copy()
+    import torch
+    t = torch.from_numpy(v.copy()).to(device) if device is not None else torch.from_numpy(v.copy())
+    dist.all_reduce(t)
+    return t.cpu().numpy()
+
+
+def sweep_sharded(engine, image, qualities: Sequence[int], mode="4:2:0", prefilter=False, *,
+                  precision="fast", device=None) -> List[dict]:
+    """Rate-distortion sweep with the points sharded over the ranks (config 4).
+    Every rank returns the full list of per-quality result dicts."""
+    dist = _dist()
+    rank = dist.get_rank() if dist else 0
+    world = dist.get_world_size() if dist else 1
+    qs = [int(q) for q in qualities]
+    mine = shard_indices(len(qs), rank, world)
+    rows = np.zeros((0, len(RECORD_FIELDS)))
+    if mine:
+        outs = engine.sweep(image, [qs[i] for i in mine], mode, prefilter, precision=precision)
+        rows = np.stack([record_from_metrics(i, qs[i], o.metrics) for i, o in zip(mine, outs)])
+    table = gather_records(rows, len(qs), device=device)
+    h, w = image.shape[0], image.shape[1]
+    return [scalars_from_record(r, h, w) for r in table]
+
+
+def batch_sharded(engine, frames_of_rank, n_total: int, quality=50, mode="4:2:0", prefilter=False, *,
+                  precision="fast", device=None) -> dict:
+    """Batch with the frames sharded over the ranks (config 5): ``frames_of_rank`` holds
+    this rank's frames (k mod world == rank, in order).  Returns the aggregate over ALL
+    frames (mean PSNR from the summed squared error, mean SSIM, total bits)."""
+    outs = engine.roundtrip_batch(frames_of_rank, quality, mode, prefilter, precision=precision,
+                                  want_recon=False) if len(frames_of_rank) else []
+    h, w = (frames_of_rank.shape[1], frames_of_rank.shape[2]) if len(frames_of_rank) else (1, 1)
+    part = np.zeros(11, dtype=np.float64)
+    for o in outs:
+        m = o.metrics
+        part += np.array([1, float(m.sse_rgb), float(m.sse_y), m.ssim_sum[0], m.ssim_sum[1],
+                          m.ssim_sum[2], m.ssim_sum[3], float(m.ssim_count), float(m.coeff_bits),
+                          float(m.nnz), float(m.luma_blocks)])
+    geo = reduce_partials(np.array([h, w], dtype=np.float64) * (1.0 if len(outs) else 0.0), device)
+    tot = reduce_partials(part, device=device)
+    n = int(round(tot[0]))
+    if n != n_total:
+        raise RuntimeError(f"ranks processed {n} frames, expected {n_total}")
+    from .utils.metrics import psnr_from_sse
+    dist = _dist()
+    world = dist.get_world_size() if dist else 1
+    contributing = max(1, min(world, n_total))
+    h, w = int(round(geo[0] / contributing)), int(round(geo[1] / contributing))
+    n_px = h * w * n
+    bits = 2 * int(round(tot[10])) + int(round(tot[8]))
+    return {
+        "frames": n, "height": h, "width": w,
+        "psnr_rgb": psnr_from_sse(tot[1], 3 * n_px), "psnr_y": psnr_from_sse(tot[2], n_px),
+        "ssim_rgb": float((tot[3] + tot[4] + tot[5]) / 3.0 / tot[7]) if tot[7] else float("nan"),
+        "ssim_y": float(tot[6] / tot[7]) if tot[7] else float("nan"),
+        "estimated_bits": bits, "bpp": float(bits / n_px), "nonzero_count": int(round(tot[9])),
+    }
