@@ -41,7 +41,7 @@ sys.path.insert(0, ROOT)
 
 H, W = 2160, 3840
 QUALITY, MODE, PREFILTER = 50, "4:2:0", False
-FRAMES = 8
+FRAMES = int(os.environ.get("JDS_BENCH_FRAMES", "8"))
 BYTES_PER_PX = 6.0          # algorithmic: 3 B read + 3 B written per pixel
 WORKLOAD = (f"{FRAMES}x 4K (3840x2160) random RGB frames per GPU per step, Q={QUALITY} {MODE} "
             f"prefilter off, round trip + PSNR/SSIM(R,G,B,Y)/bpp, fast fp32 mode")
@@ -72,11 +72,7 @@ class ClockSampler:
 
     def _nvml_loop(self):
         n = self.nvml
-        h = n.nvmlDeviceGetHandleByIndex(self.index)
-        try:
-            self.max_mhz = float(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM))
-        except Exception:
-            pass
+        h = self.handle
         bits = {"hw_slowdown": getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8),
                 "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
                 "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
@@ -86,7 +82,10 @@ class ClockSampler:
         while not self._stop.is_set():
             try:
                 self.samples.append(float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)))
-                self.power.append(n.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                try:
+                    self.power.append(n.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                except Exception:
+                    pass
                 if get_reasons:
                     r = get_reasons(h)
                     for name, bit in bits.items():
@@ -100,6 +99,17 @@ class ClockSampler:
         try:
             import pynvml
             pynvml.nvmlInit()
+            # physical index of this process's CUDA device (CUDA_VISIBLE_DEVICES aware)
+            idx = self.index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.index])
+                except (ValueError, IndexError):
+                    pass
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)      # warm the call path
             self.nvml = pynvml
             self.t = threading.Thread(target=self._nvml_loop, daemon=True)
             self.t.start()
@@ -265,6 +275,7 @@ def run_ours(args):
     d_out = torch.empty_like(d_in)
     px_per_step = FRAMES * H * W
     partial_t = torch.zeros(8, dtype=torch.float64, device=dev)
+    partial_h = torch.zeros(8, dtype=torch.float64).pin_memory()
 
     def barrier():
         if world > 1:
@@ -273,15 +284,16 @@ def run_ours(args):
 
     def reduce_partials(outs):
         """the path's only exchange: all-reduce of the metric partials (NCCL)"""
-        sse = float(sum(o.metrics.sse_rgb for o in outs))
-        ssey = float(sum(o.metrics.sse_y for o in outs))
-        bits = float(sum(o.scalars["estimated_bits"] for o in outs))
-        ssim = [float(sum(o.metrics.ssim_sum[c] for o in outs)) for c in range(4)]
-        v = torch.tensor([sse, ssey, bits] + ssim + [float(len(outs))], dtype=torch.float64)
-        partial_t.copy_(v, non_blocking=False)
+        ms = [o.metrics for o in outs]
+        sse = float(sum(m.sse_rgb for m in ms))
+        ssey = float(sum(m.sse_y for m in ms))
+        bits = float(sum(2 * m.luma_blocks + m.coeff_bits for m in ms))
+        ssim = [float(sum(m.ssim_sum[c] for m in ms)) for c in range(4)]
+        partial_h[:] = torch.tensor([sse, ssey, bits] + ssim + [float(len(outs))], dtype=torch.float64)
         if world > 1:
+            partial_t.copy_(partial_h, non_blocking=True)
             dist.all_reduce(partial_t)
-        return partial_t
+        return partial_h
 
     def step_device(precision):
         outs = eng.roundtrip_batch(d_in, QUALITY, MODE, PREFILTER, precision=precision,

@@ -35,8 +35,11 @@ constexpr int S_NT = 128;            // threads per CTA = 64 columns x 2 channel
 constexpr int S_SEG = 8;             // windows per pass-1 task
 constexpr int S_NSEG = S_OW / S_SEG; // 8
 
-constexpr int S_FPITCH = S_LW + 2;   // float2 row pitch of fpl: rows land 16 B apart in the banks
-constexpr int S_HPITCH = 2 * S_OW + 1; // float4 row pitch of hbuf: likewise
+// Shared-memory rows are padded so that consecutive ROWS start 16 bytes apart modulo 128:
+// a quarter-warp that walks 8 rows at the same column then hits 8 different bank groups.
+constexpr int S_FHALF = S_LW / 4;      // float4 per half row of fpl (even / odd pixel pairs)
+constexpr int S_FPITCH = 2 * S_FHALF + 1; // float4 row pitch of fpl: 81 * 16 B = 10 * 128 + 16
+constexpr int S_HPITCH = 2 * S_OW + 1; // float4 row pitch of hxy / hqc: 129 * 16 B = 16 * 128 + 16
 
 struct HSum {                        // window sums of one (row, pair, column)
     float2 sx, sy, sq, sc;           // .x = first channel of the pair, .y = second
@@ -44,7 +47,9 @@ struct HSum {                        // window sums of one (row, pair, column)
 
 struct SsimSmem {
     alignas(128) uint8_t raw[2][2][S_R][S_ROWB];   // [buffer][image][row][byte]
-    alignas(16) float2 fpl[2][2][S_R][S_FPITCH];   // centred fp32 [image][pair][row][col]
+    // centred fp32 samples [image][pair][row]: each float4 holds two pixels x two channels
+    // (c0 p, c1 p, c0 p+1, c1 p+1); even pixel-pairs in [0, 40), odd pixel-pairs in [40, 80)
+    alignas(16) float4 fpl[2][2][S_R][S_FPITCH];
     alignas(16) float4 hxy[S_R][S_HPITCH];         // horizontal sums (sx, sy) [row][pair*64+col]
     alignas(16) float4 hqc[S_R][S_HPITCH];         // horizontal sums (sq, sc)
     alignas(8) unsigned long long bar[2];
@@ -93,6 +98,11 @@ __device__ __forceinline__ float byte_centered(uint32_t w) {
     return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440 | B)) - 8388736.0f;
 }
 
+__device__ __forceinline__ float rcp_approx(float x) {        // MUFU.RCP, no range fix-up
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
 __device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __ffma2_rn(b, f2(-1.0f), a); }
@@ -113,7 +123,7 @@ __device__ __forceinline__ float2 ssim_window_half2(float2 sx, float2 sy, float2
     const float2 u = __ffma2_rn(sx, sx, __fmul2_rn(sy, sy));
     const float2 B2 = __ffma2_rn(sq, f2(N), sub2(f2(K2), u));
     const float2 num = __fmul2_rn(A1, A2), den = __fmul2_rn(B1, B2);
-    return __fmul2_rn(num, f2(__fdividef(1.0f, den.x), __fdividef(1.0f, den.y)));
+    return __fmul2_rn(num, f2(rcp_approx(den.x), rcp_approx(den.y)));
 }
 
 __global__ void __launch_bounds__(S_NT, 3)
@@ -177,12 +187,12 @@ k_ssim_strip(int H, int W, int seg_rows, const uint8_t* __restrict__ a_img, size
     acc.sx = acc.sy = acc.sq = acc.sc = f2(0.f);
     double ssim_a = 0.0, ssim_b = 0.0;
     const bool col_ok = want_ssim && col < nwin_x;
-    // pass-1 role: thread = (row, segment, pair), 112 of the 128 threads
-    // (row fastest: the padded row pitches then spread a quarter-warp over the banks)
-    const int p1_row = tid % S_R;
-    const int p1_seg = (tid / S_R) & (S_NSEG - 1);
-    const int p1_pair = tid / (S_NSEG * S_R);
-    const bool p1_active = tid < S_NSEG * S_R * 2;
+    // pass-1 role: thread = (row slot, segment, pair); slot 7 of every 8 idles, so a
+    // quarter-warp is 7 rows of one segment: conflict free with the padded row pitches
+    const int p1_row = tid & 7;
+    const int p1_seg = (tid >> 3) & (S_NSEG - 1);
+    const int p1_pair = tid >> 6;
+    const bool p1_active = p1_row < S_R;
     const int p1_c0 = S_SEG * p1_seg;
     double sse_a = 0.0, sse_b = 0.0;                // squared error of the pair's channels
 
@@ -206,12 +216,12 @@ k_ssim_strip(int H, int W, int seg_rows, const uint8_t* __restrict__ a_img, size
                 const float Y1 = fmaf(0.299f, R1, fmaf(0.587f, G1, 0.114f * B1));
                 const float Y2 = fmaf(0.299f, R2, fmaf(0.587f, G2, 0.114f * B2));
                 const float Y3 = fmaf(0.299f, R3, fmaf(0.587f, G3, 0.114f * B3));
-                float4* d0 = reinterpret_cast<float4*>(&sm.fpl[img][0][r][4 * g4]);
-                float4* d1 = reinterpret_cast<float4*>(&sm.fpl[img][1][r][4 * g4]);
-                d0[0] = make_float4(R0, G0, R1, G1);
-                d0[1] = make_float4(R2, G2, R3, G3);
-                d1[0] = make_float4(B0, Y0, B1, Y1);
-                d1[1] = make_float4(B2, Y2, B3, Y3);
+                // pixels 4*g4 .. 4*g4+3 = pixel-pairs 2*g4 (even half) and 2*g4+1 (odd half):
+                // consecutive threads store consecutive float4 -> no bank conflicts
+                sm.fpl[img][0][r][g4] = make_float4(R0, G0, R1, G1);
+                sm.fpl[img][0][r][S_FHALF + g4] = make_float4(R2, G2, R3, G3);
+                sm.fpl[img][1][r][g4] = make_float4(B0, Y0, B1, Y1);
+                sm.fpl[img][1][r][S_FHALF + g4] = make_float4(B2, Y2, B3, Y3);
             }
         }
     };
@@ -247,12 +257,15 @@ k_ssim_strip(int H, int W, int seg_rows, const uint8_t* __restrict__ a_img, size
 
         // ---- pass 1: horizontal 7-tap sums of x, y, x^2+y^2, xy (sliding window) ---------
         if (p1_active && p1_row < nr) {
-            const float4* qa = reinterpret_cast<const float4*>(&sm.fpl[0][p1_pair][p1_row][p1_c0]);
-            const float4* qb = reinterpret_cast<const float4*>(&sm.fpl[1][p1_pair][p1_row][p1_c0]);
+            // pixel-pair index of the segment's first pixel is 4 * seg (even): pairs alternate
+            // between the even and the odd half of the row
+            const float4* qa = &sm.fpl[0][p1_pair][p1_row][2 * p1_seg];
+            const float4* qb = &sm.fpl[1][p1_pair][p1_row][2 * p1_seg];
             float2 xs[S_SEG + 6], ys[S_SEG + 6];
 #pragma unroll
             for (int i2 = 0; i2 < (S_SEG + 6) / 2; ++i2) {
-                const float4 a = qa[i2], b = qb[i2];
+                const int off = (i2 & 1) * S_FHALF + (i2 >> 1);
+                const float4 a = qa[off], b = qb[off];
                 xs[2 * i2] = f2(a.x, a.y); xs[2 * i2 + 1] = f2(a.z, a.w);
                 ys[2 * i2] = f2(b.x, b.y); ys[2 * i2 + 1] = f2(b.z, b.w);
             }

@@ -10,7 +10,6 @@ used only where the caller hands over device tensors or pinned host tensors
 
 import ctypes as C
 import threading
-from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -20,15 +19,27 @@ from .models import CompressionParams
 from .utils.metrics import bitrate_from_partials, metrics_from_partials
 
 
-@dataclass
 class RoundTripOutputs:
-    """Raw outputs of one unit (frame or sweep point)."""
-    recon: Optional[np.ndarray]
-    coeffs: Optional[np.ndarray]
-    err_y: Optional[np.ndarray]
-    err_rgb: Optional[np.ndarray]
-    metrics: "N.JdsMetrics"
-    scalars: dict          # psnr_y, ssim_y, psnr_rgb, ssim_rgb, bpp, compression_ratio, ...
+    """Raw outputs of one unit (frame or sweep point).
+
+    ``metrics`` is the ``jds_metrics`` record of device partials; ``scalars`` (PSNR / SSIM /
+    bpp / compression ratio ... computed from the partials with the reference's final
+    formulas) is evaluated on first access."""
+
+    __slots__ = ("recon", "coeffs", "err_y", "err_rgb", "metrics", "_hw", "_scalars")
+
+    def __init__(self, recon, coeffs, err_y, err_rgb, metrics, hw):
+        self.recon, self.coeffs, self.err_y, self.err_rgb = recon, coeffs, err_y, err_rgb
+        self.metrics, self._hw, self._scalars = metrics, hw, None
+
+    @property
+    def scalars(self) -> dict:
+        if self._scalars is None:
+            h, w = self._hw
+            out = metrics_from_partials(self.metrics, h, w)
+            out.update(bitrate_from_partials(self.metrics, h, w))
+            self._scalars = out
+        return self._scalars
 
 
 def _is_torch(x) -> bool:
@@ -124,11 +135,6 @@ class Engine:
             raise TypeError(f"image must be uint8, got {a.dtype}")
         return C.c_void_p(a.ctypes.data), N.JDS_HOST, a
 
-    def _scalars(self, m, h, w) -> dict:
-        out = metrics_from_partials(m, h, w)
-        out.update(bitrate_from_partials(m, h, w))
-        return out
-
     # -- single frame ----------------------------------------------------------------
     def roundtrip(self, image, quality=50, mode="4:2:0", prefilter=False, *,
                   precision="exact", want_coeffs=False, want_error_maps=False,
@@ -167,7 +173,7 @@ class Engine:
         with self._lock:
             N.check(self._lib.jds_roundtrip(self._ctx, C.byref(p), ptr, loc, gp(recon), gp(coeffs),
                                             gp(ey), gp(ergb), loc, C.byref(m)))
-        return RoundTripOutputs(recon, coeffs, ey, ergb, m, self._scalars(m, h, w))
+        return RoundTripOutputs(recon, coeffs, ey, ergb, m, (h, w))
 
     def selected_block(self, image, quality, block_row, block_col):
         """IntermediateData.selected_block_* (engines/pipeline.py:126-151) or None."""
@@ -227,7 +233,7 @@ class Engine:
                                                   gp(coeffs), loc, ms))
         return [RoundTripOutputs(recon[i] if recon is not None else None,
                                  coeffs[i] if coeffs is not None else None, None, None, ms[i],
-                                 self._scalars(ms[i], h, w)) for i in range(n)]
+                                 (h, w)) for i in range(n)]
 
     # -- quality sweep (BASELINE config 4; gui/worker.py:55-74) -------------------------
     def sweep(self, image, qualities: Sequence[int], mode="4:2:0", prefilter=False, *,
@@ -256,7 +262,7 @@ class Engine:
         with self._lock:
             N.check(self._lib.jds_sweep(self._ctx, C.byref(p), qarr, nq, ptr, loc, rp, loc, ms))
         return [RoundTripOutputs(recon[i] if recon is not None else None, None, None, None, ms[i],
-                                 self._scalars(ms[i], h, w)) for i in range(nq)]
+                                 (h, w)) for i in range(nq)]
 
 
 _engines = {}
