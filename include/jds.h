@@ -178,6 +178,17 @@ int jds_selected_block(jds_ctx* ctx, const jds_params* params,
                        int16_t quantized[64], double dequantized[64],
                        double reconstructed[64], int* present);
 
+/*
+ * Stand-alone 8x8 block operators, exact (reference) arithmetic, host buffers:
+ *   op 0 dct2, 1 idct2 (engines/dct_engine.py:7-14), 2 encode_block (-128 then DCT, :17-20),
+ *   3 decode_block (IDCT, +128, clip, :23-27): in/out = n_blocks*64 fp64;
+ *   4 quantize (engines/quantizer.py:22-24): in fp64, qtable[64], out_q int16;
+ *   5 dequantize (:27-29): in_q int16, qtable[64], out fp64.
+ * Unused pointers are NULL.
+ */
+int jds_block_op(jds_ctx* ctx, int op, int64_t n_blocks, const double* in, const int16_t* in_q,
+                 const double* qtable, double* out, int16_t* out_q);
+
 #ifdef __cplusplus
 }
 #endif

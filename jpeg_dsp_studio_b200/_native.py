@@ -65,6 +65,8 @@ PROTOTYPES = {
                                       C.POINTER(JdsMetrics)]),
     "jds_sweep": (C.c_int, [C.c_void_p, C.POINTER(JdsParams), C.POINTER(C.c_int32), C.c_int,
                             C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(JdsMetrics)]),
+    "jds_block_op": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_void_p]),
     "jds_selected_block": (C.c_int, [C.c_void_p, C.POINTER(JdsParams), C.c_void_p, C.c_int,
                                      C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),

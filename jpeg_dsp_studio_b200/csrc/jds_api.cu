@@ -731,3 +731,38 @@ extern "C" int jds_selected_block(jds_ctx* c, const jds_params* p, const uint8_t
     *present = 1;
     return JDS_OK;
 }
+
+// Stand-alone block operators (host buffers): engines/dct_engine.py:7-27 and
+// engines/quantizer.py:22-29 on n_blocks 8x8 blocks, exact (reference) arithmetic.
+extern "C" int jds_block_op(jds_ctx* c, int op, int64_t n_blocks, const double* in,
+                            const int16_t* in_q, const double* qtable, double* out,
+                            int16_t* out_q) {
+    if (!c) return fail(JDS_ERR_INVALID, "ctx is NULL");
+    if (n_blocks < 1) return fail(JDS_ERR_INVALID, "n_blocks must be >= 1");
+    if (op < JDS_BLOCKOP_DCT2 || op > JDS_BLOCKOP_DEQUANTIZE)
+        return fail(JDS_ERR_INVALID, "unknown block op %d", op);
+    const bool needs_q = op == JDS_BLOCKOP_QUANTIZE || op == JDS_BLOCKOP_DEQUANTIZE;
+    const bool in_is_q = op == JDS_BLOCKOP_DEQUANTIZE, out_is_q = op == JDS_BLOCKOP_QUANTIZE;
+    if ((needs_q && !qtable) || (in_is_q ? !in_q : !in) || (out_is_q ? !out_q : !out))
+        return fail(JDS_ERR_INVALID, "NULL buffer for block op %d", op);
+    JDS_CUDA(cudaSetDevice(c->device));
+    const size_t n = (size_t)n_blocks * 64;
+    // layout of the scratch: in (fp64 or int16) | out (fp64 or int16) | table
+    int rc;
+    if ((rc = ensure(c, c->planes, n * 16 + 512))) return rc;
+    char* base = (char*)c->planes.p;
+    double* d_in = (double*)base;
+    double* d_out = (double*)(base + n * 8);
+    double* d_tab = (double*)(base + n * 16);
+    cudaStream_t s = c->stream;
+    if (in_is_q) JDS_CUDA(cudaMemcpyAsync(d_in, in_q, n * 2, cudaMemcpyHostToDevice, s));
+    else JDS_CUDA(cudaMemcpyAsync(d_in, in, n * 8, cudaMemcpyHostToDevice, s));
+    if (needs_q) JDS_CUDA(cudaMemcpyAsync(d_tab, qtable, 512, cudaMemcpyHostToDevice, s));
+    launch_block_ops(op, n_blocks, d_in, (const int16_t*)d_in, d_tab, d_out, (int16_t*)d_out, s);
+    c->launches++;
+    JDS_CUDA(cudaGetLastError());
+    if (out_is_q) JDS_CUDA(cudaMemcpyAsync(out_q, d_out, n * 2, cudaMemcpyDeviceToHost, s));
+    else JDS_CUDA(cudaMemcpyAsync(out, d_out, n * 8, cudaMemcpyDeviceToHost, s));
+    JDS_CUDA(cudaStreamSynchronize(s));
+    return JDS_OK;
+}

@@ -313,6 +313,62 @@ __global__ void k_selected_block(Geom g, const uint8_t* __restrict__ rgb, int bx
 }
 
 // ------------------------------------------------------------------------------
+// stand-alone 8x8 block operators of engines/dct_engine.py:7-27 and
+// engines/quantizer.py:22-29, exact arithmetic, one block per thread
+// ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_block_ops(int op, long long n_blocks, const double* __restrict__ in,
+            const int16_t* __restrict__ in_q, const double* __restrict__ qtable,
+            double* __restrict__ out, int16_t* __restrict__ out_q) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    typedef Exact P;
+    double v[64];
+    if (op == JDS_BLOCKOP_DEQUANTIZE) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) out[b * 64 + i] = P::mul((double)in_q[b * 64 + i], qtable[i]);
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < 64; ++i) v[i] = in[b * 64 + i];
+    if (op == JDS_BLOCKOP_QUANTIZE) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) out_q[b * 64 + i] = (int16_t)(int)P::rint_(P::div(v[i], qtable[i]));
+        return;
+    }
+    const bool forward = (op == JDS_BLOCKOP_DCT2 || op == JDS_BLOCKOP_ENCODE);
+    if (op == JDS_BLOCKOP_ENCODE) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) v[i] = P::sub(v[i], 128.0);
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        double t[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) t[r] = v[r * 8 + c];
+        if (forward) dct8_ref<P>(t, 0.0625); else idct8_ref<P>(t, 0.0625);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) v[r * 8 + c] = t[r];
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        if (forward) dct8_ref<P>(v + r * 8, 1.0); else idct8_ref<P>(v + r * 8, 1.0);
+    }
+    if (op == JDS_BLOCKOP_DECODE) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) v[i] = P::clamp255(P::add(v[i], 128.0));
+    }
+#pragma unroll
+    for (int i = 0; i < 64; ++i) out[b * 64 + i] = v[i];
+}
+
+void launch_block_ops(int op, long long n_blocks, const double* in, const int16_t* in_q,
+                      const double* qtable, double* out, int16_t* out_q, cudaStream_t s) {
+    const unsigned grid = (unsigned)((n_blocks + 127) / 128);
+    k_block_ops<<<grid, 128, 0, s>>>(op, n_blocks, in, in_q, qtable, out, out_q);
+}
+
+// ------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------
 template <class P>
