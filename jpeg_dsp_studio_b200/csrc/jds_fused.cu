@@ -237,22 +237,41 @@ k_fast_chroma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
     // accumulated on top of 2^23's bit pattern so the fp32 value is one FADD away
     constexpr int C_ROWS = CA_BY * 8, C_SEGS = CA_BX;
     const float ks = (SUB == 2) ? 0.25f : 0.5f;
-    for (int task = tid; task < C_ROWS * C_SEGS; task += CA_NT) {
-        const int cr = task / C_SEGS, seg = task % C_SEGS;
-        if (cr * VS < n_rows && seg * 16 < n_px) {
-            uint32_t w[VS][12];
+    // thread t owns segment t%16 of chroma rows t/16 + 8k, k = 0..3; the loads of two tasks
+    // are in flight at a time (software prefetch, 2 x VS x 3 sixteen-byte loads)
+    constexpr int NTASK = C_ROWS * C_SEGS / CA_NT;                 // 4
+    const int seg = tid & 15, crbase = tid >> 4;
+    const bool seg_ok = seg * 16 < n_px;
+    uint4 ld[2][VS][3];
+    auto fetch = [&](int k, uint4 (&dst)[VS][3]) {
+        const int cr = crbase + 8 * k;
+        if (seg_ok && cr * VS < n_rows) {
 #pragma unroll
             for (int v = 0; v < VS; ++v) {
                 // 48 contiguous bytes per thread, consecutive threads contiguous: the three
                 // 16-byte loads of a warp cover whole 128-byte lines between them
                 const uint4* q = reinterpret_cast<const uint4*>(
                     in + ((size_t)(y0 + cr * VS + v) * g.W + x0 + seg * 16) * 3);
+                dst[v][0] = __ldg(q);
+                dst[v][1] = __ldg(q + 1);
+                dst[v][2] = __ldg(q + 2);
+            }
+        }
+    };
+    fetch(0, ld[0]);
+#pragma unroll
+    for (int k = 0; k < NTASK; ++k) {
+        if (k + 1 < NTASK) fetch(k + 1, ld[(k + 1) & 1]);
+        const int cr = crbase + 8 * k;
+        if (seg_ok && cr * VS < n_rows) {
+            uint32_t w[VS][12];
+#pragma unroll
+            for (int v = 0; v < VS; ++v)
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
-                    const uint4 a = __ldg(q + i);
+                    const uint4 a = ld[k & 1][v][i];
                     w[v][4 * i] = a.x; w[v][4 * i + 1] = a.y; w[v][4 * i + 2] = a.z; w[v][4 * i + 3] = a.w;
                 }
-            }
             float cb[8], crr[8];
 #pragma unroll
             for (int gq = 0; gq < 4; ++gq) {        // 12-byte group = 4 pixels = 2 chroma samples
@@ -412,33 +431,48 @@ k_fast_luma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
     load_tables(tables + (size_t)unit * table_stride, sm.fq, sm.dq, tid, LU_NT);
 
     // ---- RGB -> level-shifted Y, block layout: a task = one row x 16 pixels ----------
-    for (int task = tid; task < LU_TH * (LU_TW / 16); task += LU_NT) {
-        const int r = task / (LU_TW / 16), seg = task % (LU_TW / 16);
-        if (r < n_rows && seg * 16 < n_px) {
-            const uint4* q = reinterpret_cast<const uint4*>(
-                in + ((size_t)(y0 + r) * g.W + x0 + seg * 16) * 3);
-            uint32_t w[12];
+    // thread t owns segment t%16 of rows t/16 + 8k, k = 0..3; all twelve 16-byte loads are
+    // issued before the first use so the DRAM / L2 latency is paid once
+    {
+        constexpr int NTASK = LU_TH * (LU_TW / 16) / LU_NT;        // 4
+        const int seg = tid & 15, rbase = tid >> 4;
+        const bool seg_ok = seg * 16 < n_px;
+        uint4 ld[NTASK][3];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const uint4 a = __ldg(q + i);
-                w[4 * i] = a.x; w[4 * i + 1] = a.y; w[4 * i + 2] = a.z; w[4 * i + 3] = a.w;
+        for (int k = 0; k < NTASK; ++k) {
+            const int r = rbase + 8 * k;
+            if (seg_ok && r < n_rows) {
+                const uint4* q = reinterpret_cast<const uint4*>(
+                    in + ((size_t)(y0 + r) * g.W + x0 + seg * 16) * 3);
+                ld[k][0] = __ldg(q);
+                ld[k][1] = __ldg(q + 1);
+                ld[k][2] = __ldg(q + 2);
             }
-            float yv[16];
+        }
 #pragma unroll
-            for (int gq = 0; gq < 4; ++gq) {
-                const uint32_t w0 = w[3 * gq], w1 = w[3 * gq + 1], w2 = w[3 * gq + 2];
-                yv[4 * gq + 0] = fmaf(0.299f, f_byte_centered<0>(w0), fmaf(0.587f, f_byte_centered<1>(w0), 0.114f * f_byte_centered<2>(w0)));
-                yv[4 * gq + 1] = fmaf(0.299f, f_byte_centered<3>(w0), fmaf(0.587f, f_byte_centered<0>(w1), 0.114f * f_byte_centered<1>(w1)));
-                yv[4 * gq + 2] = fmaf(0.299f, f_byte_centered<2>(w1), fmaf(0.587f, f_byte_centered<3>(w1), 0.114f * f_byte_centered<0>(w2)));
-                yv[4 * gq + 3] = fmaf(0.299f, f_byte_centered<1>(w2), fmaf(0.587f, f_byte_centered<2>(w2), 0.114f * f_byte_centered<3>(w2)));
+        for (int k = 0; k < NTASK; ++k) {
+            const int r = rbase + 8 * k;
+            if (seg_ok && r < n_rows) {
+                const uint32_t w[12] = {ld[k][0].x, ld[k][0].y, ld[k][0].z, ld[k][0].w,
+                                        ld[k][1].x, ld[k][1].y, ld[k][1].z, ld[k][1].w,
+                                        ld[k][2].x, ld[k][2].y, ld[k][2].z, ld[k][2].w};
+                float yv[16];
+#pragma unroll
+                for (int gq = 0; gq < 4; ++gq) {
+                    const uint32_t w0 = w[3 * gq], w1 = w[3 * gq + 1], w2 = w[3 * gq + 2];
+                    yv[4 * gq + 0] = fmaf(0.299f, f_byte_centered<0>(w0), fmaf(0.587f, f_byte_centered<1>(w0), 0.114f * f_byte_centered<2>(w0)));
+                    yv[4 * gq + 1] = fmaf(0.299f, f_byte_centered<3>(w0), fmaf(0.587f, f_byte_centered<0>(w1), 0.114f * f_byte_centered<1>(w1)));
+                    yv[4 * gq + 2] = fmaf(0.299f, f_byte_centered<2>(w1), fmaf(0.587f, f_byte_centered<3>(w1), 0.114f * f_byte_centered<0>(w2)));
+                    yv[4 * gq + 3] = fmaf(0.299f, f_byte_centered<1>(w2), fmaf(0.587f, f_byte_centered<2>(w2), 0.114f * f_byte_centered<3>(w2)));
+                }
+                const int blk = (r >> 3) * LU_BX + seg * 2, ry = r & 7;
+                float4* p0 = reinterpret_cast<float4*>(&sm.plane[blk][ry * 8]);
+                float4* p1 = reinterpret_cast<float4*>(&sm.plane[blk + 1][ry * 8]);
+                p0[0] = make_float4(yv[0], yv[1], yv[2], yv[3]);
+                p0[1] = make_float4(yv[4], yv[5], yv[6], yv[7]);
+                p1[0] = make_float4(yv[8], yv[9], yv[10], yv[11]);
+                p1[1] = make_float4(yv[12], yv[13], yv[14], yv[15]);
             }
-            const int blk = (r >> 3) * LU_BX + seg * 2, ry = r & 7;
-            float4* p0 = reinterpret_cast<float4*>(&sm.plane[blk][ry * 8]);
-            float4* p1 = reinterpret_cast<float4*>(&sm.plane[blk + 1][ry * 8]);
-            p0[0] = make_float4(yv[0], yv[1], yv[2], yv[3]);
-            p0[1] = make_float4(yv[4], yv[5], yv[6], yv[7]);
-            p1[0] = make_float4(yv[8], yv[9], yv[10], yv[11]);
-            p1[1] = make_float4(yv[12], yv[13], yv[14], yv[15]);
         }
     }
     __syncthreads();

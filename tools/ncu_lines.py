@@ -50,13 +50,17 @@ def disasm_lines(lib, kernel):
 def main():
     rep, lib, kernel = sys.argv[1:4]
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+    dis_key = sys.argv[5] if len(sys.argv) > 5 else kernel      # mangled-name substring for nvdisasm
     csvtxt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", f"regex:{kernel}"],
                             capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(csvtxt)))
+    # the first kernel block only: header at row 1, a new "Kernel Name" row starts the next
+    end = next((i for i, r in enumerate(rows[2:], 2) if r and r[0] == "Kernel Name"), len(rows))
+    rows = rows[:end]
     hdr = rows[1]
     iS, iI, iW = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("Warp Stall Sampling (All Samples)")
-    sass = [(r[iS].strip(), int(r[iI] or 0), int(r[iW] or 0)) for r in rows[2:] if len(r) > iW and r[iI].isdigit()]
-    dis = disasm_lines(lib, kernel)
+    sass = [(r[iS].strip(), int(r[iI] or 0), int(r[iW] or 0)) for r in rows[2:] if len(r) > max(iW, iI) and r[iI].isdigit()]
+    dis = disasm_lines(lib, dis_key)
     if len(dis) != len(sass):
         print(f"warning: {len(dis)} disassembled vs {len(sass)} profiled instructions (library rebuilt?)")
     per = collections.defaultdict(lambda: [0, 0])
