@@ -217,6 +217,12 @@ def test_properties_at_full_size(J):
 # fused fast-mode kernels (jds_fused.cu + jds_ssim.cu)
 # ---------------------------------------------------------------------------------
 FUSED_CASES = [
+    ("rand_16x16_420", lambda: CS.rand_rgb(31, 16, 16), 50, "4:2:0"),
+    ("rand_8x16_444", lambda: CS.rand_rgb(32, 8, 16), 70, "4:4:4"),
+    ("rand_8x32_422", lambda: CS.rand_rgb(33, 8, 32), 30, "4:2:2"),
+    ("rand_16x1040_420", lambda: CS.rand_rgb(34, 16, 1040), 60, "4:2:0"),
+    ("rand_1048x16_422", lambda: CS.rand_rgb(35, 1048, 16), 45, "4:2:2"),
+    ("rand_136x528_444", lambda: CS.rand_rgb(36, 136, 528), 85, "4:4:4"),
     ("rand_64x64_444", lambda: CS.rand_rgb(21, 64, 64), 50, "4:4:4"),
     ("rand_64x64_420", lambda: CS.rand_rgb(21, 64, 64), 50, "4:2:0"),
     ("rand_72x48_422", lambda: CS.rand_rgb(22, 72, 48), 35, "4:2:2"),
