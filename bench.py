@@ -357,6 +357,17 @@ def run_ours(args):
     achieved = alg_bytes / (dom_ms / 1e3) / 1e9
     path_gbs = alg_bytes_step / (kern_ms_step / 1e3) / 1e9
     kern_ms_step_x = sum(v["ms"] for v in stages_x.values()) / Kx
+    # DRAM traffic of the dominant kernel from the committed ncu capture (per pixel, scaled
+    # to the pixels of one launch here); null when no capture exists for that kernel
+    traffic, traffic_src = None, None
+    kmap = {"ssim": "k_ssim_strip", "block_codec": "k_fast_luma", "forward_colour": "k_fast_chroma"}
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        per_px = tj[kmap[dom]]["dram_bytes_per_pixel"]
+        traffic = round(per_px * px_per_step / launches_per_step, 0)
+        traffic_src = tj["source"]
+    except Exception:
+        pass
     cpu = cpu_baseline_sample(2)
     o0 = outs[0]
     line = {
@@ -377,7 +388,7 @@ def run_ours(args):
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                     "frac": round(achieved / peak, 4), "traffic": None,
+                     "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
                      "kernel": dom, "kernel_ms_per_launch": round(dom_ms, 4),
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes,

@@ -35,26 +35,34 @@ def generate_gradient(size: int = 512) -> np.ndarray:
     return np.clip(img, 0, 255).astype(np.uint8)
 
 
+def _bar_runs(first: int, unit: int, gap: int):
+    """Start offsets and thicknesses of the four bars (unit, unit/2, unit/4, 2 px)."""
+    runs, pos = [], first
+    for t in (unit, unit // 2, unit // 4, 2):
+        runs.append((pos, t))
+        pos += t + gap
+    return runs
+
+
 def generate_text_edges(size: int = 512) -> np.ndarray:
-    """Sharp bars and a diagonal on a light background."""
-    img = np.ones((size, size, 3), dtype=np.uint8) * 245
-    margin = size // 10
-    bar_height = size // 16
-    dark = [25, 25, 25]
-    y = margin
-    for thickness in [bar_height, bar_height // 2, bar_height // 4, 2]:
-        img[y:y + thickness, margin:size - margin] = dark
-        y += thickness + margin // 2
-    x = margin
-    for thickness in [bar_height, bar_height // 2, bar_height // 4, 2]:
-        img[size // 2 + margin:size - margin, x:x + thickness] = dark
-        x += thickness + margin // 2
-    for i in range(size // 4):
-        y_pos = size // 2 + margin + i
-        x_pos = size // 2 + i
-        if y_pos < size - margin and x_pos < size - margin:
-            img[y_pos:y_pos + 3, x_pos:x_pos + 3] = dark
-    return img
+    """Dark (25) bars of shrinking thickness - four horizontal in the upper half, four
+    vertical in the lower half - and a 3-px diagonal, on a light (245) background."""
+    m = size // 10                      # margin
+    dark = np.zeros((size, size), dtype=bool)
+    for y, t in _bar_runs(m, size // 16, m // 2):
+        dark[y:y + t, m:size - m] = True
+    for x, t in _bar_runs(m, size // 16, m // 2):
+        dark[size // 2 + m:size - m, x:x + t] = True
+    i = np.arange(size // 4)
+    yy, xx = size // 2 + m + i, size // 2 + i
+    ok = (yy < size - m) & (xx < size - m)
+    for dy in range(3):
+        for dx in range(3):
+            r, c = yy[ok] + dy, xx[ok] + dx
+            keep = (r < size) & (c < size)
+            dark[r[keep], c[keep]] = True
+    img = np.where(dark[..., None], np.uint8(25), np.uint8(245))
+    return np.ascontiguousarray(np.broadcast_to(img, (size, size, 3)), dtype=np.uint8)
 
 
 _CHROMA_BARS = np.array([
@@ -132,15 +140,11 @@ def generate_photo(size: int = 512) -> np.ndarray:
     return np.clip(img, 0, 255).astype(np.uint8)
 
 
+_DEMO = {"photo": generate_photo, "text_edges": generate_text_edges, "gradient": generate_gradient,
+         "checkerboard": generate_colored_checkerboard, "chroma_stripes": generate_chroma_stripes}
+
+
 def generate_demo_image(key: str):
-    """Demo image by key (512 px), ``None`` for an unknown key."""
-    generators = {
-        "photo": lambda: generate_photo(512),
-        "text_edges": lambda: generate_text_edges(512),
-        "gradient": lambda: generate_gradient(512),
-        "checkerboard": lambda: generate_colored_checkerboard(512),
-        "chroma_stripes": lambda: generate_chroma_stripes(512),
-    }
-    if key in generators:
-        return generators[key]()
-    return None
+    """512-px demo image by key; ``None`` for a key the GUI does not know."""
+    make = _DEMO.get(key)
+    return make(512) if make else None
