@@ -412,15 +412,87 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_sweep(args):
+    """--workload sweep: BASELINE.json config 4 - a 100-point quality sweep (Q=1..100) of one
+    4K frame, 4:2:0, points sharded round-robin over the ranks (STRONG scaling: total work
+    fixed), one all_gather of the metric records per sweep.  value = sweep points x pixels
+    per second, whole job."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    os.environ.setdefault("JDS_SCRATCH_MB", "8192")
+    import jpeg_dsp_studio_b200 as J
+    from jpeg_dsp_studio_b200 import distributed as D
+    eng = J.Engine(local)
+    stream = torch.cuda.current_stream(dev)
+    eng.use_stream(stream.cuda_stream)
+    img = np.random.default_rng(4).integers(0, 256, (H, W, 3), dtype=np.uint8)
+    d_img = torch.from_numpy(img).to(dev)
+    qs = list(range(1, 101))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step():
+        return D.sweep_sharded(eng, d_img, qs, MODE, PREFILTER, precision="fast", device=dev)
+
+    K, Wm = args.steps, max(args.warmup, 3)
+    for _ in range(Wm):
+        table = step()
+    barrier()
+    l0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(K):
+        table = step()
+    e1.record(stream)
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    if rank == 0:
+        px = len(qs) * H * W
+        line = {
+            "metric": "4K round-trip Mpixel/s (incl. PSNR/SSIM/bpp)", "value": round(px * K / (ms / 1e3) / 1e6, 2),
+            "unit": "Mpixel/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": round(ms / K, 4),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "100-point quality sweep Q=1..100 of one random 4K frame, 4:2:0, "
+                                   "fast fp32 mode, metrics only (BASELINE config 4)",
+                       "sharding": "sweep points round-robin over ranks; one all_gather of the records"},
+            "gpu_launches": eng.launch_count() - l0,
+            "rd_table_sample": {"q10": table[9], "q50": table[49], "q90": table[89]},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="batch", choices=["batch", "sweep"],
+                    help="batch = the headline (8 x 4K frames per GPU, weak scaling); "
+                         "sweep = BASELINE config 4 (100-point sweep, strong scaling)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "sweep":
+        run_sweep(args)
     else:
         run_ours(args)
 

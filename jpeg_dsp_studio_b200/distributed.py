@@ -33,6 +33,38 @@ def record_from_metrics(unit: int, quality: int, m) -> np.ndarray:
                      float(m.total_coeffs), float(m.luma_blocks)], dtype=np.float64)
 
 
+#: numpy view of a ctypes array of jds_metrics (include/jds.h), for vectorised record building
+METRICS_DTYPE = np.dtype([("sse_rgb", "<u8"), ("sse_y", "<f8"), ("ssim_sum", "<f8", (4,)),
+                          ("ssim_count", "<u8"), ("coeff_bits", "<u8"), ("nnz", "<u8"),
+                          ("total_coeffs", "<u8"), ("luma_blocks", "<u8"), ("hist50", "<i8", (50,)),
+                          ("gpu_ms", "<f8"), ("reserved", "<u8", (3,))])
+
+
+def records_from_outputs(units, qualities, outs) -> np.ndarray:
+    """(n, F) fp64 rows for a list of RoundTripOutputs of one call.  When the outputs share
+    one ctypes array of jds_metrics (the Engine's batch / sweep calls) the rows are built
+    from a zero-copy numpy view of it."""
+    n = len(outs)
+    if n == 0:
+        return np.zeros((0, len(RECORD_FIELDS)))
+    arr = getattr(outs[0], "metrics_array", None)
+    if arr is None:
+        return np.stack([record_from_metrics(u, q, o.metrics) for u, q, o in zip(units, qualities, outs)])
+    m = np.frombuffer(arr, dtype=METRICS_DTYPE, count=n)
+    rows = np.empty((n, len(RECORD_FIELDS)), dtype=np.float64)
+    rows[:, 0] = units
+    rows[:, 1] = qualities
+    rows[:, 2] = m["sse_rgb"]
+    rows[:, 3] = m["sse_y"]
+    rows[:, 4:8] = m["ssim_sum"]
+    rows[:, 8] = m["ssim_count"]
+    rows[:, 9] = m["coeff_bits"]
+    rows[:, 10] = m["nnz"]
+    rows[:, 11] = m["total_coeffs"]
+    rows[:, 12] = m["luma_blocks"]
+    return rows
+
+
 def scalars_from_record(rec: np.ndarray, height: int, width: int) -> dict:
     """The reference's result floats from a gathered record (utils/metrics.py formulas)."""
     from .utils.metrics import psnr_from_sse
@@ -74,10 +106,12 @@ def gather_records(local: np.ndarray, n_units: int, device=None) -> np.ndarray:
         import torch
         world = dist.get_world_size()
         cap = (n_units + world - 1) // world                 # rows per rank, padded
-        buf = torch.full((cap, nf), -1.0, dtype=torch.float64, device=device)
-        if len(local):
-            buf[:len(local)] = torch.from_numpy(local).to(buf.device)
-        out = torch.empty((world * cap, nf), dtype=torch.float64, device=device)
+        padded = np.full((cap, nf), -1.0, dtype=np.float64)
+        padded[:len(local)] = local
+        buf = torch.from_numpy(padded)
+        if device is not None:
+            buf = buf.to(device, non_blocking=True)
+        out = torch.empty((world * cap, nf), dtype=torch.float64, device=buf.device)
         dist.all_gather_into_tensor(out, buf)
         table = out.cpu().numpy()
         table = table[table[:, 0] >= 0]
@@ -111,8 +145,9 @@ def sweep_sharded(engine, image, qualities: Sequence[int], mode="4:2:0", prefilt
     mine = shard_indices(len(qs), rank, world)
     rows = np.zeros((0, len(RECORD_FIELDS)))
     if mine:
-        outs = engine.sweep(image, [qs[i] for i in mine], mode, prefilter, precision=precision)
-        rows = np.stack([record_from_metrics(i, qs[i], o.metrics) for i, o in zip(mine, outs)])
+        my_qs = [qs[i] for i in mine]
+        outs = engine.sweep(image, my_qs, mode, prefilter, precision=precision)
+        rows = records_from_outputs(mine, my_qs, outs)
     table = gather_records(rows, len(qs), device=device)
     h, w = image.shape[0], image.shape[1]
     return [scalars_from_record(r, h, w) for r in table]

@@ -26,11 +26,12 @@ class RoundTripOutputs:
     bpp / compression ratio ... computed from the partials with the reference's final
     formulas) is evaluated on first access."""
 
-    __slots__ = ("recon", "coeffs", "err_y", "err_rgb", "metrics", "_hw", "_scalars")
+    __slots__ = ("recon", "coeffs", "err_y", "err_rgb", "metrics", "metrics_array", "_hw", "_scalars")
 
-    def __init__(self, recon, coeffs, err_y, err_rgb, metrics, hw):
+    def __init__(self, recon, coeffs, err_y, err_rgb, metrics, hw, metrics_array=None):
         self.recon, self.coeffs, self.err_y, self.err_rgb = recon, coeffs, err_y, err_rgb
         self.metrics, self._hw, self._scalars = metrics, hw, None
+        self.metrics_array = metrics_array      # the call's whole ctypes array of jds_metrics
 
     @property
     def scalars(self) -> dict:
@@ -233,7 +234,7 @@ class Engine:
                                                   gp(coeffs), loc, ms))
         return [RoundTripOutputs(recon[i] if recon is not None else None,
                                  coeffs[i] if coeffs is not None else None, None, None, ms[i],
-                                 (h, w)) for i in range(n)]
+                                 (h, w), ms) for i in range(n)]
 
     # -- quality sweep (BASELINE config 4; gui/worker.py:55-74) -------------------------
     def sweep(self, image, qualities: Sequence[int], mode="4:2:0", prefilter=False, *,
@@ -262,7 +263,7 @@ class Engine:
         with self._lock:
             N.check(self._lib.jds_sweep(self._ctx, C.byref(p), qarr, nq, ptr, loc, rp, loc, ms))
         return [RoundTripOutputs(recon[i] if recon is not None else None, None, None, None, ms[i],
-                                 (h, w)) for i in range(nq)]
+                                 (h, w), ms) for i in range(nq)]
 
 
 _engines = {}

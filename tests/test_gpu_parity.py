@@ -322,3 +322,20 @@ def test_fused_batch_and_sweep_consistency(J):
         assert np.array_equal(o.recon, single.recon)
         assert o.scalars["estimated_bits"] == single.scalars["estimated_bits"]
         assert o.metrics.sse_rgb == single.metrics.sse_rgb
+
+
+def test_sweep_sharded_single_rank_equals_engine_sweep(J):
+    """distributed.sweep_sharded at world size 1 (zero-copy record path) returns the same
+    scalars as Engine.sweep."""
+    from jpeg_dsp_studio_b200 import distributed as D
+    img = CS.rand_rgb(55, 144, 208)
+    eng = J.get_engine()
+    qs = [3, 25, 50, 75, 97]
+    table = D.sweep_sharded(eng, img, qs, "4:2:0", False, precision="fast")
+    outs = eng.sweep(img, qs, "4:2:0", False, precision="fast")
+    for t, o, q in zip(table, outs, qs):
+        assert t["quality"] == q
+        for k in ("psnr_rgb", "psnr_y", "ssim_rgb", "ssim_y", "bpp", "estimated_bits",
+                  "nonzero_count", "total_coeffs"):
+            a, b = t[k], o.scalars[k]
+            assert a == b or abs(a - b) <= 1e-12 * max(abs(a), abs(b)), (q, k, a, b)
