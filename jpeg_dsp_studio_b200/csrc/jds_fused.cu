@@ -738,9 +738,20 @@ bool fused_supported(const Geom& g, int prefilter, const void* rgb, size_t rgb_s
 
 size_t fused_chroma_plane_floats(const Geom& g) { return g.sub ? (size_t)2 * g.plane_c : 0; }
 
+// opt in to > 48 KB dynamic shared memory once per kernel instantiation and device
 template <class K>
 static cudaError_t set_smem(K kernel, size_t bytes) {
-    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    static unsigned long long done_mask = 0;          // one static per instantiation of K... per kernel pointer below
+    static K done_kernel = nullptr;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (done_kernel == kernel && (done_mask >> (dev & 63)) & 1ull) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) {
+        if (done_kernel != kernel) { done_kernel = kernel; done_mask = 0; }
+        done_mask |= 1ull << (dev & 63);
+    }
+    return e;
 }
 
 cudaError_t launch_fused_chroma(const Geom& g, const uint8_t* rgb, size_t rgb_stride,

@@ -400,9 +400,15 @@ cudaError_t launch_ssim_strip(int H, int W, const uint8_t* a, size_t a_stride, c
                               bool want_sse, int sm_count, cudaStream_t s) {
     const size_t smem = sizeof(SsimSmem);
     {
-        cudaError_t e = cudaFuncSetAttribute(k_ssim_strip, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
-        if (e != cudaSuccess) return e;
+        static unsigned long long done_mask = 0;      // per device: the attribute is set once
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!((done_mask >> (dev & 63)) & 1ull)) {
+            cudaError_t e = cudaFuncSetAttribute(k_ssim_strip, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)smem);
+            if (e != cudaSuccess) return e;
+            done_mask |= 1ull << (dev & 63);
+        }
     }
     const int strips = (W + S_OW - 1) / S_OW;
     // vertical segments: enough CTAs to fill the machine (3 per SM x ~3 waves), but at

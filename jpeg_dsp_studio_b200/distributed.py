@@ -65,26 +65,31 @@ def records_from_outputs(units, qualities, outs) -> np.ndarray:
     return rows
 
 
-def scalars_from_record(rec: np.ndarray, height: int, width: int) -> dict:
-    """The reference's result floats from a gathered record (utils/metrics.py formulas)."""
-    from .utils.metrics import psnr_from_sse
-    f = dict(zip(RECORD_FIELDS, rec.tolist()))
+def scalars_from_table(table: np.ndarray, height: int, width: int) -> List[dict]:
+    """The reference's result floats for every row of a gathered table at once
+    (utils/metrics.py formulas, vectorised: one NumPy expression per field)."""
+    t = np.asarray(table, dtype=np.float64).reshape(-1, len(RECORD_FIELDS))
+    f = {k: t[:, i] for i, k in enumerate(RECORD_FIELDS)}
     n_px = height * width
-    bits = 2 * int(f["luma_blocks"]) + int(f["coeff_bits"])
-    cnt = f["ssim_count"]
-    out = {
-        "quality": int(f["quality"]),
-        "psnr_rgb": psnr_from_sse(f["sse_rgb"], 3 * n_px),
-        "psnr_y": psnr_from_sse(f["sse_y"], n_px),
-        "ssim_rgb": float(np.mean([f["ssim_r"], f["ssim_g"], f["ssim_b"]]) / cnt) if cnt else float("nan"),
-        "ssim_y": float(f["ssim_y"] / cnt) if cnt else float("nan"),
-        "estimated_bits": bits,
-        "bpp": float(bits / n_px),
-        "compression_ratio": float(n_px * 24 / max(bits, 1)),
-        "nonzero_count": int(f["nnz"]),
-        "total_coeffs": int(f["total_coeffs"]),
-    }
-    return out
+    with np.errstate(divide="ignore", invalid="ignore"):
+        psnr_rgb = 10 * np.log10((255.0 ** 2) / (f["sse_rgb"] / np.float64(3 * n_px)))
+        psnr_y = 10 * np.log10((255.0 ** 2) / (f["sse_y"] / np.float64(n_px)))
+        cnt = f["ssim_count"]
+        ssim_rgb = np.where(cnt > 0, (np.stack([f["ssim_r"], f["ssim_g"], f["ssim_b"]]) / cnt).mean(axis=0), np.nan)
+        ssim_y = np.where(cnt > 0, f["ssim_y"] / cnt, np.nan)
+    bits = (2 * f["luma_blocks"] + f["coeff_bits"]).astype(np.int64)
+    bpp = bits / n_px
+    ratio = (n_px * 24) / np.maximum(bits, 1)
+    return [{"quality": int(f["quality"][i]), "psnr_rgb": float(psnr_rgb[i]), "psnr_y": float(psnr_y[i]),
+             "ssim_rgb": float(ssim_rgb[i]), "ssim_y": float(ssim_y[i]), "estimated_bits": int(bits[i]),
+             "bpp": float(bpp[i]), "compression_ratio": float(ratio[i]),
+             "nonzero_count": int(f["nnz"][i]), "total_coeffs": int(f["total_coeffs"][i])}
+            for i in range(len(t))]
+
+
+def scalars_from_record(rec: np.ndarray, height: int, width: int) -> dict:
+    """One row (see scalars_from_table)."""
+    return scalars_from_table(np.asarray(rec).reshape(1, -1), height, width)[0]
 
 
 def _dist():
@@ -94,9 +99,14 @@ def _dist():
     return None
 
 
+_gather_cache = {}
+
+
 def gather_records(local: np.ndarray, n_units: int, device=None) -> np.ndarray:
     """All-gather of per-unit records: every rank returns the (n_units, F) table ordered
-    by unit.  ``local``: (n_local, F) rows whose first column is the unit index."""
+    by unit.  ``local``: (n_local, F) rows whose first column is the unit index.  Staging
+    buffers (pinned host + device) are cached per (world, capacity, device): one H2D, one
+    collective, one D2H, one synchronisation."""
     dist = _dist()
     nf = len(RECORD_FIELDS)
     local = np.asarray(local, dtype=np.float64).reshape(-1, nf)
@@ -106,14 +116,30 @@ def gather_records(local: np.ndarray, n_units: int, device=None) -> np.ndarray:
         import torch
         world = dist.get_world_size()
         cap = (n_units + world - 1) // world                 # rows per rank, padded
-        padded = np.full((cap, nf), -1.0, dtype=np.float64)
-        padded[:len(local)] = local
-        buf = torch.from_numpy(padded)
-        if device is not None:
-            buf = buf.to(device, non_blocking=True)
-        out = torch.empty((world * cap, nf), dtype=torch.float64, device=buf.device)
-        dist.all_gather_into_tensor(out, buf)
-        table = out.cpu().numpy()
+        key = (world, cap, str(device))
+        bufs = _gather_cache.get(key)
+        if bufs is None:
+            on_gpu = device is not None and torch.device(device).type == "cuda"
+            h_in = torch.empty((cap, nf), dtype=torch.float64)
+            h_out = torch.empty((world * cap, nf), dtype=torch.float64)
+            if on_gpu:
+                h_in, h_out = h_in.pin_memory(), h_out.pin_memory()
+                d_in = torch.empty((cap, nf), dtype=torch.float64, device=device)
+                d_out = torch.empty((world * cap, nf), dtype=torch.float64, device=device)
+            else:
+                d_in, d_out = h_in, h_out
+            bufs = _gather_cache[key] = (h_in, h_out, d_in, d_out, on_gpu)
+        h_in, h_out, d_in, d_out, on_gpu = bufs
+        hv = h_in.numpy()
+        hv[:] = -1.0
+        hv[:len(local)] = local
+        if on_gpu:
+            d_in.copy_(h_in, non_blocking=True)
+        dist.all_gather_into_tensor(d_out, d_in)
+        if on_gpu:
+            h_out.copy_(d_out, non_blocking=True)
+            torch.cuda.current_stream(d_out.device).synchronize()
+        table = h_out.numpy().copy()
         table = table[table[:, 0] >= 0]
     order = np.argsort(table[:, 0], kind="stable")
     table = table[order]
@@ -150,7 +176,7 @@ def sweep_sharded(engine, image, qualities: Sequence[int], mode="4:2:0", prefilt
         rows = records_from_outputs(mine, my_qs, outs)
     table = gather_records(rows, len(qs), device=device)
     h, w = image.shape[0], image.shape[1]
-    return [scalars_from_record(r, h, w) for r in table]
+    return scalars_from_table(table, h, w)
 
 
 def batch_sharded(engine, frames_of_rank, n_total: int, quality=50, mode="4:2:0", prefilter=False, *,
