@@ -339,3 +339,30 @@ def test_sweep_sharded_single_rank_equals_engine_sweep(J):
                   "nonzero_count", "total_coeffs"):
             a, b = t[k], o.scalars[k]
             assert a == b or abs(a - b) <= 1e-12 * max(abs(a), abs(b)), (q, k, a, b)
+
+
+def test_public_sweep_and_batch_api(J, oracle):
+    """quality_sweep / compress_batch (the BatchSweepWorker-shaped and batch entry points of
+    engines/pipeline.py) return CompressionResult objects consistent with single calls."""
+    img = CS.rand_rgb(61, 96, 128)
+    base = J.CompressionParams(subsampling_mode="4:2:2", use_prefilter=True)
+    rd = J.quality_sweep(img, base, range(10, 91, 20), precision="exact", keep_images=True)
+    assert [q for q, _ in rd] == [10, 30, 50, 70, 90]
+    for q, r in rd:
+        ref = oracle.compress_reconstruct(img, q, "4:2:2", True, want_maps=False)
+        assert isinstance(r, J.CompressionResult) and r.original_image is img
+        assert np.array_equal(r.reconstructed_image, ref["reconstructed_image"])
+        assert r.psnr_rgb == ref["psnr_rgb"] and r.nonzero_coeffs == ref["nonzero_coeffs"]
+        assert abs(r.ssim_y - ref["ssim_y"]) <= SSIM_TOL
+    rd_fast = J.quality_sweep(img, base, [50])            # default: fast mode, metrics only
+    assert rd_fast[0][1].reconstructed_image is None
+    assert abs(rd_fast[0][1].psnr_y - rd[2][1].psnr_y) <= PSNR_TOL_DB
+    frames = np.stack([CS.rand_rgb(70 + k, 64, 64) for k in range(3)])
+    res = J.compress_batch(frames, J.CompressionParams(quality=40, subsampling_mode="4:4:4"),
+                           precision="exact")
+    for k, r in enumerate(res):
+        ref = oracle.compress_reconstruct(frames[k], 40, "4:4:4", False, want_maps=False)
+        assert np.array_equal(r.reconstructed_image, ref["reconstructed_image"])
+        assert r.bpp == ref["exact_bits"] / (64 * 64)
+    with pytest.raises(ValueError):
+        J.quality_sweep(img, base, [0, 50])
