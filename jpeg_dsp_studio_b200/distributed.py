@@ -77,11 +77,20 @@ def scalars_from_table(table: np.ndarray, height: int, width: int) -> List[dict]
         cnt = f["ssim_count"]
         ssim_rgb = np.where(cnt > 0, (np.stack([f["ssim_r"], f["ssim_g"], f["ssim_b"]]) / cnt).mean(axis=0), np.nan)
         ssim_y = np.where(cnt > 0, f["ssim_y"] / cnt, np.nan)
-    bits = (2 * f["luma_blocks"] + f["coeff_bits"]).astype(np.int64)
-    bpp = bits / n_px
-    ratio = (n_px * 24) / np.maximum(bits, 1)
+    # bit estimate in the reference's float32 arithmetic (utils/metrics.bitrate_from_partials)
+    exact = (2 * f["luma_blocks"] + f["coeff_bits"]).astype(np.int64)
+    nnz = f["nnz"].astype(np.int64)
+    est32 = (2 * f["luma_blocks"]).astype(np.float32) + \
+        ((6 * nnz).astype(np.float32) + (f["coeff_bits"].astype(np.int64) - 6 * nnz).astype(np.float32))
+    bpp32 = est32 / np.float32(n_px)
+    ratio32 = np.float32(n_px * 24) / np.maximum(est32, np.float32(1))
+    none = nnz == 0                                   # the reference stays in Python ints then
+    bits = np.where(none, exact, est32.astype(np.int64))
+    bpp = np.where(none, exact / n_px, bpp32.astype(np.float64))
+    ratio = np.where(none, (n_px * 24) / np.maximum(exact, 1), ratio32.astype(np.float64))
     return [{"quality": int(f["quality"][i]), "psnr_rgb": float(psnr_rgb[i]), "psnr_y": float(psnr_y[i]),
              "ssim_rgb": float(ssim_rgb[i]), "ssim_y": float(ssim_y[i]), "estimated_bits": int(bits[i]),
+             "exact_bits": int(exact[i]),
              "bpp": float(bpp[i]), "compression_ratio": float(ratio[i]),
              "nonzero_count": int(f["nnz"][i]), "total_coeffs": int(f["total_coeffs"][i])}
             for i in range(len(t))]

@@ -44,20 +44,39 @@ def metrics_from_partials(m, height: int, width: int) -> Dict[str, float]:
 
 def bitrate_from_partials(m, height: int, width: int) -> Dict:
     """``estimate_bitrate_no_entropy`` (utils/metrics.py:51-92) from the exact integer
-    bit count of the device: 2 bits per luma-grid block + 6 position bits and
+    counts of the device: 2 bits per luma-grid block, 6 position bits and
     ``ceil(log2(|v|+1)) + 1`` magnitude bits per non-zero coefficient.
 
-    The reference accumulates the magnitude bits in float32 (``np.log2`` of an int16
-    array under NumPy 2), which rounds totals above 2**24; this returns the exact
-    integer arithmetic (relative difference <= 2e-7)."""
+    The reference does this arithmetic in **float32** under NumPy 2 (``np.log2`` of an
+    int16 array is float32 and Python ints are weak scalars), so ``bpp`` and
+    ``compression_ratio`` carry float32 rounding.  The same float32 operations are applied
+    here to the exact integers: bit-identical results whenever the magnitude-bit total is
+    below 2**24 (every float32 partial sum of the reference is then exact); above that the
+    reference's pairwise float32 summation may differ from the correctly rounded total by
+    a few ulp (relative 2e-7)."""
     num_pixels = height * width
     original_bits = num_pixels * 3 * 8
-    estimated_bits = 2 * int(m.luma_blocks) + int(m.coeff_bits)
+    block_overhead_bits = 2 * int(m.luma_blocks)
+    nnz = int(m.nnz)
+    exact_bits = block_overhead_bits + int(m.coeff_bits)
+    if nnz > 0:
+        magnitude_bits = np.float32(int(m.coeff_bits) - 6 * nnz)       # np.sum(... float32 ...)
+        coeff_bits = np.float32(6 * nnz) + magnitude_bits              # int (weak) + float32
+        estimated = np.float32(block_overhead_bits) + coeff_bits
+        bpp = float(estimated / np.float32(num_pixels))
+        ratio = float(np.float32(original_bits) / max(estimated, np.float32(1)))
+        est_int = int(estimated)
+    else:
+        estimated = block_overhead_bits                                  # stays a Python int
+        bpp = float(estimated / num_pixels)
+        ratio = float(original_bits / max(estimated, 1))
+        est_int = int(estimated)
     return {
-        'estimated_bits': int(estimated_bits),
-        'bpp': float(estimated_bits / num_pixels),
-        'compression_ratio': float(original_bits / max(estimated_bits, 1)),
-        'nonzero_count': int(m.nnz),
+        'estimated_bits': est_int,
+        'exact_bits': exact_bits,
+        'bpp': bpp,
+        'compression_ratio': ratio,
+        'nonzero_count': nnz,
         'total_coeffs': int(m.total_coeffs),
         'label': BITRATE_LABEL,
     }

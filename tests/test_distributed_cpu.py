@@ -103,5 +103,6 @@ def test_sweep_and_batch_sharded_over_two_gloo_ranks():
         o = P.compress_reconstruct(img, t["quality"], "4:2:0", False, want_maps=False)
         assert t["psnr_rgb"] == o["psnr_rgb"]
         assert abs(t["psnr_y"] - o["psnr_y"]) < 1e-9
-        assert t["estimated_bits"] == o["exact_bits"]
+        assert t["exact_bits"] == o["exact_bits"]
+        assert t["bpp"] == o["bpp"] and t["compression_ratio"] == o["compression_ratio"]
         assert t["nonzero_count"] == o["nonzero_coeffs"]

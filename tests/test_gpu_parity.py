@@ -64,7 +64,10 @@ def test_exact_mode_matches_reference_golden(J, name, golden_cases):
     assert res.nonzero_coeffs == g["nonzero_coeffs"]
     assert res.total_coeffs == g["total_coeffs"]
     assert res.bitrate_label == g["bitrate_label"]
-    # exact integer bit count vs the reference's float32-accumulated one
+    # the reference's float32 bit-count arithmetic reproduced from the exact integer counts:
+    # bit-identical below 2**24 bits, within float32 pairwise-summation slack above
+    if 24 * img.shape[0] * img.shape[1] / g["compression_ratio"] < 2 ** 24 - 64:
+        assert res.bpp == g["bpp"] and res.compression_ratio == g["compression_ratio"]
     assert abs(res.bpp - g["bpp"]) <= 2e-7 * g["bpp"]
     assert abs(res.compression_ratio - g["compression_ratio"]) <= 2e-7 * g["compression_ratio"]
     assert res.psnr_rgb == parse_float(g["psnr_rgb"])          # integer SSE -> exact
@@ -363,6 +366,6 @@ def test_public_sweep_and_batch_api(J, oracle):
     for k, r in enumerate(res):
         ref = oracle.compress_reconstruct(frames[k], 40, "4:4:4", False, want_maps=False)
         assert np.array_equal(r.reconstructed_image, ref["reconstructed_image"])
-        assert r.bpp == ref["exact_bits"] / (64 * 64)
+        assert r.bpp == ref["bpp"] and r.compression_ratio == ref["compression_ratio"]
     with pytest.raises(ValueError):
         J.quality_sweep(img, base, [0, 50])

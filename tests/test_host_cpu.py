@@ -119,3 +119,33 @@ def test_metric_finalisation_formulas():
     from oracle.skimage_standin import peak_signal_noise_ratio
     sse = int(np.sum((a.astype(np.int64) - b.astype(np.int64)) ** 2))
     assert psnr_from_sse(sse, a.size) == peak_signal_noise_ratio(a, b, data_range=255)
+
+
+def test_bitrate_finalisation_matches_reference_float32_arithmetic(golden_cases):
+    """utils/metrics.py:63-92 does its arithmetic in float32 under NumPy 2; the host
+    finalisation reproduces bpp / compression_ratio bit for bit from the exact integer
+    counts whenever the total stays below 2**24 bits, and within 2e-7 above."""
+    from types import SimpleNamespace
+    from jpeg_dsp_studio_b200.utils.metrics import bitrate_from_partials
+    from tests import cases as CS
+    n_equal = 0
+    for name, g in golden_cases.items():
+        c = CS.BY_NAME[name]
+        if c.big:
+            continue
+        img = c.image()
+        o = P.compress_reconstruct(img, c.quality, c.mode, c.prefilter, want_metrics=False,
+                                   want_maps=False)
+        h, w = img.shape[:2]
+        blocks = (-(-h // 8)) * (-(-w // 8))
+        m = SimpleNamespace(luma_blocks=blocks, coeff_bits=o["exact_bits"] - 2 * blocks,
+                            nnz=o["nonzero_coeffs"], total_coeffs=o["total_coeffs"])
+        b = bitrate_from_partials(m, h, w)
+        assert b["exact_bits"] == o["exact_bits"]
+        if o["exact_bits"] < 2 ** 24:
+            assert b["bpp"] == g["bpp"], name
+            assert b["compression_ratio"] == g["compression_ratio"], name
+            n_equal += 1
+        else:
+            assert abs(b["bpp"] - g["bpp"]) <= 2e-7 * g["bpp"]
+    assert n_equal >= 15
