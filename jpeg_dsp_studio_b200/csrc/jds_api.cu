@@ -336,7 +336,7 @@ static int launch_chunk(jds_ctx* c, const UnitJob& J, const ChunkPtrs& P, int n,
     // fast mode on block-aligned frames runs the fused kernels (jds_fused.cu); exact
     // mode, prefiltered / ragged frames and the GUI-only outputs (histogram, error
     // maps) run the staged kernels (jds_kernels.cu)
-    const bool fused = !exact && !c->no_fused && !want_hist && !P.d_ey && !P.d_ergb &&
+    const bool fused = !exact && !c->no_fused && !P.d_ey && !P.d_ergb &&
                        fused_supported(g, p->prefilter, P.d_rgb, P.rgb_stride, P.d_recon, frame_bytes) &&
                        ssim_strip_supported(g.H, g.W, P.d_rgb, P.rgb_stride, P.d_recon, frame_bytes);
     if (fused) {
@@ -372,7 +372,7 @@ static int launch_chunk(jds_ctx* c, const UnitJob& J, const ChunkPtrs& P, int n,
         }
         if (timed) JDS_CUDA(cudaEventRecord(evs[1], s));
         launch_codec(exact, g, fwd, fwd_stride, rec, rec_stride, P.d_tables, tstride, P.d_coeffs,
-                     ncoef, want_hist, P.d_metrics, n, s);
+                     ncoef, false, P.d_metrics, n, s);
         if (timed) JDS_CUDA(cudaEventRecord(evs[2], s));
         launch_inverse(exact, g, P.d_rgb, P.rgb_stride, fwd, fwd_stride, rec, rec_stride, P.d_recon,
                        frame_bytes, P.d_ey, P.d_ergb, P.d_metrics, n, s);
@@ -390,6 +390,11 @@ static int launch_chunk(jds_ctx* c, const UnitJob& J, const ChunkPtrs& P, int n,
             }
             c->launches++;
         }
+    }
+    if (want_hist && P.d_coeffs) {
+        // 50-bin histogram from the coefficient buffer just written (both code paths)
+        launch_hist50(P.d_coeffs, ncoef, ncoef, P.d_metrics, n, c->sm_count, s);
+        c->launches++;
     }
     if (timed) JDS_CUDA(cudaEventRecord(evs[4], s));
     JDS_CUDA(cudaGetLastError());
@@ -409,6 +414,7 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
     const size_t planes_elems = (size_t)(g.plane_y + 2 * g.plane_c);
     const size_t ncoef = 64ull * (size_t)(g.nblk_y + 2 * g.nblk_c);
     const bool want_coeffs = (p->outputs & JDS_OUT_COEFFS) && J.coeffs;
+    const bool want_hist = (p->outputs & JDS_OUT_HIST) != 0;
     const bool want_ssim = (p->outputs & JDS_OUT_SSIM) != 0;
     const bool want_recon = (p->outputs & JDS_OUT_RECON) && J.recon;
     const bool want_ey = (p->outputs & JDS_OUT_ERR_Y) && J.err_y;
@@ -423,7 +429,7 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
     // units per chunk: bounded by the scratch budget; with host buffers also small enough
     // that there are several chunks to overlap
     const size_t per_unit = planes_elems * esz * (J.shared_input ? 1 : 2) + frame_bytes * 2 +
-                            (want_coeffs ? ncoef * 2 : 0);
+                            ((want_coeffs || want_hist) ? ncoef * 2 : 0);
     int chunk = (int)(c->scratch_budget / (per_unit ? per_unit : 1));
     if (chunk < 1) chunk = 1;
     if (chunk > J.units) chunk = J.units;
@@ -469,7 +475,10 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
     const size_t coeff_slot = ncoef * 2 * (size_t)chunk;
     if (in_host && (rc = ensure(c, c->in, in_slot * (J.shared_input ? 1 : nbuf)))) return rc;
     if ((!want_recon || out_host) && (rc = ensure(c, c->recon, recon_slot * nbuf))) return rc;
-    if (want_coeffs && out_host && (rc = ensure(c, c->coeffs, coeff_slot * nbuf))) return rc;
+    // the histogram is taken from the coefficient buffer: scratch when the caller wants the
+    // histogram but not the coefficients themselves (or wants them on the host)
+    const bool coeff_scratch = (want_coeffs && out_host) || (want_hist && !want_coeffs);
+    if (coeff_scratch && (rc = ensure(c, c->coeffs, coeff_slot * nbuf))) return rc;
     if ((want_ey || want_ergb) && out_host && (rc = ensure(c, c->errs, (size_t)g.H * g.W * 8 * 2)))
         return rc;
 
@@ -489,7 +498,6 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
     JDS_CUDA(cudaMemsetAsync(d_metrics, 0, sizeof(DevMetrics) * J.units, s));
     if (J.shared_input && in_host)
         JDS_CUDA(cudaMemcpyAsync(c->in.p, J.rgb, frame_bytes, cudaMemcpyHostToDevice, s));
-    JDS_CUDA(cudaEventRecord(c->ev0, s));
 
     int chunk_idx = 0;
     bool timed_ran[jds_ctx::kTimedChunks][4];
@@ -523,14 +531,18 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
         P.d_recon = (want_recon && !out_host) ? J.recon + (size_t)u0 * frame_bytes
                                               : (uint8_t*)c->recon.p + (size_t)b * recon_slot;
         P.d_coeffs = nullptr;
-        if (want_coeffs)
-            P.d_coeffs = out_host ? (int16_t*)((char*)c->coeffs.p + (size_t)b * coeff_slot)
-                                  : J.coeffs + (size_t)u0 * ncoef;
+        if (coeff_scratch)
+            P.d_coeffs = (int16_t*)((char*)c->coeffs.p + (size_t)b * coeff_slot);
+        else if (want_coeffs)
+            P.d_coeffs = J.coeffs + (size_t)u0 * ncoef;
         P.d_ey = want_ey ? (out_host ? (double*)c->errs.p : J.err_y) : nullptr;
         P.d_ergb = want_ergb ? (out_host ? (double*)c->errs.p + (size_t)g.H * g.W : J.err_rgb) : nullptr;
         if (pipelined && chunk_idx >= nbuf)          // staging slot still being copied out?
             JDS_CUDA(cudaStreamWaitEvent(s, c->ev_out[b], 0));
 
+        // ev0 .. ev1 bracket the kernels: after the first chunk's input is on its way, before
+        // the last chunk's results are copied out
+        if (u0 == 0) JDS_CUDA(cudaEventRecord(c->ev0, s));
         // per-stage events for the first kTimedChunks chunks of the call
         cudaEvent_t* evs = chunk_idx < jds_ctx::kTimedChunks ? &c->evs[5 * chunk_idx] : nullptr;
         bool ran[4];
@@ -539,6 +551,7 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
             n_timed = chunk_idx + 1;
             for (int k = 0; k < 4; ++k) timed_ran[chunk_idx][k] = ran[k];
         }
+        if (u0 + n >= J.units) JDS_CUDA(cudaEventRecord(c->ev1, s));
         if (pipelined) {
             JDS_CUDA(cudaEventRecord(c->ev_comp[b], s));
             JDS_CUDA(cudaStreamWaitEvent(s_out, c->ev_comp[b], 0));
@@ -560,7 +573,6 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
             if (pipelined) JDS_CUDA(cudaEventRecord(c->ev_out[b], s_out));
         }
     }
-    JDS_CUDA(cudaEventRecord(c->ev1, s));
     JDS_CUDA(cudaMemcpyAsync(h_metrics, d_metrics, sizeof(DevMetrics) * J.units,
                              cudaMemcpyDeviceToHost, s));
     if (pipelined) {

@@ -313,6 +313,53 @@ __global__ void k_selected_block(Geom g, const uint8_t* __restrict__ rgb, int bx
 }
 
 // ------------------------------------------------------------------------------
+// 50-bin histogram of the int16 coefficients (np.histogram(all, 50, (-100, 100)),
+// engines/pipeline.py:124): one pass over the coefficient buffer, 8 values per 16-byte
+// load, per-WARP shared-memory histograms (no cross-warp contention) with equal bins of a
+// warp merged by __match_any_sync before the atomic.
+// ------------------------------------------------------------------------------
+constexpr int HIST_WARPS = 8;
+
+__global__ void __launch_bounds__(HIST_WARPS * 32)
+k_hist50(const int16_t* __restrict__ coeffs, size_t coeff_stride, size_t n_coeffs,
+         DevMetrics* __restrict__ metrics) {
+    __shared__ unsigned int s_h[HIST_WARPS][52];
+    const int unit = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < HIST_WARPS * 52; i += blockDim.x) (&s_h[0][0])[i] = 0;
+    __syncthreads();
+    const uint4* src = reinterpret_cast<const uint4*>(coeffs + (size_t)unit * coeff_stride);
+    const size_t n_vec = n_coeffs / 8;                       // blocks of 64: always a multiple of 8
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_vec;
+         v += (size_t)gridDim.x * blockDim.x) {
+        const uint4 q = __ldg(src + v);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int val = (int)(int16_t)(w[k >> 1] >> ((k & 1) * 16));
+            const int b = hist_bin(val);                     // -1: outside [-100, 100]
+            const unsigned peers = __match_any_sync(__activemask(), b);
+            if (b >= 0 && lane == (__ffs(peers) - 1)) atomicAdd(&s_h[warp][b], (unsigned)__popc(peers));
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < 50; b += blockDim.x) {
+        unsigned t = 0;
+#pragma unroll
+        for (int wv = 0; wv < HIST_WARPS; ++wv) t += s_h[wv][b];
+        if (t) atomicAdd(&metrics[unit].hist[b], (unsigned long long)t);
+    }
+}
+
+void launch_hist50(const int16_t* coeffs, size_t coeff_stride, size_t n_coeffs, DevMetrics* metrics,
+                   int units, int sm_count, cudaStream_t s) {
+    size_t want = (n_coeffs / 8 + HIST_WARPS * 32 - 1) / (HIST_WARPS * 32);
+    unsigned gx = (unsigned)(want < (size_t)sm_count * 8 ? (want ? want : 1) : (size_t)sm_count * 8);
+    dim3 grid(gx, units);
+    k_hist50<<<grid, HIST_WARPS * 32, 0, s>>>(coeffs, coeff_stride, n_coeffs, metrics);
+}
+
+// ------------------------------------------------------------------------------
 // stand-alone 8x8 block operators of engines/dct_engine.py:7-27 and
 // engines/quantizer.py:22-29, exact arithmetic, one block per thread
 // ------------------------------------------------------------------------------
