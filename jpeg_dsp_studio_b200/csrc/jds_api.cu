@@ -344,7 +344,7 @@ static int launch_chunk(jds_ctx* c, const UnitJob& J, const ChunkPtrs& P, int n,
         const size_t cpl_stride = fused_chroma_plane_floats(g);
         ran[0] = g.sub != 0;
         if (ran[0]) {
-            JDS_CUDA(launch_fused_chroma(g, P.d_rgb, P.rgb_stride, cpl, cpl_stride, P.d_tables,
+            JDS_CUDA(launch_fused_chroma(g, p->prefilter, P.d_rgb, P.rgb_stride, cpl, cpl_stride, P.d_tables,
                                          tstride, P.d_coeffs, ncoef, P.d_metrics, n, s));
             c->launches++;
         }

@@ -212,6 +212,41 @@ struct ChromaSmem {
     alignas(16) float dq[64];
 };
 
+// codec of the chroma tile: thread t -> channel t/64, block t%64 of plane[2][64][68]
+template <bool COEFFS>
+__device__ __forceinline__ void chroma_codec_tail(
+    const Geom& g, float (*plane)[CA_BX * CA_BY][BLK_STRIDE], const float* s_fq, const float* s_dq,
+    int bx0, int by0, int unit, float* __restrict__ cplanes, size_t cplane_stride,
+    int16_t* __restrict__ coeffs, size_t coeff_stride, DevMetrics* __restrict__ metrics) {
+    const int tid = threadIdx.x;
+    const int ch = tid >> 6, blk = tid & 63;
+    const int bx = bx0 + (blk & (CA_BX - 1)), by = by0 + (blk >> 4);
+    unsigned esum = 0, nnz = 0;
+    if (bx < g.nbx_c && by < g.nby_c) {
+        float v[64];
+        const float4* src = reinterpret_cast<const float4*>(&plane[ch][blk][0]);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float4 a = src[i];
+            v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = a.z; v[4 * i + 3] = a.w;
+        }
+        int16_t* cout = nullptr;
+        if (COEFFS)
+            cout = coeffs + (size_t)unit * coeff_stride +
+                   ((size_t)g.nblk_y + (size_t)ch * g.nblk_c + (size_t)by * g.nbx_c + bx) * 64;
+        codec_fast<COEFFS>(v, s_fq, s_dq, esum, nnz, cout);
+        float* dst = cplanes + (size_t)unit * cplane_stride + (size_t)ch * g.plane_c +
+                     (size_t)(by * 8) * g.wcp + bx * 8;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            float4* d4 = reinterpret_cast<float4*>(dst + (size_t)r * g.wcp);
+            d4[0] = make_float4(v[r * 8], v[r * 8 + 1], v[r * 8 + 2], v[r * 8 + 3]);
+            d4[1] = make_float4(v[r * 8 + 4], v[r * 8 + 5], v[r * 8 + 6], v[r * 8 + 7]);
+        }
+    }
+    flush_stats(esum, nnz, metrics + unit);
+}
+
 template <int SUB, bool COEFFS>
 __global__ void __launch_bounds__(CA_NT)
 k_fast_chroma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
@@ -309,33 +344,144 @@ k_fast_chroma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
     }
     __syncthreads();
 
-    // ---- codec: one block per thread ---------------------------------------------
-    const int ch = tid >> 6, blk = tid & 63;
-    const int bx = bx0 + (blk & (CA_BX - 1)), by = by0 + (blk >> 4);
-    unsigned esum = 0, nnz = 0;
-    if (bx < g.nbx_c && by < g.nby_c) {
-        float v[64];
-        const float4* src = reinterpret_cast<const float4*>(&sm.plane[ch][blk][0]);
+    chroma_codec_tail<COEFFS>(g, sm.plane, sm.fq, sm.dq, bx0, by0, unit, cplanes, cplane_stride,
+                              coeffs, coeff_stride, metrics);
+}
+
+// ------------------------------------------------------------------------------
+// chroma kernel with the anti-alias prefilter (use_prefilter=True):
+// cv2.GaussianBlur(3x3, sigma 0.75, BORDER_REFLECT_101) of full-resolution Cb/Cr followed by
+// the 2x1 / 2x2 INTER_AREA average (engines/color_space.py:38-49).  Blur and average are
+// linear, so per axis they fold into one 4-tap filter [a, b, b, a], a = ke/2,
+// b = (kc+ke)/2, on the pixel pair and its two neighbours (4:2:2 keeps the 3-tap blur
+// vertically).  Phase A filters every luma row of the tile (+1 halo row each side)
+// horizontally into shared memory, phase B combines rows.
+// ------------------------------------------------------------------------------
+template <int SUB>
+struct ChromaPfSmem {
+    static constexpr int LROWS = CA_BY * 8 * (SUB == 2 ? 2 : 1) + 2;     // luma rows incl. halo
+    alignas(16) float2 hrow[LROWS][CA_BX * 8];                            // (cb, cr), level shifted
+    alignas(16) float plane[2][CA_BX * CA_BY][BLK_STRIDE];
+    alignas(16) float fq[64];
+    alignas(16) float dq[64];
+};
+
+template <int SUB, bool COEFFS>
+__global__ void __launch_bounds__(CA_NT)
+k_fast_chroma_pf(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
+                 float* __restrict__ cplanes, size_t cplane_stride,
+                 const QTables* __restrict__ tables, int table_stride,
+                 int16_t* __restrict__ coeffs, size_t coeff_stride,
+                 DevMetrics* __restrict__ metrics) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    ChromaPfSmem<SUB>& sm = *reinterpret_cast<ChromaPfSmem<SUB>*>(smem_raw);
+    constexpr int VS = (SUB == 2) ? 2 : 1;
+    constexpr int LROWS = ChromaPfSmem<SUB>::LROWS;
+    constexpr float KE = (float)JDS_KE, KC = (float)JDS_KC;
+    constexpr float HA = 0.5f * KE, HB = 0.5f * (KC + KE);                // folded 4-tap
+    const int tid = threadIdx.x;
+    const int unit = blockIdx.z;
+    const uint8_t* in = rgb + (size_t)unit * rgb_stride;
+    const int bx0 = blockIdx.x * CA_BX, by0 = blockIdx.y * CA_BY;
+    const int x0 = bx0 * 16, y0 = by0 * 8 * VS;
+    const int n_rows = min(LROWS - 2, g.H - y0);                          // tile's own luma rows
+    const int n_px = min(CA_BX * 16, g.W - x0);
+    load_tables(tables + (size_t)unit * table_stride, sm.fq, sm.dq, tid, CA_NT);
+
+    // ---- phase A: a task = one luma row (halo rows included) x 16 pixels -> 8 samples ----
+    for (int task = tid; task < LROWS * CA_BX; task += CA_NT) {
+        const int lr = task / CA_BX, seg = task % CA_BX;
+        if (lr >= n_rows + 2 || seg * 16 >= n_px) continue;
+        // smem row lr holds image row y0 + lr - 1, REFLECT_101 at the top / bottom edge
+        int y = y0 + lr - 1;
+        y = y < 0 ? -y : (y >= g.H ? 2 * (g.H - 1) - y : y);
+        const int xs = x0 + seg * 16;
+        const uint8_t* row = in + ((size_t)y * g.W + xs) * 3;
+        // 18 pixels xs-1 .. xs+16: the aligned 48 bytes plus the 16-byte chunks either side
+        const bool has_l = xs > 0, has_r = xs + 16 < g.W;
+        const uint4* q = reinterpret_cast<const uint4*>(row);
+        const uint4 c0 = __ldg(q), c1 = __ldg(q + 1), c2 = __ldg(q + 2);
+        const uint4 cl = has_l ? __ldg(q - 1) : make_uint4(0, 0, 0, 0);
+        const uint4 cr4 = has_r ? __ldg(q + 3) : make_uint4(0, 0, 0, 0);
+        const uint32_t w[12] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w};
+        float cb[18], cr[18];                       // index i <-> pixel xs - 1 + i
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const float4 a = src[i];
-            v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = a.z; v[4 * i + 3] = a.w;
+        for (int gq = 0; gq < 4; ++gq) {
+            const uint32_t w0 = w[3 * gq], w1 = w[3 * gq + 1], w2 = w[3 * gq + 2];
+            const float R[4] = {f_byte_centered<0>(w0), f_byte_centered<3>(w0), f_byte_centered<2>(w1), f_byte_centered<1>(w2)};
+            const float G[4] = {f_byte_centered<1>(w0), f_byte_centered<0>(w1), f_byte_centered<3>(w1), f_byte_centered<2>(w2)};
+            const float B[4] = {f_byte_centered<2>(w0), f_byte_centered<1>(w1), f_byte_centered<0>(w2), f_byte_centered<3>(w2)};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                cb[1 + 4 * gq + k] = fmaf(-0.168736f, R[k], fmaf(-0.331264f, G[k], 0.5f * B[k]));
+                cr[1 + 4 * gq + k] = fmaf(0.5f, R[k], fmaf(-0.418688f, G[k], -0.081312f * B[k]));
+            }
         }
-        int16_t* cout = nullptr;
-        if (COEFFS)
-            cout = coeffs + (size_t)unit * coeff_stride +
-                   ((size_t)g.nblk_y + (size_t)ch * g.nblk_c + (size_t)by * g.nbx_c + bx) * 64;
-        codec_fast<COEFFS>(v, sm.fq, sm.dq, esum, nnz, cout);
-        float* dst = cplanes + (size_t)unit * cplane_stride + (size_t)ch * g.plane_c +
-                     (size_t)(by * 8) * g.wcp + bx * 8;
+        if (has_l) {                                // pixel xs-1 = bytes 13,14,15 of the chunk before
+            const float r = f_byte_centered<1>(cl.w), gg = f_byte_centered<2>(cl.w), b = f_byte_centered<3>(cl.w);
+            cb[0] = fmaf(-0.168736f, r, fmaf(-0.331264f, gg, 0.5f * b));
+            cr[0] = fmaf(0.5f, r, fmaf(-0.418688f, gg, -0.081312f * b));
+        } else {                                    // REFLECT_101: pixel -1 = pixel 1
+            cb[0] = cb[2];
+            cr[0] = cr[2];
+        }
+        if (has_r) {                                // pixel xs+16 = bytes 0,1,2 of the chunk after
+            const float r = f_byte_centered<0>(cr4.x), gg = f_byte_centered<1>(cr4.x), b = f_byte_centered<2>(cr4.x);
+            cb[17] = fmaf(-0.168736f, r, fmaf(-0.331264f, gg, 0.5f * b));
+            cr[17] = fmaf(0.5f, r, fmaf(-0.418688f, gg, -0.081312f * b));
+        } else {                                    // pixel W = pixel W-2
+            cb[17] = cb[15];
+            cr[17] = cr[15];
+        }
+        float4* dst = reinterpret_cast<float4*>(&sm.hrow[lr][seg * 8]);
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            float4* d4 = reinterpret_cast<float4*>(dst + (size_t)r * g.wcp);
-            d4[0] = make_float4(v[r * 8], v[r * 8 + 1], v[r * 8 + 2], v[r * 8 + 3]);
-            d4[1] = make_float4(v[r * 8 + 4], v[r * 8 + 5], v[r * 8 + 6], v[r * 8 + 7]);
+        for (int k2 = 0; k2 < 4; ++k2) {            // two samples per float4 store
+            float o[4];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int k = 2 * k2 + h;           // sample k: pixels 2k, 2k+1 -> cb[2k .. 2k+3]
+                o[2 * h] = fmaf(HA, cb[2 * k] + cb[2 * k + 3], HB * (cb[2 * k + 1] + cb[2 * k + 2]));
+                o[2 * h + 1] = fmaf(HA, cr[2 * k] + cr[2 * k + 3], HB * (cr[2 * k + 1] + cr[2 * k + 2]));
+            }
+            dst[k2] = make_float4(o[0], o[1], o[2], o[3]);
         }
     }
-    flush_stats(esum, nnz, metrics + unit);
+    __syncthreads();
+
+    // ---- phase B: vertical taps, a task = one chroma row x 8 samples ---------------------
+    for (int task = tid; task < CA_BY * 8 * CA_BX; task += CA_NT) {
+        const int cr_ = task / CA_BX, seg = task % CA_BX;
+        if (cr_ * VS >= n_rows || seg * 16 >= n_px) continue;
+        float ob[8], orr[8];
+        // smem rows of this chroma row: luma rows VS*cr_-1 .. VS*cr_+VS  ->  lr = VS*cr_ .. +VS+1
+        const float4* r0 = reinterpret_cast<const float4*>(&sm.hrow[VS * cr_][seg * 8]);
+        const float4* r1 = reinterpret_cast<const float4*>(&sm.hrow[VS * cr_ + 1][seg * 8]);
+        const float4* r2 = reinterpret_cast<const float4*>(&sm.hrow[VS * cr_ + 2][seg * 8]);
+        const float4* r3 = reinterpret_cast<const float4*>(&sm.hrow[VS * cr_ + (SUB == 2 ? 3 : 2)][seg * 8]);
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) {
+            const float4 a = r0[k2], b = r1[k2], c = r2[k2], d = r3[k2];
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+            const float cv[4] = {c.x, c.y, c.z, c.w}, dv[4] = {d.x, d.y, d.z, d.w};
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                o[e] = (SUB == 2) ? fmaf(HA, av[e] + dv[e], HB * (bv[e] + cv[e]))
+                                  : fmaf(KE, av[e] + cv[e], KC * bv[e]);
+            ob[2 * k2] = o[0]; orr[2 * k2] = o[1];
+            ob[2 * k2 + 1] = o[2]; orr[2 * k2 + 1] = o[3];
+        }
+        const int blk = (cr_ >> 3) * CA_BX + seg, ry = cr_ & 7;
+        float4* pb = reinterpret_cast<float4*>(&sm.plane[0][blk][ry * 8]);
+        float4* pr = reinterpret_cast<float4*>(&sm.plane[1][blk][ry * 8]);
+        pb[0] = make_float4(ob[0], ob[1], ob[2], ob[3]);
+        pb[1] = make_float4(ob[4], ob[5], ob[6], ob[7]);
+        pr[0] = make_float4(orr[0], orr[1], orr[2], orr[3]);
+        pr[1] = make_float4(orr[4], orr[5], orr[6], orr[7]);
+    }
+    __syncthreads();
+    chroma_codec_tail<COEFFS>(g, sm.plane, sm.fq, sm.dq, bx0, by0, unit, cplanes, cplane_stride,
+                              coeffs, coeff_stride, metrics);
 }
 
 // ------------------------------------------------------------------------------
@@ -729,7 +875,7 @@ k_fast_444(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
 // ------------------------------------------------------------------------------
 bool fused_supported(const Geom& g, int prefilter, const void* rgb, size_t rgb_stride,
                      const void* recon, size_t recon_stride) {
-    if (prefilter && g.sub != 0) return false;        // prefilter: staged kernels (for now)
+    if (prefilter && g.sub != 0 && (g.H < 2 || g.W < 2)) return false;
     if ((g.W % 16) != 0 || (g.H % 8) != 0) return false;
     if (g.sub == 2 && (g.H % 16) != 0) return false;   // chroma planes must be whole blocks
     if (((uintptr_t)rgb | (uintptr_t)recon | rgb_stride | recon_stride) & 15) return false;
@@ -754,12 +900,26 @@ static cudaError_t set_smem(K kernel, size_t bytes) {
     return e;
 }
 
-cudaError_t launch_fused_chroma(const Geom& g, const uint8_t* rgb, size_t rgb_stride,
+cudaError_t launch_fused_chroma(const Geom& g, int prefilter, const uint8_t* rgb, size_t rgb_stride,
                                 float* cplanes, size_t cplane_stride, const QTables* tables,
                                 int table_stride, int16_t* coeffs, size_t coeff_stride,
                                 DevMetrics* metrics, int units, cudaStream_t s) {
     dim3 grid((g.nbx_c + CA_BX - 1) / CA_BX, (g.nby_c + CA_BY - 1) / CA_BY, units);
     cudaError_t e;
+    if (prefilter) {
+#define JDS_LAUNCH_PF(SUBV, CO)                                                                 \
+    do {                                                                                        \
+        e = set_smem(k_fast_chroma_pf<SUBV, CO>, sizeof(ChromaPfSmem<SUBV>));                    \
+        if (e != cudaSuccess) return e;                                                          \
+        k_fast_chroma_pf<SUBV, CO><<<grid, CA_NT, sizeof(ChromaPfSmem<SUBV>), s>>>(              \
+            g, rgb, rgb_stride, cplanes, cplane_stride, tables, table_stride, coeffs,            \
+            coeff_stride, metrics);                                                              \
+    } while (0)
+        if (g.sub == 2) { if (coeffs) JDS_LAUNCH_PF(2, true); else JDS_LAUNCH_PF(2, false); }
+        else { if (coeffs) JDS_LAUNCH_PF(1, true); else JDS_LAUNCH_PF(1, false); }
+#undef JDS_LAUNCH_PF
+        return cudaGetLastError();
+    }
 #define JDS_LAUNCH_CA(SUBV, CO)                                                                 \
     do {                                                                                        \
         e = set_smem(k_fast_chroma<SUBV, CO>, sizeof(ChromaSmem<SUBV>));                         \

@@ -28,7 +28,7 @@ cudaError_t launch_ssim_strip(int H, int W, const uint8_t* a, size_t a_stride, c
 bool fused_supported(const Geom& g, int prefilter, const void* rgb, size_t rgb_stride,
                      const void* recon, size_t recon_stride);
 size_t fused_chroma_plane_floats(const Geom& g);
-cudaError_t launch_fused_chroma(const Geom& g, const uint8_t* rgb, size_t rgb_stride,
+cudaError_t launch_fused_chroma(const Geom& g, int prefilter, const uint8_t* rgb, size_t rgb_stride,
                                 float* cplanes, size_t cplane_stride, const QTables* tables,
                                 int table_stride, int16_t* coeffs, size_t coeff_stride,
                                 DevMetrics* metrics, int units, cudaStream_t s);

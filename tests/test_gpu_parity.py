@@ -369,3 +369,60 @@ def test_public_sweep_and_batch_api(J, oracle):
         assert r.bpp == ref["bpp"] and r.compression_ratio == ref["compression_ratio"]
     with pytest.raises(ValueError):
         J.quality_sweep(img, base, [0, 50])
+
+
+PF_CASES = [
+    ("rand_64x64_420_pf", lambda: CS.rand_rgb(41, 64, 64), 50, "4:2:0"),
+    ("rand_16x16_420_pf", lambda: CS.rand_rgb(42, 16, 16), 60, "4:2:0"),
+    ("rand_72x48_422_pf", lambda: CS.rand_rgb(43, 72, 48), 35, "4:2:2"),
+    ("rand_272x400_420_pf", lambda: CS.rand_rgb(44, 272, 400), 80, "4:2:0"),
+    ("rand_264x528_422_pf", lambda: CS.rand_rgb(45, 264, 528), 20, "4:2:2"),
+    ("photo512_420_pf", lambda: CS.TI.generate_photo(512), 75, "4:2:0"),
+    ("cfg3_4k_q75_420_pf", lambda: CS.rand_rgb(3, 2160, 3840), 75, "4:2:0"),
+    ("rand1080p_422_pf", lambda: CS.rand_rgb(46, 1080, 1920), 40, "4:2:2"),
+]
+
+
+@pytest.mark.parametrize("name,make,q,mode", PF_CASES, ids=[c[0] for c in PF_CASES])
+def test_fused_prefilter_kernel_against_exact_mode(J, name, make, q, mode):
+    """use_prefilter=True through the fused chroma kernel (blur + decimation folded into one
+    4-tap filter per axis, REFLECT_101 borders) against the bit-exact path."""
+    img = make()
+    eng = J.get_engine()
+    ex = eng.roundtrip(img, q, mode, True, precision="exact", want_coeffs=True, want_hist=True)
+    eng.stage_times(reset=True)
+    fa = eng.roundtrip(img, q, mode, True, precision="fast", want_coeffs=True, want_hist=True)
+    st = eng.stage_times(reset=True)
+    assert st["inverse_colour"]["launches"] == 0, "fused kernels were not used"
+    coef_mm = float(np.mean(ex.coeffs != fa.coeffs))
+    pix_mm = float(np.mean(ex.recon != fa.recon))
+    print(f"\n[fused+prefilter] {name}: coeff mismatch {coef_mm:.3e}, pixel mismatch {pix_mm:.3e}, "
+          f"dPSNR_y {fa.scalars['psnr_y'] - ex.scalars['psnr_y']:+.2e} dB, "
+          f"dSSIM_y {fa.scalars['ssim_y'] - ex.scalars['ssim_y']:+.2e}")
+    assert coef_mm <= 1e-5
+    assert pix_mm <= 5e-4
+    assert close_psnr(fa.scalars["psnr_y"], ex.scalars["psnr_y"])
+    assert close_psnr(fa.scalars["psnr_rgb"], ex.scalars["psnr_rgb"])
+    assert abs(fa.scalars["ssim_y"] - ex.scalars["ssim_y"]) <= SSIM_TOL
+    assert abs(fa.scalars["ssim_rgb"] - ex.scalars["ssim_rgb"]) <= SSIM_TOL
+    # histogram kernel: exact w.r.t. the path's own coefficients
+    h = np.histogram(fa.coeffs, bins=50, range=(-100, 100))[0]
+    assert np.array_equal(np.array(list(fa.metrics.hist50)), h)
+    if coef_mm == 0.0:
+        assert np.array_equal(np.array(list(fa.metrics.hist50)), np.array(list(ex.metrics.hist50)))
+
+
+def test_cli_entry_matches_reference_demo(J, capsys, tmp_path):
+    """`python -m jpeg_dsp_studio_b200 --cli` = the reference's main.py run_cli on its
+    256x256 checkerboard (main.py:46-91): same PSNR / SSIM / BPP lines."""
+    from jpeg_dsp_studio_b200.__main__ import main
+    from oracle import numpy_port as P
+    out = str(tmp_path / "recon.png")
+    assert main(["--cli", "--output", out]) == 0
+    text = capsys.readouterr().out
+    ref = P.compress_reconstruct(CS.TI.generate_colored_checkerboard(256), 50, "4:2:0", False,
+                                 want_maps=False)
+    assert f"PSNR (Y): {ref['psnr_y']:.2f} dB" in text
+    assert f"SSIM (Y): {ref['ssim_y']:.4f}" in text
+    assert f"BPP: {ref['bpp']:.3f}" in text
+    assert f"Compression Ratio: {ref['compression_ratio']:.2f}x" in text
