@@ -40,6 +40,10 @@ inline int geom_init(int H, int W, int sub, Geom* g) {
 
 inline void fill_tables(int quality, QTables* t) {
     quant_table_host(quality, t->q);
+    for (int i = 0; i < 64; ++i) {
+        volatile double r = 1.0 / t->q[i];        // correctly rounded reciprocal
+        t->rq[i] = r;
+    }
     double s[8];
     s[0] = 1.0;
     for (int k = 1; k < 8; ++k) s[k] = sqrt(2.0) * cos(k * M_PI / 16.0);

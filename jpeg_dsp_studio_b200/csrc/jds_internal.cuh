@@ -30,10 +30,11 @@ struct DevMetrics {
 };
 
 // Quantiser tables of one unit, in the arithmetic the policy needs.
-//   exact: q[i] = Q (fp64, integer valued);         fq unused, dq = Q
+//   exact: q[i] = Q (fp64, integer valued), rq[i] = RN(1/Q);   fq, dq unused
 //   fast : fq[i] = 1 / (Q * AAN_FWD[u] * AAN_FWD[v]);  dq[i] = Q * AAN_INV[u] * AAN_INV[v]
 struct QTables {
     double q[64];
+    double rq[64];   // RN(1/Q): exact mode divides by Markstein's 3-operation sequence
     float fq[64];
     float dq[64];
 };

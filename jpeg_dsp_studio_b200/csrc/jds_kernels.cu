@@ -61,6 +61,7 @@ k_codec(Geom g, const typename P::T* __restrict__ fwd, size_t fwd_stride,
         const QTables* src = tables + (size_t)unit * table_stride;
         for (int i = threadIdx.x; i < 64; i += blockDim.x) {
             tb.q[i] = src->q[i];
+            tb.rq[i] = src->rq[i];
             tb.fq[i] = src->fq[i];
             tb.dq[i] = src->dq[i];
         }
@@ -166,6 +167,79 @@ k_inverse(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
         if (err_rgb) err_rgb[(size_t)y * g.W + x] = o.err_rgb;
         sse = o.sse_rgb;
         ssey = o.sse_y;
+    }
+    __shared__ unsigned long long s_sse[8];
+    __shared__ double s_ssey[8];
+    sse = warp_sum_u64(sse);
+    ssey = warp_sum_f64(ssey);
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    if ((tid & 31) == 0) {
+        s_sse[tid >> 5] = sse;
+        s_ssey[tid >> 5] = ssey;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long a = 0;
+        double bsum = 0.0;
+        const int nw = (blockDim.x * blockDim.y) >> 5;
+        for (int i = 0; i < nw; ++i) {
+            a += s_sse[i];
+            bsum += s_ssey[i];
+        }
+        DevMetrics* m = metrics + unit;
+        if (a) atomicAdd(&m->sse_rgb, a);
+        if (bsum != 0.0) atomicAdd(&m->sse_y, bsum);
+    }
+}
+
+// Stage 3, four pixels per thread (W % 4 == 0): same per-pixel arithmetic, but the 12 output
+// bytes leave as three 32-bit stores and the error maps as 16-byte stores.
+template <class P>
+__global__ void __launch_bounds__(256)
+k_inverse4(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
+           const typename P::T* __restrict__ fwd, size_t fwd_stride,
+           const typename P::T* __restrict__ rec, size_t rec_stride,
+           uint8_t* __restrict__ recon, size_t recon_stride,
+           double* __restrict__ err_y, double* __restrict__ err_rgb,
+           DevMetrics* __restrict__ metrics) {
+    typedef typename P::T T;
+    const int unit = blockIdx.z;
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    unsigned long long sse = 0;
+    double ssey = 0.0;
+    if (x < g.W && y < g.H) {
+        const uint8_t* in = rgb + (size_t)unit * rgb_stride;
+        const T* Yf = fwd + (size_t)unit * fwd_stride;
+        const T* Yr = rec + (size_t)unit * rec_stride;
+        const T* Cbr = Yr + g.plane_y;
+        const T* Crr = Cbr + g.plane_c;
+        uint32_t by[12];
+        double ey[4], ergb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const PixelOut o = inverse_pixel<P>(g, in, x + i, y, Yf, Yr, Cbr, Crr);
+            by[3 * i] = o.r; by[3 * i + 1] = o.g; by[3 * i + 2] = o.b;
+            ey[i] = o.err_y;
+            ergb[i] = o.err_rgb;
+            sse += o.sse_rgb;
+            ssey += o.sse_y;
+        }
+        uint32_t* out = reinterpret_cast<uint32_t*>(recon + (size_t)unit * recon_stride +
+                                                    ((size_t)y * g.W + x) * 3);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            out[i] = by[4 * i] | (by[4 * i + 1] << 8) | (by[4 * i + 2] << 16) | (by[4 * i + 3] << 24);
+        if (err_y) {
+            double2* d = reinterpret_cast<double2*>(err_y + (size_t)y * g.W + x);
+            d[0] = make_double2(ey[0], ey[1]);
+            d[1] = make_double2(ey[2], ey[3]);
+        }
+        if (err_rgb) {
+            double2* d = reinterpret_cast<double2*>(err_rgb + (size_t)y * g.W + x);
+            d[0] = make_double2(ergb[0], ergb[1]);
+            d[1] = make_double2(ergb[2], ergb[3]);
+        }
     }
     __shared__ unsigned long long s_sse[8];
     __shared__ double s_ssey[8];
@@ -473,6 +547,20 @@ void launch_inverse(bool exact, const Geom& g, const uint8_t* rgb, size_t rgb_st
                     const void* fwd, size_t fwd_stride, const void* rec, size_t rec_stride,
                     uint8_t* recon, size_t recon_stride, double* err_y, double* err_rgb,
                     DevMetrics* metrics, int units, cudaStream_t s) {
+    const bool aligned = (g.W % 4) == 0 && (((uintptr_t)recon | recon_stride) & 3) == 0 &&
+                         (((uintptr_t)err_y | (uintptr_t)err_rgb) & 15) == 0;
+    if (aligned) {
+        dim3 blk4(32, 8), grid4((g.W / 4 + 31) / 32, (g.H + 7) / 8, units);
+        if (exact)
+            k_inverse4<Exact><<<grid4, blk4, 0, s>>>(g, rgb, rgb_stride, (const double*)fwd, fwd_stride,
+                                                     (const double*)rec, rec_stride, recon,
+                                                     recon_stride, err_y, err_rgb, metrics);
+        else
+            k_inverse4<Fast><<<grid4, blk4, 0, s>>>(g, rgb, rgb_stride, (const float*)fwd, fwd_stride,
+                                                    (const float*)rec, rec_stride, recon,
+                                                    recon_stride, err_y, err_rgb, metrics);
+        return;
+    }
     dim3 blk(32, 8), grid((g.W + 31) / 32, (g.H + 7) / 8, units);
     if (exact)
         k_inverse<Exact><<<grid, blk, 0, s>>>(g, rgb, rgb_stride, (const double*)fwd, fwd_stride,

@@ -127,7 +127,13 @@ struct BlockCodec<Exact> {
 #pragma unroll
         for (int i = 0; i < 64; ++i) {
             if (dct_out) dct_out[i] = v[i];
-            const double qv = P::rint_(P::div(v[i], tb.q[i]));
+            // X / Q correctly rounded without the division subroutine (Markstein): with
+            // y = RN(1/Q), q0 = RN(X y), r = X - q0 Q (exact in one FMA), RN(q0 + r y) is the
+            // IEEE quotient for every integer Q in 1..255 (102 M cases incl. near-ties checked
+            // against x/Q in tests/emul; tests/test_device_math_on_cpu.py)
+            const double q0 = P::mul(v[i], tb.rq[i]);
+            const double rem = P::fma(-q0, tb.q[i], v[i]);
+            const double qv = P::rint_(P::fma(rem, tb.rq[i], q0));
             const int qi = (int)qv;
             q[i] = (int16_t)qi;
             bits += coeff_bits(qi);

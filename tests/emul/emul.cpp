@@ -111,3 +111,30 @@ extern "C" double emul_ssim_window(int use_float, const double* x, const double*
                                              (float)sxy, (float)shift);
     return ssim_from_sums<double>(sx, sy, sxx, syy, sxy, shift);
 }
+
+// Markstein quotient used by BlockCodec<Exact> against the IEEE division, n samples per
+// divisor 1..255 (returns the number of mismatches)
+extern "C" long emul_division_selftest(long n_per_q) {
+    unsigned long long st = 88172645463325252ULL;
+    auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return (double)(st >> 11) / 9007199254740992.0; };
+    long bad = 0;
+    for (int q = 1; q <= 255; ++q) {
+        const double Q = q;
+        volatile double rqv = 1.0 / Q;
+        const double rq = rqv;
+        for (long i = 0; i < n_per_q; ++i) {
+            double x;
+            switch (i & 3) {
+                case 0: x = (rnd() * 2 - 1) * 1100.0; break;
+                case 1: x = (rnd() * 2 - 1) * 8.0; break;
+                case 2: x = (floor(rnd() * 2200) - 1100 + 0.5) * q; break;          // exact ties
+                default: x = nextafter((floor(rnd() * 2200) - 1100 + 0.5) * q, rnd() > 0.5 ? 1e9 : -1e9);
+            }
+            const double q0 = Exact::mul(x, rq);
+            const double rem = Exact::fma(-q0, Q, x);
+            const double got = Exact::fma(rem, rq, q0);
+            if (got != Exact::div(x, Q)) ++bad;
+        }
+    }
+    return bad;
+}

@@ -89,3 +89,10 @@ def test_ssim_window_formula(emul):
         for use_float, shift, tol in ((0, 0.0, 1e-12), (0, 128.0, 1e-12), (1, 128.0, 2e-5)):
             got = emul.emul_ssim_window(use_float, vp(x), vp(y), C.c_double(shift))
             assert abs(got - want) <= tol, (trial, use_float, shift, got, want)
+
+
+def test_markstein_division_equals_ieee_division(emul):
+    """exact mode quantises with RN(q0 + (X - q0 Q) RN(1/Q)) instead of the fp64 division
+    subroutine; it must be the IEEE quotient for every table entry 1..255."""
+    emul.emul_division_selftest.restype = C.c_long
+    assert emul.emul_division_selftest(C.c_long(40000)) == 0
