@@ -333,9 +333,8 @@ static int launch_chunk(jds_ctx* c, const UnitJob& J, const ChunkPtrs& P, int n,
     const size_t rec_stride = planes_elems;
 
     if (timed) JDS_CUDA(cudaEventRecord(evs[0], s));
-    // fast mode on block-aligned frames runs the fused kernels (jds_fused.cu); exact
-    // mode, prefiltered / ragged frames and the GUI-only outputs (histogram, error
-    // maps) run the staged kernels (jds_kernels.cu)
+    // fast mode on block-aligned frames runs the fused kernels (jds_fused.cu); exact mode,
+    // ragged frames and the fp64 error maps run the staged kernels (jds_kernels.cu)
     const bool fused = !exact && !c->no_fused && !P.d_ey && !P.d_ergb &&
                        fused_supported(g, p->prefilter, P.d_rgb, P.rgb_stride, P.d_recon, frame_bytes) &&
                        ssim_strip_supported(g.H, g.W, P.d_rgb, P.rgb_stride, P.d_recon, frame_bytes);
