@@ -426,3 +426,48 @@ def test_cli_entry_matches_reference_demo(J, capsys, tmp_path):
     assert f"SSIM (Y): {ref['ssim_y']:.4f}" in text
     assert f"BPP: {ref['bpp']:.3f}" in text
     assert f"Compression Ratio: {ref['compression_ratio']:.2f}x" in text
+
+
+def test_calls_from_worker_threads(J, oracle):
+    """The reference is called from a QThread worker (gui/worker.py:23-36): the drop-in must
+    be callable from any Python thread, also concurrently (one engine lock per device)."""
+    import threading
+    imgs = [CS.rand_rgb(90 + k, 64 + 16 * k, 96) for k in range(4)]
+    refs = [oracle.compress_reconstruct(im, 40 + 10 * k, "4:2:0", bool(k & 1), want_maps=False)
+            for k, im in enumerate(imgs)]
+    out, errs = [None] * 4, []
+
+    def work(k):
+        try:
+            p = J.CompressionParams(quality=40 + 10 * k, use_prefilter=bool(k & 1))
+            for _ in range(3):
+                out[k] = J.compress_reconstruct(imgs[k], p, (k, 1))
+        except Exception as e:           # pragma: no cover
+            errs.append(e)
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    for k in range(4):
+        res, inter = out[k]
+        assert np.array_equal(res.reconstructed_image, refs[k]["reconstructed_image"])
+        assert np.array_equal(inter.all_quantized_coeffs, refs[k]["all_quantized_coeffs"])
+        assert res.bpp == refs[k]["bpp"]
+
+
+def test_pipelined_host_batch_with_coefficients(J, oracle):
+    """Host-buffer batch large enough to be pipelined over the three streams (many chunks,
+    staging slots reused), coefficients and pixels checked frame by frame."""
+    frames = np.stack([CS.rand_rgb(500 + k, 256, 512) for k in range(40)])     # 393 KB each
+    eng = J.Engine(0)
+    outs = eng.roundtrip_batch(frames, 55, "4:2:0", False, precision="exact", want_coeffs=True)
+    for k in (0, 1, 2, 17, 38, 39):
+        ref = oracle.compress_reconstruct(frames[k], 55, "4:2:0", False, want_maps=False)
+        assert np.array_equal(outs[k].recon, ref["reconstructed_image"]), k
+        assert np.array_equal(outs[k].coeffs, ref["all_quantized_coeffs"]), k
+    fast = eng.roundtrip_batch(frames, 55, "4:2:0", False, precision="fast", want_coeffs=True)
+    mm = np.mean([np.mean(f.recon != e.recon) for f, e in zip(fast, outs)])
+    assert mm <= 5e-4
+    eng.close()
