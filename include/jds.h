@@ -121,6 +121,8 @@ int jds_ctx_launch_count(jds_ctx* ctx, uint64_t* launches);
  * the four stage kernels - forward colour, block codec, inverse colour, SSIM - since
  * the last reset; bench.py's roofline line is computed from these */
 int jds_ctx_stage_times(jds_ctx* ctx, double ms[4], uint64_t launches[4], int reset);
+/* per-kernel events are recorded only while enabled (off by default: ~20 us per call) */
+int jds_ctx_stage_timing(jds_ctx* ctx, int enable);
 
 /* ---- host-only helpers (no GPU needed) ---------------------------------------- */
 /* engines/quantizer.py:7-19 scale_quant_matrix(JPEG_LUMA_Q50, quality) -> 64 doubles */

@@ -74,6 +74,7 @@ struct jds_ctx {
     bool legacy_ssim = false;     // JDS_LEGACY_SSIM=1: use the tile kernel (debug / A-B runs)
     bool no_fused = false;        // JDS_NO_FUSED=1: fast mode through the staged kernels
     bool l2_chunking = false;     // JDS_L2_CHUNK=1: size launches so a frame sequence stays in L2
+    bool stage_timing = false;    // per-kernel CUDA events (jds_ctx_stage_timing)
     size_t scratch_budget = (size_t)1 << 30;
 };
 
@@ -204,6 +205,12 @@ extern "C" int jds_ctx_synchronize(jds_ctx* c) {
     if (!c) return fail(JDS_ERR_INVALID, "ctx is NULL");
     JDS_CUDA(cudaSetDevice(c->device));
     JDS_CUDA(cudaStreamSynchronize(c->stream));
+    return JDS_OK;
+}
+
+extern "C" int jds_ctx_stage_timing(jds_ctx* c, int enable) {
+    if (!c) return fail(JDS_ERR_INVALID, "ctx is NULL");
+    c->stage_timing = enable != 0;
     return JDS_OK;
 }
 
@@ -543,7 +550,8 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
         // the last chunk's results are copied out
         if (u0 == 0) JDS_CUDA(cudaEventRecord(c->ev0, s));
         // per-stage events for the first kTimedChunks chunks of the call
-        cudaEvent_t* evs = chunk_idx < jds_ctx::kTimedChunks ? &c->evs[5 * chunk_idx] : nullptr;
+        cudaEvent_t* evs = (c->stage_timing && chunk_idx < jds_ctx::kTimedChunks)
+                               ? &c->evs[5 * chunk_idx] : nullptr;
         bool ran[4];
         if ((rc = launch_chunk(c, J, P, n, evs, ran))) return rc;
         if (evs) {

@@ -44,9 +44,11 @@ inline void fill_tables(int quality, QTables* t) {
         volatile double r = 1.0 / t->q[i];        // correctly rounded reciprocal
         t->rq[i] = r;
     }
-    double s[8];
-    s[0] = 1.0;
-    for (int k = 1; k < 8; ++k) s[k] = sqrt(2.0) * cos(k * M_PI / 16.0);
+    static double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};      // AAN scale factors, computed once
+    if (s[0] == 0.0) {
+        for (int k = 7; k >= 1; --k) s[k] = sqrt(2.0) * cos(k * M_PI / 16.0);
+        s[0] = 1.0;
+    }
     for (int u = 0; u < 8; ++u)
         for (int v = 0; v < 8; ++v) {
             const double fwd = (2.0 * sqrt(2.0) * s[u]) * (2.0 * sqrt(2.0) * s[v]);

@@ -116,7 +116,11 @@ class Engine:
     STAGES = ("forward_colour", "block_codec", "inverse_colour", "ssim")
 
     def stage_times(self, reset: bool = True) -> dict:
-        """Accumulated device ms and launch count per stage kernel since the last reset."""
+        """Accumulated device ms and launch count per stage kernel since the last reset.
+        The first call switches the per-kernel events on (they are off by default)."""
+        if not getattr(self, "_stage_timing", False):
+            N.check(self._lib.jds_ctx_stage_timing(self._ctx, 1))
+            self._stage_timing = True
         ms = (C.c_double * 4)()
         ln = (C.c_uint64 * 4)()
         N.check(self._lib.jds_ctx_stage_times(self._ctx, ms, ln, int(reset)))
