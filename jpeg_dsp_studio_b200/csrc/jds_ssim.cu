@@ -126,7 +126,7 @@ __device__ __forceinline__ float2 ssim_window_half2(float2 sx, float2 sy, float2
     return __fmul2_rn(num, f2(rcp_approx(den.x), rcp_approx(den.y)));
 }
 
-__global__ void __launch_bounds__(S_NT, 3)
+__global__ void __launch_bounds__(S_NT, 4)
 k_ssim_strip(int H, int W, int seg_rows, const uint8_t* __restrict__ a_img, size_t a_stride,
              const uint8_t* __restrict__ b_img, size_t b_stride, DevMetrics* __restrict__ metrics,
              int want_ssim, int want_sse) {
@@ -201,10 +201,13 @@ k_ssim_strip(int H, int W, int seg_rows, const uint8_t* __restrict__ a_img, size
         const int buf = chunk & 1;
         const int nrp = min(S_R, in_end - (py0 + chunk * S_R));
         mbar_wait(&sm.bar[buf], (uint32_t)((chunk >> 1) & 1));
-        for (int task = tid; task < 2 * S_R * (S_LW / 4); task += S_NT) {
-            const int img = task / (S_R * (S_LW / 4));
-            const int rem = task % (S_R * (S_LW / 4));
-            const int r = rem / (S_LW / 4), g4 = rem % (S_LW / 4);
+        // only the 72 columns pass 1 reads (64 windows + 6, rounded to a group of 4) are
+        // converted: 2 x 7 x 18 = 252 tasks = two rounds of the 128 threads
+        constexpr int PG = (S_OW + 6 + 3) / 4;
+        for (int task = tid; task < 2 * S_R * PG; task += S_NT) {
+            const int img = task / (S_R * PG);
+            const int rem = task % (S_R * PG);
+            const int r = rem / PG, g4 = rem % PG;
             if (r < nrp) {
                 const uint32_t* w = reinterpret_cast<const uint32_t*>(&sm.raw[buf][img][r][12 * g4]);
                 const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
@@ -261,52 +264,49 @@ k_ssim_strip(int H, int W, int seg_rows, const uint8_t* __restrict__ a_img, size
             // between the even and the odd half of the row
             const float4* qa = &sm.fpl[0][p1_pair][p1_row][2 * p1_seg];
             const float4* qb = &sm.fpl[1][p1_pair][p1_row][2 * p1_seg];
+            // sliding 7-tap window over 14 pixels, two pixels per 16-byte load; pixels are
+            // loaded just before they enter the window and dropped 7 steps later, so only a
+            // short history is live (register pressure decides the occupancy of this kernel)
+            const bool own_row = (y0 + p1_row) < py1;
+            const bool own_all = p1_c0 + S_SEG <= own_px;
             float2 xs[S_SEG + 6], ys[S_SEG + 6];
+            float2 wx = f2(0.f), wy = f2(0.f), wq = f2(0.f), wc = f2(0.f), sse = f2(0.f);
 #pragma unroll
             for (int i2 = 0; i2 < (S_SEG + 6) / 2; ++i2) {
                 const int off = (i2 & 1) * S_FHALF + (i2 >> 1);
                 const float4 a = qa[off], b = qb[off];
                 xs[2 * i2] = f2(a.x, a.y); xs[2 * i2 + 1] = f2(a.z, a.w);
                 ys[2 * i2] = f2(b.x, b.y); ys[2 * i2 + 1] = f2(b.z, b.w);
-            }
-            // squared error of the 8 pixels this task owns (exact for the integer channels)
-            if ((y0 + p1_row) < py1) {
-                float2 sse = f2(0.f);
-                if (p1_c0 + S_SEG <= own_px) {
 #pragma unroll
-                    for (int i = 0; i < S_SEG; ++i) {
+                for (int k = 0; k < 2; ++k) {
+                    const int i = 2 * i2 + k;
+                    if (i < S_SEG) {
+                        // squared error of the 8 pixels this task owns (exact: integer channels)
                         const float2 d = sub2(xs[i], ys[i]);
-                        sse = __ffma2_rn(d, d, sse);
+                        if (own_all || p1_c0 + i < own_px) sse = __ffma2_rn(d, d, sse);
                     }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < S_SEG; ++i)
-                        if (p1_c0 + i < own_px) {
-                            const float2 d = sub2(xs[i], ys[i]);
-                            sse = __ffma2_rn(d, d, sse);
+                    wx = __fadd2_rn(wx, xs[i]);
+                    wy = __fadd2_rn(wy, ys[i]);
+                    wq = __ffma2_rn(xs[i], xs[i], __ffma2_rn(ys[i], ys[i], wq));
+                    wc = __ffma2_rn(xs[i], ys[i], wc);
+                    if (i >= 6) {
+                        const int j = i - 6;
+                        sm.hxy[p1_row][p1_pair * S_OW + p1_c0 + j] = make_float4(wx.x, wx.y, wy.x, wy.y);
+                        sm.hqc[p1_row][p1_pair * S_OW + p1_c0 + j] = make_float4(wq.x, wq.y, wc.x, wc.y);
+                        if (j < S_SEG - 1) {
+                            const float2 ox = xs[j], oy = ys[j];
+                            const float2 nox = sub2(f2(0.f), ox), noy = sub2(f2(0.f), oy);
+                            wx = __fadd2_rn(wx, nox);
+                            wy = __fadd2_rn(wy, noy);
+                            wq = __ffma2_rn(nox, ox, __ffma2_rn(noy, oy, wq));
+                            wc = __ffma2_rn(nox, oy, wc);
                         }
+                    }
                 }
+            }
+            if (own_row) {
                 sse_a += (double)sse.x;
                 sse_b += (double)sse.y;
-            }
-            float2 wx = f2(0.f), wy = f2(0.f), wq = f2(0.f), wc = f2(0.f);
-#pragma unroll
-            for (int i = 0; i < S_SEG + 6; ++i) {
-                wx = __fadd2_rn(wx, xs[i]);
-                wy = __fadd2_rn(wy, ys[i]);
-                wq = __ffma2_rn(xs[i], xs[i], __ffma2_rn(ys[i], ys[i], wq));
-                wc = __ffma2_rn(xs[i], ys[i], wc);
-                if (i >= 6) {
-                    const int j = i - 6;
-                    sm.hxy[p1_row][p1_pair * S_OW + p1_c0 + j] = make_float4(wx.x, wx.y, wy.x, wy.y);
-                    sm.hqc[p1_row][p1_pair * S_OW + p1_c0 + j] = make_float4(wq.x, wq.y, wc.x, wc.y);
-                    const float2 ox = xs[j], oy = ys[j];
-                    const float2 nox = sub2(f2(0.f), ox), noy = sub2(f2(0.f), oy);
-                    wx = __fadd2_rn(wx, nox);
-                    wy = __fadd2_rn(wy, noy);
-                    wq = __ffma2_rn(nox, ox, __ffma2_rn(noy, oy, wq));
-                    wc = __ffma2_rn(nox, oy, wc);
-                }
             }
         }
         __syncthreads();
@@ -406,6 +406,10 @@ cudaError_t launch_ssim_strip(int H, int W, const uint8_t* a, size_t a_stride, c
         if (!((done_mask >> (dev & 63)) & 1ull)) {
             cudaError_t e = cudaFuncSetAttribute(k_ssim_strip, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  (int)smem);
+            if (e != cudaSuccess) return e;
+            // ask for the largest shared-memory carve-out so four 54 KB CTAs fit an SM
+            e = cudaFuncSetAttribute(k_ssim_strip, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxShared);
             if (e != cudaSuccess) return e;
             done_mask |= 1ull << (dev & 63);
         }
