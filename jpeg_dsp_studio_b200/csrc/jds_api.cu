@@ -57,6 +57,8 @@ struct jds_ctx {
     static constexpr int kTimedChunks = 32;             // chunks per call with per-stage events
     cudaEvent_t evs[5 * kTimedChunks] = {};
     cudaStream_t s_in = nullptr, s_out = nullptr;      // copy streams of the pipelined host path
+    cudaStream_t stream2 = nullptr;                    // second compute stream (L2-sized sequences)
+    cudaEvent_t ev_setup = nullptr, ev_join = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr},
                 ev_out[2] = {nullptr, nullptr};
     int plan_chunk = 1;
@@ -136,6 +138,9 @@ extern "C" int jds_ctx_create(int device, jds_ctx** out) {
     for (int i = 0; i < 5 * jds_ctx::kTimedChunks && e == cudaSuccess; ++i) e = cudaEventCreate(&c->evs[i]);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_setup, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
         e = cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_comp[i], cudaEventDisableTiming);
@@ -184,6 +189,9 @@ extern "C" int jds_ctx_destroy(jds_ctx* c) {
         if (c->ev_comp[i]) cudaEventDestroy(c->ev_comp[i]);
         if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
     }
+    if (c->ev_setup) cudaEventDestroy(c->ev_setup);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_out) cudaStreamDestroy(c->s_out);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -318,8 +326,8 @@ struct ChunkPtrs {
     bool first_chunk;
 };
 
-static int launch_chunk(jds_ctx* c, const UnitJob& J, const ChunkPtrs& P, int n,
-                        cudaEvent_t* evs /* 5 events or NULL */, bool ran[4]) {
+static int launch_chunk(jds_ctx* c, const UnitJob& J, const ChunkPtrs& P, int n, cudaStream_t s,
+                        int scratch_slot, cudaEvent_t* evs /* 5 events or NULL */, bool ran[4]) {
     const bool timed = evs != nullptr;
     const Geom& g = J.g;
     const jds_params* p = J.p;
@@ -330,7 +338,6 @@ static int launch_chunk(jds_ctx* c, const UnitJob& J, const ChunkPtrs& P, int n,
     const size_t ncoef = 64ull * (size_t)(g.nblk_y + 2 * g.nblk_c);
     const bool want_hist = (p->outputs & JDS_OUT_HIST) != 0;
     const bool want_ssim = (p->outputs & JDS_OUT_SSIM) != 0;
-    cudaStream_t s = c->stream;
     const int tstride = J.qualities ? 1 : 0;
     const int fwd_units = J.shared_input ? 1 : c->plan_chunk;
     char* planes = (char*)c->planes.p;
@@ -346,8 +353,9 @@ static int launch_chunk(jds_ctx* c, const UnitJob& J, const ChunkPtrs& P, int n,
                        fused_supported(g, p->prefilter, P.d_rgb, P.rgb_stride, P.d_recon, frame_bytes) &&
                        ssim_strip_supported(g.H, g.W, P.d_rgb, P.rgb_stride, P.d_recon, frame_bytes);
     if (fused) {
-        float* cpl = (float*)c->planes.p;
         const size_t cpl_stride = fused_chroma_plane_floats(g);
+        // each compute stream has its own chroma-plane scratch
+        float* cpl = (float*)c->planes.p + (size_t)scratch_slot * cpl_stride * (size_t)c->plan_chunk;
         ran[0] = g.sub != 0;
         if (ran[0]) {
             JDS_CUDA(launch_fused_chroma(g, p->prefilter, P.d_rgb, P.rgb_stride, cpl, cpl_stride, P.d_tables,
@@ -465,10 +473,19 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
     }
     c->plan_chunk = chunk;
     const int nbuf = pipelined ? 2 : 1;
+    // L2-sized launch sequences: alternate chunks over two compute streams so the wave tail
+    // and launch gaps of one frame's kernels are filled by the next frame's (fast mode only;
+    // off while per-kernel timing is on, which wants kernels one at a time)
+    const bool dual = c->l2_chunking && !exact && !c->stage_timing && J.units > chunk;
 
     int rc;
     const int fwd_units = J.shared_input ? 1 : chunk;
-    if ((rc = ensure(c, c->planes, planes_elems * esz * (size_t)(fwd_units + chunk)))) return rc;
+    {
+        size_t need = planes_elems * esz * (size_t)(fwd_units + chunk);
+        const size_t need2 = 2 * fused_chroma_plane_floats(g) * sizeof(float) * (size_t)chunk;
+        if (dual && need2 > need) need = need2;
+        if ((rc = ensure(c, c->planes, need))) return rc;
+    }
     if ((rc = ensure(c, c->metrics, sizeof(DevMetrics) * (size_t)J.units))) return rc;
     const int n_tables_total = J.qualities ? J.units : 1;
     if ((rc = ensure(c, c->tables, sizeof(QTables) * (size_t)n_tables_total))) return rc;
@@ -504,6 +521,10 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
     JDS_CUDA(cudaMemsetAsync(d_metrics, 0, sizeof(DevMetrics) * J.units, s));
     if (J.shared_input && in_host)
         JDS_CUDA(cudaMemcpyAsync(c->in.p, J.rgb, frame_bytes, cudaMemcpyHostToDevice, s));
+    if (dual) {
+        JDS_CUDA(cudaEventRecord(c->ev_setup, s));
+        JDS_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_setup, 0));
+    }
 
     int chunk_idx = 0;
     bool timed_ran[jds_ctx::kTimedChunks][4];
@@ -511,6 +532,8 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
     for (int u0 = 0; u0 < J.units; u0 += chunk, ++chunk_idx) {
         const int n = (J.units - u0 < chunk) ? (J.units - u0) : chunk;
         const int b = chunk_idx % nbuf;
+        const int slot = dual ? (chunk_idx & 1) : 0;
+        cudaStream_t cs = slot ? c->stream2 : s;           // compute stream of this chunk
         ChunkPtrs P;
         P.first_chunk = (u0 == 0);
         P.d_tables = d_tables + (J.qualities ? u0 : 0);
@@ -527,7 +550,7 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
                                      cudaMemcpyHostToDevice, s_in));
             if (pipelined) {
                 JDS_CUDA(cudaEventRecord(c->ev_in[b], s_in));
-                JDS_CUDA(cudaStreamWaitEvent(s, c->ev_in[b], 0));
+                JDS_CUDA(cudaStreamWaitEvent(cs, c->ev_in[b], 0));
             }
             P.d_rgb = slot;
         } else {
@@ -544,7 +567,7 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
         P.d_ey = want_ey ? (out_host ? (double*)c->errs.p : J.err_y) : nullptr;
         P.d_ergb = want_ergb ? (out_host ? (double*)c->errs.p + (size_t)g.H * g.W : J.err_rgb) : nullptr;
         if (pipelined && chunk_idx >= nbuf)          // staging slot still being copied out?
-            JDS_CUDA(cudaStreamWaitEvent(s, c->ev_out[b], 0));
+            JDS_CUDA(cudaStreamWaitEvent(cs, c->ev_out[b], 0));
 
         // ev0 .. ev1 bracket the kernels: after the first chunk's input is on its way, before
         // the last chunk's results are copied out
@@ -553,14 +576,20 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
         cudaEvent_t* evs = (c->stage_timing && chunk_idx < jds_ctx::kTimedChunks)
                                ? &c->evs[5 * chunk_idx] : nullptr;
         bool ran[4];
-        if ((rc = launch_chunk(c, J, P, n, evs, ran))) return rc;
+        if ((rc = launch_chunk(c, J, P, n, cs, slot, evs, ran))) return rc;
         if (evs) {
             n_timed = chunk_idx + 1;
             for (int k = 0; k < 4; ++k) timed_ran[chunk_idx][k] = ran[k];
         }
-        if (u0 + n >= J.units) JDS_CUDA(cudaEventRecord(c->ev1, s));
+        if (u0 + n >= J.units) {
+            if (dual) {                              // join the second compute stream
+                JDS_CUDA(cudaEventRecord(c->ev_join, c->stream2));
+                JDS_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));
+            }
+            JDS_CUDA(cudaEventRecord(c->ev1, s));
+        }
         if (pipelined) {
-            JDS_CUDA(cudaEventRecord(c->ev_comp[b], s));
+            JDS_CUDA(cudaEventRecord(c->ev_comp[b], cs));
             JDS_CUDA(cudaStreamWaitEvent(s_out, c->ev_comp[b], 0));
         }
         // --- results back ---

@@ -115,6 +115,12 @@ class Engine:
 
     STAGES = ("forward_colour", "block_codec", "inverse_colour", "ssim")
 
+    def set_stage_timing(self, enable: bool):
+        """Per-kernel CUDA events on/off (off by default; while on, launch sequences run on
+        one stream so that kernel times do not overlap)."""
+        N.check(self._lib.jds_ctx_stage_timing(self._ctx, int(bool(enable))))
+        self._stage_timing = bool(enable)
+
     def stage_times(self, reset: bool = True) -> dict:
         """Accumulated device ms and launch count per stage kernel since the last reset.
         The first call switches the per-kernel events on (they are off by default)."""
