@@ -181,6 +181,25 @@ int jds_selected_block(jds_ctx* ctx, const jds_params* params,
                        double reconstructed[64], int* present);
 
 /*
+ * GUI plot payload.  One round trip that returns what the reference's plots
+ * draw instead of the bulky intermediates they are drawn from:
+ *   value_hist[JDS_VALUE_HIST_BINS]  count of every int16 coefficient value, value v at
+ *       index v + 1024 (replaces all_quantized_coeffs for the "Quantized Coefficient
+ *       Distribution" plot: gui/compression_tab.py:662-667 -> gui/widgets/mpl_canvas.py:81-100;
+ *       the host bins it exactly as matplotlib's hist / np.histogram(bins=50) would)
+ *   heat_y, heat_rgb  H*W uint8 = trunc(clip(error_map * 10, 0, 255)), the amplified error
+ *       map of gui/widgets/mpl_canvas.py:116-118 (replaces the 8 B/px fp64 error maps)
+ *   recon  H*W*3 uint8 reconstruction.
+ * recon, heat_y, heat_rgb and value_hist may each be NULL.  params->outputs selects the
+ * metrics (JDS_OUT_SSIM | JDS_OUT_PSNR | JDS_OUT_HIST); in JDS_EXACT precision all outputs are
+ * bit-identical to the reference's arrays reduced the same way.
+ */
+#define JDS_VALUE_HIST_BINS 2048
+int jds_plot_payload(jds_ctx* ctx, const jds_params* params, const uint8_t* rgb, int rgb_loc,
+                     uint8_t* recon, uint8_t* heat_y, uint8_t* heat_rgb, int64_t* value_hist,
+                     int out_loc, jds_metrics* metrics);
+
+/*
  * Stand-alone 8x8 block operators, exact (reference) arithmetic, host buffers:
  *   op 0 dct2, 1 idct2 (engines/dct_engine.py:7-14), 2 encode_block (-128 then DCT, :17-20),
  *   3 decode_block (IDCT, +128, clip, :23-27): in/out = n_blocks*64 fp64;

@@ -18,6 +18,7 @@ JDS_EXACT, JDS_FAST = 0, 1
 JDS_HOST, JDS_DEVICE = 0, 1
 JDS_OUT_RECON, JDS_OUT_COEFFS, JDS_OUT_ERR_Y, JDS_OUT_ERR_RGB = 1, 2, 4, 8
 JDS_OUT_HIST, JDS_OUT_SSIM, JDS_OUT_PSNR = 16, 32, 64
+JDS_VALUE_HIST_BINS = 2048
 
 SUBSAMPLING = {"4:4:4": JDS_SUB_444, "4:2:2": JDS_SUB_422, "4:2:0": JDS_SUB_420}
 PRECISION = {"exact": JDS_EXACT, "fast": JDS_FAST}
@@ -66,6 +67,9 @@ PROTOTYPES = {
                                       C.POINTER(JdsMetrics)]),
     "jds_sweep": (C.c_int, [C.c_void_p, C.POINTER(JdsParams), C.POINTER(C.c_int32), C.c_int,
                             C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(JdsMetrics)]),
+    "jds_plot_payload": (C.c_int, [C.c_void_p, C.POINTER(JdsParams), C.c_void_p, C.c_int,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                   C.POINTER(JdsMetrics)]),
     "jds_block_op": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_void_p]),
     "jds_selected_block": (C.c_int, [C.c_void_p, C.POINTER(JdsParams), C.c_void_p, C.c_int,

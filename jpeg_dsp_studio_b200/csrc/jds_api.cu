@@ -64,7 +64,7 @@ struct jds_ctx {
     int plan_chunk = 1;
     double stage_ms[4] = {0, 0, 0, 0};   // forward, codec, inverse, ssim (accumulated)
     uint64_t stage_launches[4] = {0, 0, 0, 0};
-    DevBuf planes, in, recon, coeffs, errs, metrics, tables, selected;
+    DevBuf planes, in, recon, coeffs, errs, metrics, tables, selected, payload;
     void* h_metrics = nullptr;   // pinned
     size_t h_metrics_bytes = 0;
     void* h_tables = nullptr;    // pinned
@@ -174,7 +174,7 @@ extern "C" int jds_ctx_destroy(jds_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->planes, &c->in, &c->recon, &c->coeffs, &c->errs,
-                      &c->metrics, &c->tables, &c->selected};
+                      &c->metrics, &c->tables, &c->selected, &c->payload};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->h_metrics) cudaFreeHost(c->h_metrics);
@@ -723,6 +723,80 @@ extern "C" int jds_sweep(jds_ctx* c, const jds_params* p, const int32_t* qualiti
     J.out_loc = out_loc;
     J.metrics = metrics;
     return run_job(c, J);
+}
+
+// GUI plot payload: the round trip plus, instead of the 25 MB coefficient
+// array and the 66 MB fp64 error maps, what the reference's plots draw from them
+// (gui/compression_tab.py:653-676 -> gui/widgets/mpl_canvas.py:81-130): the count of every
+// coefficient value and the x10 clipped error map(s) as uint8.
+extern "C" int jds_plot_payload(jds_ctx* c, const jds_params* p, const uint8_t* rgb, int rgb_loc,
+                                uint8_t* recon, uint8_t* heat_y, uint8_t* heat_rgb,
+                                int64_t* value_hist, int out_loc, jds_metrics* metrics) {
+    if (!c || !rgb || !metrics) return fail(JDS_ERR_INVALID, "NULL argument");
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (p->quality < 1 || p->quality > 100)
+        return fail(JDS_ERR_INVALID, "Quality must be 1-100, got %d", p->quality);
+    UnitJob J;
+    memset(&J, 0, sizeof J);
+    if ((rc = make_geom(p->height, p->width, p->subsampling, &J.g))) return rc;
+    const Geom& g = J.g;
+    JDS_CUDA(cudaSetDevice(c->device));
+    const size_t px = (size_t)g.H * g.W;
+    const size_t frame_bytes = px * 3;
+    const size_t ncoef = 64ull * (size_t)(g.nblk_y + 2 * g.nblk_c);
+    const bool out_host = out_loc == JDS_HOST;
+    // scratch layout: [err_y f64][err_rgb f64][coeffs i16][hist u64][heat_y u8][heat_rgb u8][recon u8]
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t o_ey = 0, o_ergb = o_ey + up(px * 8), o_coef = o_ergb + up(heat_rgb ? px * 8 : 0);
+    const size_t o_hist = o_coef + up(value_hist ? ncoef * 2 : 0);
+    const size_t o_hy = o_hist + up(VALUE_HIST_BINS * 8), o_hrgb = o_hy + up(px);
+    const size_t o_recon = o_hrgb + up(px), total = o_recon + up(frame_bytes);
+    if ((rc = ensure(c, c->payload, total))) return rc;
+    char* base = (char*)c->payload.p;
+    const uint8_t* d_rgb = rgb;
+    if (rgb_loc == JDS_HOST) {
+        if ((rc = ensure(c, c->in, frame_bytes))) return rc;
+        JDS_CUDA(cudaMemcpyAsync(c->in.p, rgb, frame_bytes, cudaMemcpyHostToDevice, c->stream));
+        d_rgb = (const uint8_t*)c->in.p;
+    }
+    jds_params q = *p;
+    q.outputs = (p->outputs & (JDS_OUT_SSIM | JDS_OUT_PSNR | JDS_OUT_HIST)) | JDS_OUT_RECON;
+    if (heat_y) q.outputs |= JDS_OUT_ERR_Y;
+    if (heat_rgb) q.outputs |= JDS_OUT_ERR_RGB;
+    if (value_hist) q.outputs |= JDS_OUT_COEFFS;
+    J.p = &q;
+    J.units = 1;
+    J.rgb = d_rgb;
+    J.rgb_loc = JDS_DEVICE;
+    J.recon = (recon && !out_host) ? recon : (uint8_t*)(base + o_recon);
+    J.coeffs = value_hist ? (int16_t*)(base + o_coef) : nullptr;
+    J.err_y = heat_y ? (double*)(base + o_ey) : nullptr;
+    J.err_rgb = heat_rgb ? (double*)(base + o_ergb) : nullptr;
+    J.out_loc = JDS_DEVICE;
+    J.metrics = metrics;
+    if ((rc = run_job(c, J))) return rc;
+    cudaStream_t s = c->stream;
+    unsigned long long* d_hist = (unsigned long long*)(base + o_hist);
+    if (value_hist) {
+        JDS_CUDA(cudaMemsetAsync(d_hist, 0, VALUE_HIST_BINS * 8, s));
+        launch_value_hist(J.coeffs, ncoef, d_hist, c->sm_count, s);
+        c->launches++;
+    }
+    uint8_t* d_hy = (heat_y && !out_host) ? heat_y : (uint8_t*)(base + o_hy);
+    uint8_t* d_hrgb = (heat_rgb && !out_host) ? heat_rgb : (uint8_t*)(base + o_hrgb);
+    if (heat_y) { launch_heat_u8(J.err_y, d_hy, px, s); c->launches++; }
+    if (heat_rgb) { launch_heat_u8(J.err_rgb, d_hrgb, px, s); c->launches++; }
+    JDS_CUDA(cudaGetLastError());
+    const cudaMemcpyKind kind = out_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    if (value_hist) JDS_CUDA(cudaMemcpyAsync(value_hist, d_hist, VALUE_HIST_BINS * 8, kind, s));
+    if (out_host) {
+        if (heat_y) JDS_CUDA(cudaMemcpyAsync(heat_y, d_hy, px, kind, s));
+        if (heat_rgb) JDS_CUDA(cudaMemcpyAsync(heat_rgb, d_hrgb, px, kind, s));
+        if (recon) JDS_CUDA(cudaMemcpyAsync(recon, J.recon, frame_bytes, kind, s));
+    }
+    JDS_CUDA(cudaStreamSynchronize(s));
+    return JDS_OK;
 }
 
 extern "C" int jds_selected_block(jds_ctx* c, const jds_params* p, const uint8_t* rgb,

@@ -434,6 +434,71 @@ void launch_hist50(const int16_t* coeffs, size_t coeff_stride, size_t n_coeffs, 
 }
 
 // ------------------------------------------------------------------------------
+// GUI plot payload: what the reference's plots draw, reduced on the device
+//   * value histogram: count of every int16 coefficient value (index v + 1024); the host
+//     bins it the way matplotlib's ax.hist / np.histogram(bins=50) does
+//     (gui/widgets/mpl_canvas.py:81-100, gui/compression_tab.py:662-667)
+//   * heat map: clip(err * 10, 0, 255) (gui/widgets/mpl_canvas.py:116-118) truncated to uint8
+// ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(HIST_WARPS * 32)
+k_value_hist(const int16_t* __restrict__ coeffs, size_t n_coeffs,
+             unsigned long long* __restrict__ hist) {
+    __shared__ unsigned int s_h[VALUE_HIST_BINS];
+    const int lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < VALUE_HIST_BINS; i += blockDim.x) s_h[i] = 0;
+    __syncthreads();
+    const uint4* src = reinterpret_cast<const uint4*>(coeffs);
+    const size_t n_vec = n_coeffs / 8;
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_vec;
+         v += (size_t)gridDim.x * blockDim.x) {
+        const uint4 q = __ldg(src + v);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int val = (int)(int16_t)(w[k >> 1] >> ((k & 1) * 16));
+            const int b = val + VALUE_HIST_BINS / 2;          // |val| <= 1016 by construction
+            const unsigned peers = __match_any_sync(__activemask(), b);
+            if ((unsigned)b < (unsigned)VALUE_HIST_BINS && lane == (__ffs(peers) - 1))
+                atomicAdd(&s_h[b], (unsigned)__popc(peers));
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < VALUE_HIST_BINS; b += blockDim.x)
+        if (s_h[b]) atomicAdd(&hist[b], (unsigned long long)s_h[b]);
+}
+
+void launch_value_hist(const int16_t* coeffs, size_t n_coeffs, unsigned long long* hist,
+                       int sm_count, cudaStream_t s) {
+    size_t want = (n_coeffs / 8 + HIST_WARPS * 32 - 1) / (HIST_WARPS * 32);
+    unsigned gx = (unsigned)(want < (size_t)sm_count * 8 ? (want ? want : 1) : (size_t)sm_count * 8);
+    k_value_hist<<<gx, HIST_WARPS * 32, 0, s>>>(coeffs, n_coeffs, hist);
+}
+
+__global__ void __launch_bounds__(256)
+k_heat_u8(const double* __restrict__ err, uint8_t* __restrict__ out, size_t n) {
+    // four pixels per thread; the un-fused multiply and the clip are numpy's
+    const size_t i4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i4 >= n) return;
+    if (i4 + 4 <= n && ((uintptr_t)(out + i4) & 3) == 0) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double v = fmin(fmax(__dmul_rn(err[i4 + k], 10.0), 0.0), 255.0);
+            w |= (uint32_t)(int)v << (8 * k);
+        }
+        *reinterpret_cast<uint32_t*>(out + i4) = w;
+    } else {
+        for (size_t i = i4; i < n && i < i4 + 4; ++i)
+            out[i] = (uint8_t)(int)fmin(fmax(__dmul_rn(err[i], 10.0), 0.0), 255.0);
+    }
+}
+
+void launch_heat_u8(const double* err, uint8_t* out, size_t n, cudaStream_t s) {
+    const size_t threads = (n + 3) / 4;
+    k_heat_u8<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(err, out, n);
+}
+
+// ------------------------------------------------------------------------------
 // stand-alone 8x8 block operators of engines/dct_engine.py:7-27 and
 // engines/quantizer.py:22-29, exact arithmetic, one block per thread
 // ------------------------------------------------------------------------------

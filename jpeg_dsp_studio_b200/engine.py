@@ -86,6 +86,45 @@ def _precision_code(precision) -> int:
         raise ValueError(f"precision must be 'exact' or 'fast', got {precision!r}") from None
 
 
+def histogram_from_values(value_hist: np.ndarray, bins: int = 50):
+    """``np.histogram(coeffs, bins)`` - what matplotlib's ``ax.hist(coeffs, bins=bins)``
+    computes (gui/widgets/mpl_canvas.py:96) - from the per-value counts: the distinct
+    values go through NumPy's own binning as an int16 array weighted by their counts, so the
+    bin edges and every count equal those of the full coefficient array (counts < 2^53 are
+    exact as fp64 weights).  Returns (int64 counts, fp64 edges)."""
+    value_hist = np.asarray(value_hist)
+    present = np.nonzero(value_hist)[0]
+    if present.size == 0:
+        return np.histogram(np.zeros(0, dtype=np.int16), bins=bins)
+    values = (present - len(value_hist) // 2).astype(np.int16)
+    counts, edges = np.histogram(values, bins=bins, range=(float(values.min()), float(values.max())),
+                                 weights=value_hist[present].astype(np.float64))
+    return counts.astype(np.int64), edges
+
+
+class PlotPayload:
+    """Result of Engine.plot_payload: ``reconstructed_image`` (uint8 H x W x 3),
+    ``error_heat_y`` / ``error_heat_rgb`` (uint8 H x W = trunc(clip(error_map * 10, 0, 255)),
+    gui/widgets/mpl_canvas.py:116-118), ``value_hist`` (int64[2048], value v at v + 1024),
+    ``hist_counts`` / ``hist_edges`` (the 50-bin histogram matplotlib would draw), and the
+    scalar metrics through ``outputs.scalars``."""
+    __slots__ = ("reconstructed_image", "error_heat_y", "error_heat_rgb", "value_hist",
+                 "hist_counts", "hist_edges", "outputs")
+
+    def __init__(self, recon, heat_y, heat_rgb, value_hist, counts, edges, outputs):
+        self.reconstructed_image = recon
+        self.error_heat_y = heat_y
+        self.error_heat_rgb = heat_rgb
+        self.value_hist = value_hist
+        self.hist_counts = counts
+        self.hist_edges = edges
+        self.outputs = outputs
+
+    @property
+    def scalars(self):
+        return self.outputs.scalars
+
+
 class Engine:
     """A libjds context bound to one CUDA device."""
 
@@ -209,6 +248,44 @@ class Engine:
             N.check(self._lib.jds_roundtrip(self._ctx, C.byref(p), ptr, loc, gp(recon), gp(coeffs),
                                             gp(ey), gp(ergb), loc, C.byref(m)))
         return RoundTripOutputs(recon, coeffs, ey, ergb, m, (h, w))
+
+    # -- GUI plot payload -------------------------------------------------
+    def plot_payload(self, image, quality=50, mode="4:2:0", prefilter=False, *,
+                     precision="exact", want_heat_rgb=False, want_ssim=True,
+                     bins=50) -> "PlotPayload":
+        """What the reference's analysis plots draw (gui/compression_tab.py:653-676), reduced
+        on the device: the coefficient histogram as matplotlib's ``ax.hist(coeffs, bins)``
+        would compute it and the x10 clipped error map as uint8 - about 1 byte per pixel
+        back instead of the 3 B/px int16 coefficients and 8 B/px fp64 error maps."""
+        h, w, _ = self._frame_geometry(image)
+        ptr, loc, keep = self._in_ptr(image)
+        flags = N.JDS_OUT_RECON | N.JDS_OUT_PSNR | (N.JDS_OUT_SSIM if want_ssim else 0)
+        p = self._params(h, w, quality, mode, prefilter, precision, flags)
+        m = N.JdsMetrics()
+        vhist = host_array((N.JDS_VALUE_HIST_BINS,), np.int64)
+        if loc == N.JDS_DEVICE:
+            import torch
+            dev = keep.device
+            recon = torch.empty((h, w, 3), dtype=torch.uint8, device=dev)
+            heat_y = torch.empty((h, w), dtype=torch.uint8, device=dev)
+            heat_rgb = torch.empty((h, w), dtype=torch.uint8, device=dev) if want_heat_rgb else None
+            d_hist = torch.empty(N.JDS_VALUE_HIST_BINS, dtype=torch.int64, device=dev)
+            hist_ptr = C.c_void_p(d_hist.data_ptr())
+        else:
+            recon = host_array((h, w, 3), np.uint8)
+            heat_y = host_array((h, w), np.uint8)
+            heat_rgb = host_array((h, w), np.uint8) if want_heat_rgb else None
+            d_hist = None
+            hist_ptr = C.c_void_p(vhist.ctypes.data)
+        gp = lambda t: None if t is None else C.c_void_p(t.data_ptr() if _is_torch(t) else t.ctypes.data)
+        with self._lock:
+            N.check(self._lib.jds_plot_payload(self._ctx, C.byref(p), ptr, loc, gp(recon), gp(heat_y),
+                                               gp(heat_rgb), hist_ptr, loc, C.byref(m)))
+        if d_hist is not None:
+            vhist = d_hist.cpu().numpy()
+        counts, edges = histogram_from_values(vhist, bins)
+        return PlotPayload(recon, heat_y, heat_rgb, np.asarray(vhist), counts, edges,
+                           RoundTripOutputs(recon, None, None, None, m, (h, w)))
 
     def selected_block(self, image, quality, block_row, block_col):
         """IntermediateData.selected_block_* (engines/pipeline.py:126-151) or None."""

@@ -6,8 +6,8 @@ own unit tests exercise."""
 from ..utils.constants import JPEG_LUMA_Q50
 from .dct_engine import dct2, idct2, encode_block, decode_block
 from .quantizer import scale_quant_matrix, quantize, dequantize
-from .pipeline import compress_reconstruct, quality_sweep, compress_batch
+from .pipeline import compress_reconstruct, quality_sweep, compress_batch, plot_payload
 
 __all__ = ['dct2', 'idct2', 'encode_block', 'decode_block', 'scale_quant_matrix', 'quantize',
            'dequantize', 'JPEG_LUMA_Q50', 'compress_reconstruct', 'quality_sweep',
-           'compress_batch']
+           'compress_batch', 'plot_payload']

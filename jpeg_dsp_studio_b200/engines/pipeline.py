@@ -174,3 +174,29 @@ def compress_batch(frames, params: CompressionParams, *, precision: str = "fast"
             decode_time_ms=max(wall_ms / max(len(outs), 1) - float(o.metrics.gpu_ms), 0.0),
             bitrate_label=BITRATE_LABEL))
     return results
+
+
+def plot_payload(image_rgb, params: CompressionParams, *, precision: str = "exact",
+                 device: Optional[int] = None, want_heat_rgb: bool = False, bins: int = 50):
+    """The round trip for the GUI's analysis plots (gui/compression_tab.py:653-676) without
+    the bulky intermediates: returns ``(CompressionResult, PlotPayload)`` where the payload
+    holds the 50-bin coefficient histogram exactly as ``ax.hist(all_quantized_coeffs, 50)``
+    computes it (gui/widgets/mpl_canvas.py:96) and ``clip(error_map_y * 10, 0, 255)``
+    (mpl_canvas.py:118) as uint8 - bit-identical to reducing the reference's arrays in
+    ``precision="exact"``."""
+    image_rgb = _validate(image_rgb, params)
+    eng = get_engine(device)
+    t0 = time.perf_counter()
+    pay = eng.plot_payload(image_rgb, params.quality, params.subsampling_mode, params.use_prefilter,
+                           precision=precision, want_heat_rgb=want_heat_rgb, bins=bins)
+    wall_ms = (time.perf_counter() - t0) * 1000.0
+    s = pay.scalars
+    gpu_ms = float(pay.outputs.metrics.gpu_ms)
+    result = CompressionResult(
+        original_image=image_rgb, reconstructed_image=pay.reconstructed_image,
+        psnr_y=s['psnr_y'], ssim_y=s['ssim_y'], psnr_rgb=s['psnr_rgb'], ssim_rgb=s['ssim_rgb'],
+        bpp=s['bpp'], compression_ratio=s['compression_ratio'],
+        nonzero_coeffs=s['nonzero_count'], total_coeffs=s['total_coeffs'],
+        encode_time_ms=gpu_ms, decode_time_ms=max(wall_ms - gpu_ms, 0.0),
+        bitrate_label=BITRATE_LABEL)
+    return result, pay

@@ -151,3 +151,27 @@ def test_bitrate_finalisation_matches_reference_float32_arithmetic(golden_cases)
         else:
             assert abs(b["bpp"] - g["bpp"]) <= 2e-7 * g["bpp"]
     assert n_equal >= 15
+
+
+def test_histogram_from_value_counts_equals_numpy_histogram_of_the_coefficients():
+    """SURVEY 8f #2 host logic: binning the per-value counts (what the device returns) through
+    np.histogram equals np.histogram of the full coefficient array (what matplotlib's ax.hist
+    computes, gui/widgets/mpl_canvas.py:96) - counts and edges, any bin count."""
+    from jpeg_dsp_studio_b200.engine import histogram_from_values
+    from tests import cases as CS
+    for seed, q, mode in ((1, 10, "4:2:0"), (2, 50, "4:4:4"), (3, 95, "4:2:2")):
+        img = CS.rand_rgb(seed, 64, 80)
+        coeffs = P.compress_reconstruct(img, q, mode, False, want_maps=False)["all_quantized_coeffs"]
+        vals, cnt = np.unique(coeffs, return_counts=True)
+        vh = np.zeros(2048, dtype=np.int64)
+        vh[vals.astype(np.int64) + 1024] = cnt
+        for bins in (7, 50, 64):
+            c, e = histogram_from_values(vh, bins)
+            wc, we = np.histogram(coeffs.flatten(), bins=bins)
+            assert np.array_equal(c, wc) and np.array_equal(e, we)
+    # a single distinct value (flat frame): numpy widens the range by +-0.5
+    vh = np.zeros(2048, dtype=np.int64)
+    vh[1024] = 4096
+    c, e = histogram_from_values(vh, 50)
+    wc, we = np.histogram(np.zeros(4096, dtype=np.int16), bins=50)
+    assert np.array_equal(c, wc) and np.array_equal(e, we)
