@@ -257,14 +257,7 @@ static int make_geom(int H, int W, int sub, Geom* g) {
         case 0: return JDS_OK;
         case 1: return fail(JDS_ERR_INVALID, "bad frame size %dx%d", H, W);
         case 2: return fail(JDS_ERR_INVALID, "Unknown subsampling mode: %d", sub);
-        case 3:
-            return fail(JDS_ERR_UNSUPPORTED,
-                        "odd width %d with chroma subsampling: OpenCV's fractional INTER_AREA / "
-                        "non-2x INTER_LINEAR path is not implemented", W);
-        default:
-            return fail(JDS_ERR_UNSUPPORTED,
-                        "odd height %d with 4:2:0: OpenCV's fractional INTER_AREA / non-2x "
-                        "INTER_LINEAR path is not implemented", H);
+        default: return fail(JDS_ERR_INVALID, "bad frame geometry %dx%d mode %d", H, W, sub);
     }
 }
 

@@ -8,13 +8,16 @@
 
 namespace jds {
 
-// returns 0 ok, 1 bad size, 2 bad mode, 3 odd width (subsampled), 4 odd height (4:2:0)
+// returns 0 ok, 1 bad size, 2 bad mode
 inline int geom_init(int H, int W, int sub, Geom* g) {
     if (H < 1 || W < 1) return 1;
     if (sub < 0 || sub > 2) return 2;
-    if (sub != 0 && (W % 2)) return 3;
-    if (sub == 2 && (H % 2)) return 4;
+    if (sub != 0 && W < 2) return 1;              // cv2.resize to width 0 raises
+    if (sub == 2 && H < 2) return 1;
     memset(g, 0, sizeof *g);
+    // an odd width (odd height under 4:2:0) sends cv2.resize(INTER_AREA) down its general
+    // (fractional) path for both axes
+    g->general = (sub != 0 && (W % 2)) || (sub == 2 && (H % 2));
     g->H = H;
     g->W = W;
     g->sub = sub;

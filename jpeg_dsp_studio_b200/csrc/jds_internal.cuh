@@ -14,6 +14,7 @@ struct Geom {
     int nbx_y, nby_y, nbx_c, nby_c;   // 8x8 blocks per plane
     int sub;         // JDS_SUB_*
     int W4;          // 4*floor(W/4): columns the OpenCV blur row pass does with FMA (A2)
+    int general;     // chroma decimation by fractional-area weights (odd W, or odd H at 4:2:0)
     double sx, sy;   // wc/W, hc/H: cv2.resize(INTER_LINEAR) source step (A8)
     long long nblk_y, nblk_c;         // blocks per plane
     long long plane_y, plane_c;       // elements per padded plane

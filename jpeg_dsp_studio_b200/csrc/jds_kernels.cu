@@ -43,6 +43,23 @@ k_forward(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
     forward_cell<P, SUB, PF>(g, in, cx, cy, Y, Cb, Cr);
 }
 
+// general geometry (odd width, or odd height under 4:2:0): one thread per luma pixel; the
+// threads inside the chroma plane also produce one area-weighted chroma sample each
+template <class P, bool PF>
+__global__ void __launch_bounds__(256)
+k_forward_general(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
+                  typename P::T* __restrict__ fwd, size_t fwd_stride) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= g.W || y >= g.H) return;
+    const uint8_t* in = rgb + (size_t)blockIdx.z * rgb_stride;
+    typename P::T* Y = fwd + (size_t)blockIdx.z * fwd_stride;
+    typename P::T* Cb = Y + g.plane_y;
+    typename P::T* Cr = Cb + g.plane_c;
+    forward_luma<P>(g, in, x, y, Y);
+    if (x < g.wc && y < g.hc) forward_chroma_area<P, PF>(g, in, x, y, Cb, Cr);
+}
+
 // ------------------------------------------------------------------------------
 // Stage 2
 // ------------------------------------------------------------------------------
@@ -560,6 +577,14 @@ void launch_block_ops(int op, long long n_blocks, const double* in, const int16_
 template <class P>
 static void launch_forward_t(const Geom& g, int prefilter, const uint8_t* rgb, size_t rgb_stride,
                              typename P::T* fwd, size_t fwd_stride, int units, cudaStream_t s) {
+    if (g.general) {
+        dim3 blk(32, 8), grid((g.W + 31) / 32, (g.H + 7) / 8, units);
+        if (prefilter)
+            k_forward_general<P, true><<<grid, blk, 0, s>>>(g, rgb, rgb_stride, fwd, fwd_stride);
+        else
+            k_forward_general<P, false><<<grid, blk, 0, s>>>(g, rgb, rgb_stride, fwd, fwd_stride);
+        return;
+    }
     dim3 blk(32, 8), grid((g.wc + 31) / 32, (g.hc + 7) / 8, units);
     if (g.sub == 0)
         k_forward<P, 0, false><<<grid, blk, 0, s>>>(g, rgb, rgb_stride, fwd, fwd_stride);

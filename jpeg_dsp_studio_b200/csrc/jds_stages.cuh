@@ -91,6 +91,112 @@ JDS_HD void forward_cell(const Geom& g, const uint8_t* __restrict__ rgb, int cx,
 }
 
 // ------------------------------------------------------------------------------
+// Stage 1, general geometry: an odd width (or an odd height under 4:2:0) makes
+// cv2.resize(INTER_AREA) (engines/color_space.py:44-49) leave its integer-factor path and
+// weight every source sample by its overlap with the destination cell
+// (OpenCV imgproc/resize.cpp computeResizeAreaTab + ResizeArea_Invoker<double,double>).
+// ------------------------------------------------------------------------------
+struct AreaTaps {
+    int s0;          // first source index; taps are s0 .. s0+n-1
+    int n;           // 1..4 for shrink factors in [1, 3)
+    float a[4];      // weights, rounded to float like DecimateAlpha::alpha
+};
+
+// Taps of destination index d.  Every operation is an individually rounded fp64 one, in
+// OpenCV's order (both policies: the taps are geometry, not signal).
+JDS_HD void area_taps(int ssize, int dsize, int d, AreaTaps& t) {
+    typedef Exact E;
+    const double scale = E::div((double)ssize, (double)dsize);
+    const double fsx1 = E::mul((double)d, scale);
+    const double fsx2 = E::add(fsx1, scale);
+    const double rest = E::sub((double)ssize, fsx1);
+    const double cell = scale < rest ? scale : rest;
+    int sx1 = (int)ceil(fsx1), sx2 = (int)floor(fsx2);
+    if (sx2 > ssize - 1) sx2 = ssize - 1;
+    if (sx1 > sx2) sx1 = sx2;
+    t.n = 0;
+    t.s0 = sx1;
+    const double left = E::sub((double)sx1, fsx1);
+    if (left > 1e-3) {
+        t.s0 = sx1 - 1;
+        t.a[t.n++] = (float)E::div(left, cell);
+    }
+    const float full = (float)E::div(1.0, cell);
+    for (int sx = sx1; sx < sx2 && t.n < 4; ++sx) t.a[t.n++] = full;
+    const double right = E::sub(fsx2, (double)sx2);
+    if (right > 1e-3 && t.n < 4) {
+        double m = right < 1.0 ? right : 1.0;
+        if (cell < m) m = cell;
+        t.a[t.n++] = (float)E::div(m, cell);
+    }
+}
+
+// full-resolution Cb, Cr of pixel (y, x), after the optional 3x3 prefilter (A2)
+template <class P, bool PF>
+JDS_HD void chroma_at(const Geom& g, const uint8_t* __restrict__ rgb, int y, int x,
+                      typename P::T& cb, typename P::T& cr) {
+    typedef typename P::T T;
+    if (!PF) {
+        T r, gg, b;
+        load_rgb<P>(rgb, g.W, y, x, r, gg, b);
+        rgb_to_cbcr<P>(r, gg, b, cb, cr);
+        return;
+    }
+    T rb[3], rr[3];
+    const bool tail = x >= g.W4;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int yy = reflect101(y - 1 + i, g.H);
+        T vb[3], vr[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            T r, gg, b;
+            load_rgb<P>(rgb, g.W, yy, reflect101(x - 1 + j, g.W), r, gg, b);
+            rgb_to_cbcr<P>(r, gg, b, vb[j], vr[j]);
+        }
+        rb[i] = blur_row<P>(vb[0], vb[1], vb[2], tail);
+        rr[i] = blur_row<P>(vr[0], vr[1], vr[2], tail);
+    }
+    cb = blur_col<P>(rb[0], rb[1], rb[2]);
+    cr = blur_col<P>(rr[0], rr[1], rr[2]);
+}
+
+// one luma sample (general geometry: the chroma cells do not tile the luma plane)
+template <class P>
+JDS_HD void forward_luma(const Geom& g, const uint8_t* __restrict__ rgb, int x, int y,
+                         typename P::T* __restrict__ Yp) {
+    typename P::T r, gg, b;
+    load_rgb<P>(rgb, g.W, y, x, r, gg, b);
+    Yp[(size_t)y * g.Wp + x] = luma601<P>(r, gg, b);
+}
+
+// one decimated chroma sample by area weighting: per source row buf = buf + S*alpha over
+// the x taps in order, then sum = beta*buf (first row) / sum + beta*buf (no FMA)
+template <class P, bool PF>
+JDS_HD void forward_chroma_area(const Geom& g, const uint8_t* __restrict__ rgb, int cx, int cy,
+                                typename P::T* __restrict__ Cbp, typename P::T* __restrict__ Crp) {
+    typedef typename P::T T;
+    AreaTaps tx, ty;
+    area_taps(g.W, g.wc, cx, tx);
+    area_taps(g.H, g.hc, cy, ty);
+    T sum_b = T(0), sum_r = T(0);
+    for (int j = 0; j < ty.n; ++j) {
+        T buf_b = T(0), buf_r = T(0);
+        for (int i = 0; i < tx.n; ++i) {
+            T cb, cr;
+            chroma_at<P, PF>(g, rgb, ty.s0 + j, tx.s0 + i, cb, cr);
+            buf_b = P::add(buf_b, P::mul(cb, T(tx.a[i])));
+            buf_r = P::add(buf_r, P::mul(cr, T(tx.a[i])));
+        }
+        const T beta = T(ty.a[j]);
+        sum_b = j == 0 ? P::mul(beta, buf_b) : P::add(sum_b, P::mul(beta, buf_b));
+        sum_r = j == 0 ? P::mul(beta, buf_r) : P::add(sum_r, P::mul(beta, buf_r));
+    }
+    Cbp[(size_t)cy * g.wcp + cx] = sum_b;
+    Crp[(size_t)cy * g.wcp + cx] = sum_r;
+}
+
+// ------------------------------------------------------------------------------
 // Stage 2: one 8x8 block: (reflect-padded) load, -128, DCT, quantise, bit model,
 // dequantise, IDCT, +128, clip.   engines/pipeline.py:47-82 inner loops,
 // engines/dct_engine.py:17-27, engines/quantizer.py:22-29.
@@ -253,7 +359,9 @@ JDS_HD void store_block(T* __restrict__ plane, int stride, int h, int w, int bx,
 // ------------------------------------------------------------------------------
 template <class P>
 JDS_HD void upsample_taps(int i, int n_src, double step, int& i0, int& i1, typename P::T& f) {
-    double ff = ((double)i + 0.5) * step - 0.5;
+    // IPP forms the source coordinate with one FMA (visible only when the factor is not
+    // exactly 2, i.e. odd sizes)
+    double ff = Exact::fma((double)i + 0.5, step, -0.5);
     double s = floor(ff);
     ff -= s;
     int si = (int)s;

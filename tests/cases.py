@@ -71,6 +71,18 @@ CASES = [
     Case("rand64x64_q1_420", lambda: rand_rgb(9, 64, 64), 1, "4:2:0", False),
     Case("rand72x40_q99_422_pf", lambda: rand_rgb(10, 72, 40), 99, "4:2:2", True, (8, 4)),
     Case("rand30x46_q25_420_pf", lambda: rand_rgb(12, 30, 46), 25, "4:2:0", True),
+    # --- odd sizes with subsampling: cv2's fractional INTER_AREA taps and IPP's non-2x
+    #     bilinear factors (engines/color_space.py:44-49, 64-65) ----------------------------
+    Case("rand33x47_q50_420", lambda: rand_rgb(20, 33, 47), 50, "4:2:0", False, (1, 2)),
+    Case("rand33x47_q50_420_pf", lambda: rand_rgb(20, 33, 47), 50, "4:2:0", True),
+    Case("rand47x33_q30_422_pf", lambda: rand_rgb(21, 47, 33), 30, "4:2:2", True),
+    Case("rand48x33_q80_420", lambda: rand_rgb(22, 48, 33), 80, "4:2:0", False),
+    Case("rand33x48_q20_420_pf", lambda: rand_rgb(23, 33, 48), 20, "4:2:0", True),
+    Case("rand99x101_q10_422", lambda: rand_rgb(24, 99, 101), 10, "4:2:2", False),
+    Case("rand9x7_q50_420_pf", lambda: rand_rgb(25, 9, 7), 50, "4:2:0", True),
+    Case("rand251x335_q75_420_pf", lambda: rand_rgb(26, 251, 335), 75, "4:2:0", True, (30, 41)),
+    Case("photo301x401_q60_420", lambda: np.ascontiguousarray(TI.generate_photo(512)[:301, :401]), 60, "4:2:0", False),
+    Case("preview853x1280_q50_420", lambda: photo_tiled(853, 1280), 50, "4:2:0", False, big=True),
     # flat image: identical round trip -> PSNR inf, SSIM 1 (SURVEY §8a error list)
     Case("flat64_q50_444", lambda: np.full((64, 64, 3), 128, np.uint8), 50, "4:4:4", False),
     Case("phototile1080p_q50_420", lambda: photo_tiled(1080, 1920), 50, "4:2:0", False, big=True),

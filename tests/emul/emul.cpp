@@ -37,7 +37,17 @@ static int run(int H, int W, int quality, int sub, int prefilter, const uint8_t*
     const size_t pe = (size_t)(g.plane_y + 2 * g.plane_c);
     std::vector<T> fwd(pe, T(0)), rec(pe, T(0));
     T *Y = fwd.data(), *Cb = Y + g.plane_y, *Cr = Cb + g.plane_c;
-    if (sub == 0) run_forward<P, 0, false>(g, rgb, Y, Cb, Cr);
+    if (g.general) {
+        for (int y = 0; y < g.H; ++y)
+            for (int x = 0; x < g.W; ++x) {
+                forward_luma<P>(g, rgb, x, y, Y);
+                if (x < g.wc && y < g.hc) {
+                    if (prefilter) forward_chroma_area<P, true>(g, rgb, x, y, Cb, Cr);
+                    else forward_chroma_area<P, false>(g, rgb, x, y, Cb, Cr);
+                }
+            }
+    }
+    else if (sub == 0) run_forward<P, 0, false>(g, rgb, Y, Cb, Cr);
     else if (sub == 1 && !prefilter) run_forward<P, 1, false>(g, rgb, Y, Cb, Cr);
     else if (sub == 1) run_forward<P, 1, true>(g, rgb, Y, Cb, Cr);
     else if (!prefilter) run_forward<P, 2, false>(g, rgb, Y, Cb, Cr);

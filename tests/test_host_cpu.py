@@ -72,11 +72,20 @@ def test_coeff_count(native, h, w, mode, want):
     assert n.value == want
 
 
-def test_odd_sizes_with_subsampling_are_refused_loudly(native):
+def test_odd_sizes_with_subsampling_are_supported(native):
+    """Odd widths / heights floor the chroma plane like cv2.resize((W//2, H//2))
+    (engines/color_space.py:44-49): 251x333 -> 125x166 chroma, padded to 128x168."""
     lib = native.load()
     n = C.c_uint64()
-    assert lib.jds_coeff_count(251, 333, native.JDS_SUB_420, C.byref(n)) == native.JDS_ERR_UNSUPPORTED
-    assert lib.jds_coeff_count(251, 333, native.JDS_SUB_444, C.byref(n)) == native.JDS_OK
+    assert lib.jds_coeff_count(251, 333, native.JDS_SUB_420, C.byref(n)) == native.JDS_OK
+    assert n.value == 64 * (32 * 42 + 2 * 16 * 21)
+    assert lib.jds_coeff_count(251, 333, native.JDS_SUB_422, C.byref(n)) == native.JDS_OK
+    assert n.value == 64 * (32 * 42 + 2 * 32 * 21)
+    ch, cw = C.c_int(), C.c_int()
+    assert lib.jds_plane_dims(251, 333, native.JDS_SUB_420, C.byref(ch), C.byref(cw)) == native.JDS_OK
+    assert (ch.value, cw.value) == (125, 166)
+    # a subsampled plane cannot have width / height 0 (cv2.resize raises there too)
+    assert lib.jds_coeff_count(8, 1, native.JDS_SUB_422, C.byref(n)) == native.JDS_ERR_INVALID
 
 
 def test_params_validation_like_reference():
