@@ -200,6 +200,19 @@ int jds_plot_payload(jds_ctx* ctx, const jds_params* params, const uint8_t* rgb,
                      int out_loc, jds_metrics* metrics);
 
 /*
+ * Preview downscale: the step in front of the round trip when the GUI's
+ * preview mode is on (gui/compression_tab.py:532-552).
+ *   jds_preview_size: the reference's size rule - frames that fit the target are kept,
+ *       otherwise scale = min(target_w/w, target_h/h), new = int(dim * scale)  (:541-547).
+ *   jds_resize_area:  cv2.resize(uint8 RGB, (out_w, out_h), interpolation=cv2.INTER_AREA)
+ *       (:549-552), bit-identical to OpenCV 4.13 for shrinking (out <= in on both axes);
+ *       enlarging returns JDS_ERR_UNSUPPORTED.  rgb / out: host or device, like jds_roundtrip.
+ */
+int jds_preview_size(int height, int width, int target_w, int target_h, int* out_h, int* out_w);
+int jds_resize_area(jds_ctx* ctx, const uint8_t* rgb, int rgb_loc, int height, int width,
+                    uint8_t* out, int out_h, int out_w, int out_loc);
+
+/*
  * Stand-alone 8x8 block operators, exact (reference) arithmetic, host buffers:
  *   op 0 dct2, 1 idct2 (engines/dct_engine.py:7-14), 2 encode_block (-128 then DCT, :17-20),
  *   3 decode_block (IDCT, +128, clip, :23-27): in/out = n_blocks*64 fp64;

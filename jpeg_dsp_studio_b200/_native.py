@@ -70,6 +70,10 @@ PROTOTYPES = {
     "jds_plot_payload": (C.c_int, [C.c_void_p, C.POINTER(JdsParams), C.c_void_p, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                    C.POINTER(JdsMetrics)]),
+    "jds_preview_size": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int),
+                                   C.POINTER(C.c_int)]),
+    "jds_resize_area": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                  C.c_int, C.c_int, C.c_int]),
     "jds_block_op": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_void_p]),
     "jds_selected_block": (C.c_int, [C.c_void_p, C.POINTER(JdsParams), C.c_void_p, C.c_int,

@@ -792,6 +792,59 @@ extern "C" int jds_plot_payload(jds_ctx* c, const jds_params* p, const uint8_t* 
     return JDS_OK;
 }
 
+// Preview downscale in front of the round trip (gui/compression_tab.py:532-552)
+extern "C" int jds_preview_size(int height, int width, int target_w, int target_h, int* out_h,
+                                int* out_w) {
+    if (!out_h || !out_w) return fail(JDS_ERR_INVALID, "NULL argument");
+    if (height < 1 || width < 1 || target_w < 1 || target_h < 1)
+        return fail(JDS_ERR_INVALID, "bad preview geometry %dx%d -> %dx%d", height, width, target_h, target_w);
+    if (width <= target_w && height <= target_h) {       // :541-543: small images are kept
+        *out_h = height;
+        *out_w = width;
+        return JDS_OK;
+    }
+    // :545-547 in Python floats (IEEE double): scale = min(tw / w, th / h); int() truncates
+    volatile double sx = (double)target_w / (double)width, sy = (double)target_h / (double)height;
+    volatile double scale = sx < sy ? sx : sy;
+    volatile double fw = (double)width * scale, fh = (double)height * scale;
+    *out_w = (int)fw;
+    *out_h = (int)fh;
+    return JDS_OK;
+}
+
+extern "C" int jds_resize_area(jds_ctx* c, const uint8_t* rgb, int rgb_loc, int height, int width,
+                               uint8_t* out, int out_h, int out_w, int out_loc) {
+    if (!c || !rgb || !out) return fail(JDS_ERR_INVALID, "NULL argument");
+    if (height < 1 || width < 1 || out_h < 1 || out_w < 1)
+        return fail(JDS_ERR_INVALID, "bad resize geometry %dx%d -> %dx%d", height, width, out_h, out_w);
+    if (out_h > height || out_w > width)
+        return fail(JDS_ERR_UNSUPPORTED, "INTER_AREA enlargement (%dx%d -> %dx%d) is not part of the "
+                    "preview path", height, width, out_h, out_w);
+    JDS_CUDA(cudaSetDevice(c->device));
+    const size_t in_bytes = (size_t)height * width * 3, out_bytes = (size_t)out_h * out_w * 3;
+    int rc;
+    const uint8_t* d_in = rgb;
+    uint8_t* d_out = out;
+    cudaStream_t s = c->stream;
+    if (rgb_loc == JDS_HOST) {
+        if ((rc = ensure(c, c->in, in_bytes))) return rc;
+        JDS_CUDA(cudaMemcpyAsync(c->in.p, rgb, in_bytes, cudaMemcpyHostToDevice, s));
+        d_in = (const uint8_t*)c->in.p;
+    }
+    if (out_loc == JDS_HOST) {
+        if ((rc = ensure(c, c->recon, out_bytes))) return rc;
+        d_out = (uint8_t*)c->recon.p;
+    }
+    if (launch_resize_area_u8(height, width, out_h, out_w, d_in, d_out, s))
+        return fail(JDS_ERR_INVALID, "bad resize geometry");
+    c->launches++;
+    JDS_CUDA(cudaGetLastError());
+    if (out_loc == JDS_HOST)
+        JDS_CUDA(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, s));
+    JDS_CUDA(cudaStreamSynchronize(s));
+    return JDS_OK;
+}
+
 extern "C" int jds_selected_block(jds_ctx* c, const jds_params* p, const uint8_t* rgb,
                                   int rgb_loc, int block_row, int block_col,
                                   double original[64], double shifted[64], double dct[64],

@@ -96,15 +96,20 @@ JDS_HD void forward_cell(const Geom& g, const uint8_t* __restrict__ rgb, int cx,
 // weight every source sample by its overlap with the destination cell
 // (OpenCV imgproc/resize.cpp computeResizeAreaTab + ResizeArea_Invoker<double,double>).
 // ------------------------------------------------------------------------------
-struct AreaTaps {
-    int s0;          // first source index; taps are s0 .. s0+n-1
-    int n;           // 1..4 for shrink factors in [1, 3)
-    float a[4];      // weights, rounded to float like DecimateAlpha::alpha
+struct AreaSpan {
+    int s0;            // first source index; the taps are s0 .. s0+n-1
+    int n;
+    float al, af, ar;  // weights of a partial first tap, of the whole taps, of a partial last
+                       // tap - rounded to float like OpenCV's DecimateAlpha::alpha
+    bool left, right;  // is the first / last tap a partial one?
+    JDS_HD float weight(int i) const {
+        return (i == 0 && left) ? al : ((i == n - 1 && right) ? ar : af);
+    }
 };
 
-// Taps of destination index d.  Every operation is an individually rounded fp64 one, in
-// OpenCV's order (both policies: the taps are geometry, not signal).
-JDS_HD void area_taps(int ssize, int dsize, int d, AreaTaps& t) {
+// Taps of destination index d when `ssize` samples shrink to `dsize`.  Every operation is an
+// individually rounded fp64 one, in OpenCV's order (both policies: taps are geometry).
+JDS_HD void area_span(int ssize, int dsize, int d, AreaSpan& t) {
     typedef Exact E;
     const double scale = E::div((double)ssize, (double)dsize);
     const double fsx1 = E::mul((double)d, scale);
@@ -114,21 +119,17 @@ JDS_HD void area_taps(int ssize, int dsize, int d, AreaTaps& t) {
     int sx1 = (int)ceil(fsx1), sx2 = (int)floor(fsx2);
     if (sx2 > ssize - 1) sx2 = ssize - 1;
     if (sx1 > sx2) sx1 = sx2;
-    t.n = 0;
-    t.s0 = sx1;
-    const double left = E::sub((double)sx1, fsx1);
-    if (left > 1e-3) {
-        t.s0 = sx1 - 1;
-        t.a[t.n++] = (float)E::div(left, cell);
-    }
-    const float full = (float)E::div(1.0, cell);
-    for (int sx = sx1; sx < sx2 && t.n < 4; ++sx) t.a[t.n++] = full;
-    const double right = E::sub(fsx2, (double)sx2);
-    if (right > 1e-3 && t.n < 4) {
-        double m = right < 1.0 ? right : 1.0;
-        if (cell < m) m = cell;
-        t.a[t.n++] = (float)E::div(m, cell);
-    }
+    const double lw = E::sub((double)sx1, fsx1);
+    const double rw = E::sub(fsx2, (double)sx2);
+    t.left = lw > 1e-3;
+    t.right = rw > 1e-3;
+    t.s0 = t.left ? sx1 - 1 : sx1;
+    t.n = (sx2 - sx1) + (t.left ? 1 : 0) + (t.right ? 1 : 0);
+    t.al = (float)E::div(lw, cell);
+    t.af = (float)E::div(1.0, cell);
+    double m = rw < 1.0 ? rw : 1.0;
+    if (cell < m) m = cell;
+    t.ar = (float)E::div(m, cell);
 }
 
 // full-resolution Cb, Cr of pixel (y, x), after the optional 3x3 prefilter (A2)
@@ -176,19 +177,19 @@ template <class P, bool PF>
 JDS_HD void forward_chroma_area(const Geom& g, const uint8_t* __restrict__ rgb, int cx, int cy,
                                 typename P::T* __restrict__ Cbp, typename P::T* __restrict__ Crp) {
     typedef typename P::T T;
-    AreaTaps tx, ty;
-    area_taps(g.W, g.wc, cx, tx);
-    area_taps(g.H, g.hc, cy, ty);
+    AreaSpan tx, ty;
+    area_span(g.W, g.wc, cx, tx);
+    area_span(g.H, g.hc, cy, ty);
     T sum_b = T(0), sum_r = T(0);
     for (int j = 0; j < ty.n; ++j) {
         T buf_b = T(0), buf_r = T(0);
         for (int i = 0; i < tx.n; ++i) {
             T cb, cr;
             chroma_at<P, PF>(g, rgb, ty.s0 + j, tx.s0 + i, cb, cr);
-            buf_b = P::add(buf_b, P::mul(cb, T(tx.a[i])));
-            buf_r = P::add(buf_r, P::mul(cr, T(tx.a[i])));
+            buf_b = P::add(buf_b, P::mul(cb, T(tx.weight(i))));
+            buf_r = P::add(buf_r, P::mul(cr, T(tx.weight(i))));
         }
-        const T beta = T(ty.a[j]);
+        const T beta = T(ty.weight(j));
         sum_b = j == 0 ? P::mul(beta, buf_b) : P::add(sum_b, P::mul(beta, buf_b));
         sum_r = j == 0 ? P::mul(beta, buf_r) : P::add(sum_r, P::mul(beta, buf_r));
     }

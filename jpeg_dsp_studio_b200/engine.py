@@ -287,6 +287,23 @@ class Engine:
         return PlotPayload(recon, heat_y, heat_rgb, np.asarray(vhist), counts, edges,
                            RoundTripOutputs(recon, None, None, None, m, (h, w)))
 
+    # -- preview downscale (gui/compression_tab.py:532-552) ----------------
+    def resize_area(self, image, out_h: int, out_w: int):
+        """cv2.resize(image, (out_w, out_h), interpolation=cv2.INTER_AREA) for a uint8
+        H x W x 3 frame being shrunk; output follows the input's location."""
+        h, w, _ = self._frame_geometry(image)
+        ptr, loc, keep = self._in_ptr(image)
+        if loc == N.JDS_DEVICE:
+            import torch
+            out = torch.empty((out_h, out_w, 3), dtype=torch.uint8, device=keep.device)
+            optr = C.c_void_p(out.data_ptr())
+        else:
+            out = host_array((out_h, out_w, 3), np.uint8)
+            optr = C.c_void_p(out.ctypes.data)
+        with self._lock:
+            N.check(self._lib.jds_resize_area(self._ctx, ptr, loc, h, w, optr, int(out_h), int(out_w), loc))
+        return out
+
     def selected_block(self, image, quality, block_row, block_col):
         """IntermediateData.selected_block_* (engines/pipeline.py:126-151) or None."""
         h, w, _ = self._frame_geometry(image)

@@ -3,6 +3,7 @@ minus file I/O which is out of scope)."""
 
 from .constants import JPEG_LUMA_Q50, ZIGZAG_ORDER
 from .metrics import Timer, metrics_from_partials, bitrate_from_partials, psnr_from_sse
+from .preview import PREVIEW_RESOLUTIONS, preview_size, make_preview
 from .test_images import (generate_colored_checkerboard, generate_thin_stripes,
                           generate_gradient, generate_text_edges, generate_chroma_stripes,
                           generate_photo, generate_demo_image)
@@ -12,5 +13,5 @@ __all__ = [
     'bitrate_from_partials', 'psnr_from_sse',
     'generate_colored_checkerboard', 'generate_thin_stripes', 'generate_gradient',
     'generate_text_edges', 'generate_chroma_stripes', 'generate_photo',
-    'generate_demo_image',
+    'generate_demo_image', 'PREVIEW_RESOLUTIONS', 'preview_size', 'make_preview',
 ]

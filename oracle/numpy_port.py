@@ -512,3 +512,56 @@ def compress_reconstruct(image_rgb, quality=50, mode="4:2:0", prefilter=False,
     out["selected_block"] = sel
     out["selected_block_idx"] = selected_block_idx
     return out
+
+
+# ------------------------------------------------------------------------------------------
+# Preview downscale in front of the round trip
+# ------------------------------------------------------------------------------------------
+def preview_size(h, w, target_w, target_h):
+    """/root/reference/gui/compression_tab.py:538-547 (_update_preview_image)."""
+    if w <= target_w and h <= target_h:
+        return h, w
+    scale = min(target_w / w, target_h / h)
+    return int(h * scale), int(w * scale)
+
+
+def resize_area_u8(src, dh, dw):
+    """cv2.resize(uint8 H x W x C, (dw, dh), interpolation=cv2.INTER_AREA) for shrinking
+    (/root/reference/gui/compression_tab.py:549-552).  OpenCV 4.13 imgproc/resize.cpp:
+    integer factors on both axes -> resizeAreaFast_ (int sum; 2x2 -> (sum+2)>>2, else
+    saturate_cast<uchar>(sum * (1.f/area))); otherwise ResizeArea_Invoker<uchar, float>
+    with the taps of area_tab, fp32 accumulation without FMA.
+    [verified against cv2 4.13.0: tests/test_preview_cpu.py]"""
+    sh, sw, cn = src.shape
+    sx, sy = sw / dw, sh / dh
+    isx, isy = int(np.rint(sx)), int(np.rint(sy))
+    eps = np.finfo(np.float64).eps
+    if abs(sx - isx) < eps and abs(sy - isy) < eps:
+        a = src[:dh * isy, :dw * isx].reshape(dh, isy, dw, isx, cn).astype(np.int64).sum(axis=(1, 3))
+        if isx == 2 and isy == 2:
+            return ((a + 2) >> 2).astype(np.uint8)
+        v = a.astype(np.float32) * (np.float32(1.0) / np.float32(isx * isy))
+        return np.clip(np.rint(v), 0, 255).astype(np.uint8)
+    f32 = np.float32
+    S = src.astype(f32)
+    buf = np.zeros((sh, dw, cn), dtype=f32)
+    for dx, s_, a in area_tab(sw, dw):
+        buf[:, dx, :] = buf[:, dx, :] + S[:, s_, :] * f32(a)
+    out = np.zeros((dh, dw, cn), dtype=f32)
+    first = np.ones(dh, dtype=bool)
+    for dy, s_, b in area_tab(sh, dh):
+        if first[dy]:
+            out[dy] = f32(b) * buf[s_]
+            first[dy] = False
+        else:
+            out[dy] = out[dy] + f32(b) * buf[s_]
+    return np.clip(np.rint(out), 0, 255).astype(np.uint8)
+
+
+def make_preview(image, target_w, target_h):
+    """/root/reference/gui/compression_tab.py:532-552."""
+    h, w = image.shape[:2]
+    nh, nw = preview_size(h, w, target_w, target_h)
+    if (nh, nw) == (h, w):
+        return image.copy()
+    return resize_area_u8(image, nh, nw)
