@@ -223,6 +223,33 @@ int jds_resize_area(jds_ctx* ctx, const uint8_t* rgb, int rgb_loc, int height, i
 int jds_block_op(jds_ctx* ctx, int op, int64_t n_blocks, const double* in, const int16_t* in_q,
                  const double* qtable, double* out, int16_t* out_q);
 
+/*
+ * The reference's stage functions as stand-alone operators, exact arithmetic, so that every
+ * row of the path can be called (and checked against the reference) on its own.
+ *   jds_color_convert   direction 0: rgb_to_ycbcr (engines/color_space.py:8-14);
+ *                       direction 1: ycbcr_to_rgb incl. np.clip(0,255) (:17-24).
+ *                       in/out: n_pixels x 3 fp64, host.
+ *   jds_subsample_plane subsample_chroma of ONE chroma plane (:27-53): optional
+ *                       cv2.GaussianBlur(3x3, 0.75), then cv2.resize(INTER_AREA) to
+ *                       (W//2, H) / (W//2, H//2); out = jds_plane_dims() fp64 samples, host.
+ *   jds_upsample_plane  upsample_chroma(method='bilinear') of ONE plane (:56-66):
+ *                       cv2.resize(INTER_LINEAR) to out_height x out_width (enlarging only).
+ *   jds_compare_images  compute_psnr_ssim (utils/metrics.py:9-28) partial sums of two uint8
+ *                       RGB frames (host or device): sse_rgb, sse_y, ssim_sum[4], ssim_count.
+ *   jds_bitrate_partials estimate_bitrate_no_entropy (utils/metrics.py:63-83) counts of an
+ *                       int16 coefficient array: non-zeros and 6 + ceil(log2(|v|+1)) + 1 bits
+ *                       per non-zero (block overhead is added by the caller).
+ */
+int jds_color_convert(jds_ctx* ctx, int direction, int64_t n_pixels, const double* in, double* out);
+int jds_subsample_plane(jds_ctx* ctx, const double* plane, int height, int width, int subsampling,
+                        int prefilter, double* out);
+int jds_upsample_plane(jds_ctx* ctx, const double* plane, int height, int width, double* out,
+                       int out_height, int out_width);
+int jds_compare_images(jds_ctx* ctx, const uint8_t* a, const uint8_t* b, int loc, int height,
+                       int width, jds_metrics* metrics);
+int jds_bitrate_partials(jds_ctx* ctx, const int16_t* coeffs, int loc, uint64_t n, uint64_t* nnz,
+                         uint64_t* coeff_bits);
+
 #ifdef __cplusplus
 }
 #endif

@@ -74,6 +74,15 @@ PROTOTYPES = {
                                    C.POINTER(C.c_int)]),
     "jds_resize_area": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                   C.c_int, C.c_int, C.c_int]),
+    "jds_color_convert": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
+    "jds_subsample_plane": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_void_p]),
+    "jds_upsample_plane": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                     C.c_int]),
+    "jds_compare_images": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                     C.POINTER(JdsMetrics)]),
+    "jds_bitrate_partials": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64,
+                                       C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "jds_block_op": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_void_p]),
     "jds_selected_block": (C.c_int, [C.c_void_p, C.POINTER(JdsParams), C.c_void_p, C.c_int,

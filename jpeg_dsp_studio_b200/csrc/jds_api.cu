@@ -934,3 +934,152 @@ extern "C" int jds_block_op(jds_ctx* c, int op, int64_t n_blocks, const double* 
     JDS_CUDA(cudaStreamSynchronize(s));
     return JDS_OK;
 }
+
+// ------------------------------------------------------------------------------
+// stand-alone stage operators (csrc/jds_ops.cu), host buffers for the fp64 planes
+// ------------------------------------------------------------------------------
+extern "C" int jds_color_convert(jds_ctx* c, int direction, int64_t n_pixels, const double* in,
+                                 double* out) {
+    if (!c || !in || !out) return fail(JDS_ERR_INVALID, "NULL argument");
+    if (n_pixels < 1 || (direction != 0 && direction != 1))
+        return fail(JDS_ERR_INVALID, "bad colour conversion request");
+    JDS_CUDA(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)n_pixels * 24;
+    int rc;
+    if ((rc = ensure(c, c->planes, 2 * bytes))) return rc;
+    double* d_in = (double*)c->planes.p;
+    double* d_out = d_in + (size_t)n_pixels * 3;
+    cudaStream_t s = c->stream;
+    JDS_CUDA(cudaMemcpyAsync(d_in, in, bytes, cudaMemcpyHostToDevice, s));
+    launch_color_f64(direction, n_pixels, d_in, d_out, s);
+    c->launches++;
+    JDS_CUDA(cudaGetLastError());
+    JDS_CUDA(cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, s));
+    JDS_CUDA(cudaStreamSynchronize(s));
+    return JDS_OK;
+}
+
+extern "C" int jds_subsample_plane(jds_ctx* c, const double* plane, int height, int width,
+                                   int subsampling, int prefilter, double* out) {
+    if (!c || !plane || !out) return fail(JDS_ERR_INVALID, "NULL argument");
+    Geom g;
+    int rc = make_geom(height, width, subsampling, &g);
+    if (rc) return rc;
+    if (subsampling != JDS_SUB_444 && prefilter && (height < 2 || width < 2))
+        return fail(JDS_ERR_UNSUPPORTED, "prefilter on a %dx%d plane", height, width);
+    JDS_CUDA(cudaSetDevice(c->device));
+    const size_t in_bytes = (size_t)height * width * 8, out_bytes = (size_t)g.hc * g.wc * 8;
+    if (subsampling == JDS_SUB_444) {                 // engines/color_space.py:35-36: a copy
+        memcpy(out, plane, in_bytes);
+        return JDS_OK;
+    }
+    if ((rc = ensure(c, c->planes, in_bytes + out_bytes + 256))) return rc;
+    double* d_in = (double*)c->planes.p;
+    double* d_out = (double*)((char*)c->planes.p + ((in_bytes + 255) & ~(size_t)255));
+    cudaStream_t s = c->stream;
+    JDS_CUDA(cudaMemcpyAsync(d_in, plane, in_bytes, cudaMemcpyHostToDevice, s));
+    launch_subsample_plane(d_in, height, width, g.hc, g.wc, subsampling, prefilter, d_out, s);
+    c->launches++;
+    JDS_CUDA(cudaGetLastError());
+    JDS_CUDA(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, s));
+    JDS_CUDA(cudaStreamSynchronize(s));
+    return JDS_OK;
+}
+
+extern "C" int jds_upsample_plane(jds_ctx* c, const double* plane, int height, int width,
+                                  double* out, int out_height, int out_width) {
+    if (!c || !plane || !out) return fail(JDS_ERR_INVALID, "NULL argument");
+    if (height < 1 || width < 1 || out_height < height || out_width < width)
+        return fail(JDS_ERR_UNSUPPORTED, "upsample %dx%d -> %dx%d: only enlarging is restated",
+                    height, width, out_height, out_width);
+    if ((height < 2 && out_height != height) || (width < 2 && out_width != width))
+        return fail(JDS_ERR_UNSUPPORTED, "upsampling a 1-sample axis is not restated");
+    JDS_CUDA(cudaSetDevice(c->device));
+    const size_t in_bytes = (size_t)height * width * 8, out_bytes = (size_t)out_height * out_width * 8;
+    int rc;
+    if ((rc = ensure(c, c->planes, in_bytes + out_bytes + 256))) return rc;
+    double* d_in = (double*)c->planes.p;
+    double* d_out = (double*)((char*)c->planes.p + ((in_bytes + 255) & ~(size_t)255));
+    cudaStream_t s = c->stream;
+    JDS_CUDA(cudaMemcpyAsync(d_in, plane, in_bytes, cudaMemcpyHostToDevice, s));
+    launch_upsample_plane(d_in, height, width, out_height, out_width, d_out, s);
+    c->launches++;
+    JDS_CUDA(cudaGetLastError());
+    JDS_CUDA(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, s));
+    JDS_CUDA(cudaStreamSynchronize(s));
+    return JDS_OK;
+}
+
+extern "C" int jds_compare_images(jds_ctx* c, const uint8_t* a, const uint8_t* b, int loc,
+                                  int height, int width, jds_metrics* m) {
+    if (!c || !a || !b || !m) return fail(JDS_ERR_INVALID, "NULL argument");
+    if (height < 1 || width < 1) return fail(JDS_ERR_INVALID, "bad frame size %dx%d", height, width);
+    JDS_CUDA(cudaSetDevice(c->device));
+    const size_t frame_bytes = (size_t)height * width * 3;
+    int rc;
+    if ((rc = ensure(c, c->metrics, sizeof(DevMetrics)))) return rc;
+    if ((rc = ensure_pinned(&c->h_metrics, &c->h_metrics_bytes, sizeof(DevMetrics)))) return rc;
+    const uint8_t *d_a = a, *d_b = b;
+    cudaStream_t s = c->stream;
+    if (loc == JDS_HOST) {
+        if ((rc = ensure(c, c->in, frame_bytes))) return rc;
+        if ((rc = ensure(c, c->recon, frame_bytes))) return rc;
+        JDS_CUDA(cudaMemcpyAsync(c->in.p, a, frame_bytes, cudaMemcpyHostToDevice, s));
+        JDS_CUDA(cudaMemcpyAsync(c->recon.p, b, frame_bytes, cudaMemcpyHostToDevice, s));
+        d_a = (const uint8_t*)c->in.p;
+        d_b = (const uint8_t*)c->recon.p;
+    }
+    DevMetrics* dm = (DevMetrics*)c->metrics.p;
+    JDS_CUDA(cudaMemsetAsync(dm, 0, sizeof(DevMetrics), s));
+    const bool ssim_ok = height >= 7 && width >= 7;
+    // squared errors in integer / fp64 (PSNR_rgb exact, PSNR_y to fp64 rounding); SSIM sums
+    // from the strip kernel where the layout allows, else from the tile kernel
+    launch_sse_u8(d_a, d_b, (long long)height * width, dm, c->sm_count, s);
+    c->launches++;
+    if (ssim_ok) {
+        if (!c->legacy_ssim && ssim_strip_supported(height, width, d_a, frame_bytes, d_b, frame_bytes))
+            JDS_CUDA(launch_ssim_strip(height, width, d_a, frame_bytes, d_b, frame_bytes, dm, 1, true,
+                                       false, c->sm_count, s));
+        else
+            launch_ssim(true, height, width, d_a, frame_bytes, d_b, frame_bytes, dm, 1, s);
+        c->launches++;
+    }
+    JDS_CUDA(cudaGetLastError());
+    JDS_CUDA(cudaMemcpyAsync(c->h_metrics, dm, sizeof(DevMetrics), cudaMemcpyDeviceToHost, s));
+    JDS_CUDA(cudaStreamSynchronize(s));
+    const DevMetrics& d = *(const DevMetrics*)c->h_metrics;
+    memset(m, 0, sizeof *m);
+    m->sse_rgb = d.sse_rgb;
+    m->sse_y = d.sse_y;
+    for (int k = 0; k < 4; ++k) m->ssim_sum[k] = d.ssim_sum[k];
+    m->ssim_count = ssim_ok ? (uint64_t)(height - 6) * (uint64_t)(width - 6) : 0;
+    return JDS_OK;
+}
+
+extern "C" int jds_bitrate_partials(jds_ctx* c, const int16_t* coeffs, int loc, uint64_t n,
+                                    uint64_t* nnz, uint64_t* coeff_bits) {
+    if (!c || !coeffs || !nnz || !coeff_bits) return fail(JDS_ERR_INVALID, "NULL argument");
+    JDS_CUDA(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = ensure(c, c->metrics, sizeof(DevMetrics)))) return rc;
+    if ((rc = ensure_pinned(&c->h_metrics, &c->h_metrics_bytes, sizeof(DevMetrics)))) return rc;
+    cudaStream_t s = c->stream;
+    const int16_t* d_c = coeffs;
+    if (loc == JDS_HOST && n) {
+        if ((rc = ensure(c, c->coeffs, (size_t)n * 2))) return rc;
+        JDS_CUDA(cudaMemcpyAsync(c->coeffs.p, coeffs, (size_t)n * 2, cudaMemcpyHostToDevice, s));
+        d_c = (const int16_t*)c->coeffs.p;
+    }
+    DevMetrics* dm = (DevMetrics*)c->metrics.p;
+    JDS_CUDA(cudaMemsetAsync(dm, 0, sizeof(DevMetrics), s));
+    if (n) {
+        launch_bitcount(d_c, n, dm, c->sm_count, s);
+        c->launches++;
+    }
+    JDS_CUDA(cudaGetLastError());
+    JDS_CUDA(cudaMemcpyAsync(c->h_metrics, dm, sizeof(DevMetrics), cudaMemcpyDeviceToHost, s));
+    JDS_CUDA(cudaStreamSynchronize(s));
+    *nnz = ((const DevMetrics*)c->h_metrics)->nnz;
+    *coeff_bits = ((const DevMetrics*)c->h_metrics)->coeff_bits;
+    return JDS_OK;
+}

@@ -45,6 +45,13 @@ void launch_value_hist(const int16_t* coeffs, size_t n_coeffs, unsigned long lon
 void launch_heat_u8(const double* err, uint8_t* out, size_t n, cudaStream_t s);
 int launch_resize_area_u8(int H, int W, int dh, int dw, const uint8_t* src, uint8_t* dst,
                           cudaStream_t s);
+void launch_color_f64(int direction, long long n, const double* in, double* out, cudaStream_t s);
+void launch_subsample_plane(const double* p, int H, int W, int hc, int wc, int sub, int prefilter,
+                            double* out, cudaStream_t s);
+void launch_upsample_plane(const double* p, int h, int w, int H, int W, double* out, cudaStream_t s);
+void launch_sse_u8(const uint8_t* a, const uint8_t* b, long long n_px, DevMetrics* m, int sm_count,
+                   cudaStream_t s);
+void launch_bitcount(const int16_t* c, unsigned long long n, DevMetrics* m, int sm_count, cudaStream_t s);
 enum { JDS_BLOCKOP_DCT2 = 0, JDS_BLOCKOP_IDCT2 = 1, JDS_BLOCKOP_ENCODE = 2, JDS_BLOCKOP_DECODE = 3,
        JDS_BLOCKOP_QUANTIZE = 4, JDS_BLOCKOP_DEQUANTIZE = 5 };
 void launch_block_ops(int op, long long n_blocks, const double* in, const int16_t* in_q,

@@ -100,3 +100,90 @@ class Timer:
         result = func(*args, **kwargs)
         self.decode_time_ms = (time.perf_counter() - start) * 1000.0
         return result
+
+
+# ---------------------------------------------------------------------------------------
+# the reference's two stand-alone metric functions, computed by the CUDA kernels
+# ---------------------------------------------------------------------------------------
+def compute_psnr_ssim(original_rgb, reconstructed_rgb) -> Dict[str, float]:
+    """PSNR and SSIM on RGB and on BT.601 Y of two uint8 RGB images - the reference's
+    ``compute_psnr_ssim`` (utils/metrics.py:9-28).  The squared errors and the 7x7-window
+    SSIM sums are reduced on the GPU (jds_compare_images); PSNR_rgb is bit-identical (integer
+    sums), PSNR_y within 1e-9 dB, SSIM within 1e-5 of scikit-image's."""
+    import ctypes as C
+    from .. import _native as N
+    from ..engine import get_engine, _is_torch
+    a, b = original_rgb, reconstructed_rgb
+    if tuple(a.shape) != tuple(b.shape):
+        raise ValueError("Input images must have the same dimensions.")      # skimage's message
+    if a.ndim != 3 or a.shape[2] != 3:
+        raise ValueError(f"expected H x W x 3 images, got shape {tuple(a.shape)}")
+    if min(a.shape[:2]) < 7:
+        raise ValueError(
+            "win_size exceeds image extent. Either ensure that your images are at least "
+            "7x7; or pass win_size explicitly in the function call, with an odd value "
+            "less than or equal to the smaller side of your images.")
+    eng = get_engine()
+    if _is_torch(a) != _is_torch(b):
+        raise TypeError("both images must be NumPy arrays or both torch tensors")
+    pa, loc, keep_a = eng._in_ptr(a)
+    pb, loc_b, keep_b = eng._in_ptr(b)
+    if loc != loc_b:
+        raise ValueError("both images must live on the same side (host or device)")
+    m = N.JdsMetrics()
+    h, w = int(a.shape[0]), int(a.shape[1])
+    with eng._lock:
+        N.check(eng._lib.jds_compare_images(eng._ctx, pa, pb, loc, h, w, C.byref(m)))
+    r = metrics_from_partials(m, h, w)
+    return {'psnr_rgb': r['psnr_rgb'], 'ssim_rgb': r['ssim_rgb'],
+            'psnr_y': r['psnr_y'], 'ssim_y': r['ssim_y']}
+
+
+class _Partials:
+    __slots__ = ("luma_blocks", "nnz", "coeff_bits", "total_coeffs")
+
+
+def estimate_bitrate_no_entropy(quantized_coeffs, original_shape, block_size: int = 8) -> Dict:
+    """Compressed-size estimate without entropy coding - the reference's
+    ``estimate_bitrate_no_entropy`` (utils/metrics.py:51-92): 2 bits per block of the luma
+    grid, 6 position bits and ``ceil(log2(|v|+1)) + 1`` magnitude bits per non-zero
+    coefficient.  The counts come from the GPU (jds_bitrate_partials); the final arithmetic is
+    the reference's, including its float32 rounding for int16 input (NumPy 2)."""
+    import ctypes as C
+    from .. import _native as N
+    from ..engine import get_engine
+    q = np.asarray(quantized_coeffs)
+    if q.dtype.kind not in "iu" or q.dtype.itemsize < 2:
+        raise NotImplementedError(f"coefficient dtype {q.dtype}: the pipeline passes int16")
+    wide = q.dtype.itemsize > 2                  # np.log2 of int32/int64 is float64: exact sums
+    if q.dtype != np.int16:
+        if q.size and (q.max() > 32767 or q.min() < -32767):
+            raise ValueError("coefficients outside the int16 range")
+        q16 = q.astype(np.int16)
+    else:
+        q16 = q
+    q16 = np.ascontiguousarray(q16).reshape(-1)
+    h, w = original_shape
+    eng = get_engine()
+    nnz, bits = C.c_uint64(), C.c_uint64()
+    with eng._lock:
+        N.check(eng._lib.jds_bitrate_partials(eng._ctx, C.c_void_p(q16.ctypes.data), N.JDS_HOST,
+                                              q16.size, C.byref(nnz), C.byref(bits)))
+    p = _Partials()
+    p.luma_blocks = (-(-h // block_size)) * (-(-w // block_size))
+    p.nnz, p.coeff_bits, p.total_coeffs = nnz.value, bits.value, int(q.size)
+    if not wide:
+        r = bitrate_from_partials(p, h, w)
+    else:
+        num_pixels, original_bits = h * w, h * w * 24
+        overhead = 2 * p.luma_blocks
+        if p.nnz:
+            estimated = overhead + (6 * p.nnz + np.float64(p.coeff_bits - 6 * p.nnz))
+            r = {'estimated_bits': int(estimated), 'bpp': float(estimated / num_pixels),
+                 'compression_ratio': float(original_bits / max(estimated, 1))}
+        else:
+            r = {'estimated_bits': int(overhead), 'bpp': float(overhead / num_pixels),
+                 'compression_ratio': float(original_bits / max(overhead, 1))}
+        r.update(nonzero_count=p.nnz, total_coeffs=p.total_coeffs, label=BITRATE_LABEL)
+    return {k: r[k] for k in ('estimated_bits', 'bpp', 'compression_ratio', 'nonzero_count',
+                              'total_coeffs', 'label')}
