@@ -280,8 +280,11 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    REDUCE_MODE = os.environ.get("JDS_BENCH_REDUCE", "async")    # async | sync | off (diagnosis)
     pending = []                                    # in-flight all-reduces (handle, buffers)
-    NBUF = 4
+    # deep ring of result buffers: a step waits for the all-reduce issued NBUF-1 steps earlier,
+    # so per-step jitter of one rank is not paid by all ranks every step
+    NBUF = int(os.environ.get("JDS_BENCH_REDUCE_DEPTH", "16"))
     partial_ts = [torch.zeros(8, dtype=torch.float64, device=dev) for _ in range(NBUF)]
     partial_hs = [torch.zeros(8, dtype=torch.float64).pin_memory() for _ in range(NBUF)]
     step_no = [0]
@@ -300,9 +303,12 @@ def run_ours(args):
         while len(pending) >= NBUF - 1:
             pending.pop(0).wait()
         partial_hs[b].numpy()[:] = [sse, ssey, bits] + ssim + [float(len(outs))]
-        if world > 1:
+        if world > 1 and REDUCE_MODE != "off":
             partial_ts[b].copy_(partial_hs[b], non_blocking=True)
-            pending.append(dist.all_reduce(partial_ts[b], async_op=True))
+            if REDUCE_MODE == "sync":
+                dist.all_reduce(partial_ts[b])
+            else:
+                pending.append(dist.all_reduce(partial_ts[b], async_op=True))
         return partial_hs[b]
 
     def drain():

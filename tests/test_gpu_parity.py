@@ -471,3 +471,43 @@ def test_pipelined_host_batch_with_coefficients(J, oracle):
     mm = np.mean([np.mean(f.recon != e.recon) for f, e in zip(fast, outs)])
     assert mm <= 5e-4
     eng.close()
+
+
+def test_maximum_sizes_8k(J, oracle):
+    """8K (7680x4320) frame: index arithmetic beyond 2^25 pixels.  Exact-mode coefficients of
+    block-aligned crops must equal the oracle run on the crop alone (4:4:4 blocks depend only
+    on their own pixels); the fast mode must agree with the exact mode within tolerance."""
+    h, w = 4320, 7680
+    img = CS.photo_tiled(h, w)
+    img[::7, ::5, 1] ^= 0x55                             # break the 512-pixel tiling period
+    eng = J.get_engine()
+    ex = eng.roundtrip(img, 60, "4:4:4", False, precision="exact", want_coeffs=True)
+    nbx = w // 8
+    coeffs = np.asarray(ex.coeffs).reshape(3, h // 8, nbx, 64)
+    for (y0, x0) in ((0, 0), (4320 - 64, 7680 - 64), (2048, 4096), (4000, 128)):
+        crop = np.ascontiguousarray(img[y0:y0 + 64, x0:x0 + 64])
+        ref = oracle.compress_reconstruct(crop, 60, "4:4:4", False, want_metrics=False, want_maps=False)
+        want = ref["all_quantized_coeffs"].reshape(3, 8, 8, 64)
+        got = coeffs[:, y0 // 8:y0 // 8 + 8, x0 // 8:x0 // 8 + 8]
+        assert np.array_equal(got, want), (y0, x0)
+        assert np.array_equal(np.asarray(ex.recon)[y0:y0 + 64, x0:x0 + 64], ref["reconstructed_image"])
+    e420 = eng.roundtrip(img, 50, "4:2:0", False, precision="exact")
+    f420 = eng.roundtrip(img, 50, "4:2:0", False, precision="fast")
+    se, sf = e420.scalars, f420.scalars
+    assert abs(se["psnr_y"] - sf["psnr_y"]) <= PSNR_TOL_DB
+    assert abs(se["ssim_rgb"] - sf["ssim_rgb"]) <= SSIM_TOL
+    assert abs(se["nonzero_count"] - sf["nonzero_count"]) <= 1e-5 * se["total_coeffs"]
+    diff = (np.asarray(e420.recon) != np.asarray(f420.recon)).mean()
+    print(f"8K fast vs exact: pixel mismatch {diff:.2e}")
+    assert diff < 1e-3
+
+
+def test_extreme_aspect_strips(J, oracle):
+    """One block row / one block column of maximum length (ragged SSIM strips, single-CTA rows)."""
+    for shape in ((8, 16384), (16384, 8), (16, 8200), (23, 4099)):
+        img = CS.rand_rgb(shape[0] + shape[1], *shape)
+        o = J.get_engine().roundtrip(img, 40, "4:2:0", True, precision="exact", want_coeffs=True)
+        ref = oracle.compress_reconstruct(img, 40, "4:2:0", True, want_maps=False)
+        assert np.array_equal(np.asarray(o.coeffs), ref["all_quantized_coeffs"]), shape
+        assert np.array_equal(np.asarray(o.recon), ref["reconstructed_image"]), shape
+        assert abs(o.scalars["ssim_y"] - ref["ssim_y"]) <= SSIM_TOL
