@@ -168,6 +168,25 @@ int jds_sweep(jds_ctx* ctx, const jds_params* params, const int32_t* qualities, 
               uint8_t* recon, int out_loc, jds_metrics* metrics);
 
 /*
+ * jds_sweep whose results stay on the device, for sweeps sharded over several GPUs
+ * (BASELINE.json config 4; the loop of gui/worker.py:55-74 with its points dealt round-robin
+ * to the ranks).  After the kernels one record of JDS_RECORD_FIELDS doubles per quality is
+ * written to `records` (DEVICE memory, `capacity` rows):
+ *   unit (= unit0 + i*unit_step), quality, sse_rgb, sse_y, ssim_sum[R,G,B,Y], ssim_count,
+ *   coeff_bits, nnz, total_coeffs, luma_blocks          (the fields of jds_metrics)
+ * rows n_q .. capacity-1 are marked empty (unit = -1), so every rank contributes `capacity`
+ * rows to one all-gather.  Unlike every other entry point this one returns WITHOUT
+ * synchronising: the records are ordered on the context's stream (jds_ctx_set_stream), the
+ * caller enqueues its collective / copy there and synchronises once.  capacity <=
+ * JDS_SWEEP_RECORDS_MAX; params->outputs may hold JDS_OUT_SSIM | JDS_OUT_PSNR only.
+ */
+#define JDS_RECORD_FIELDS 13
+#define JDS_SWEEP_RECORDS_MAX 128
+int jds_sweep_records(jds_ctx* ctx, const jds_params* params, const int32_t* qualities, int n_q,
+                      const uint8_t* rgb, int rgb_loc, int unit0, int unit_step,
+                      double* records, int capacity);
+
+/*
  * The six 8x8 arrays of IntermediateData.selected_block_* for luma block
  * (block_row, block_col) (engines/pipeline.py:126-151): original, shifted, dct,
  * dequantized, reconstructed as fp64[64] and quantized as int16[64], all host

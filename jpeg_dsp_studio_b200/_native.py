@@ -19,6 +19,7 @@ JDS_HOST, JDS_DEVICE = 0, 1
 JDS_OUT_RECON, JDS_OUT_COEFFS, JDS_OUT_ERR_Y, JDS_OUT_ERR_RGB = 1, 2, 4, 8
 JDS_OUT_HIST, JDS_OUT_SSIM, JDS_OUT_PSNR = 16, 32, 64
 JDS_VALUE_HIST_BINS = 2048
+JDS_RECORD_FIELDS, JDS_SWEEP_RECORDS_MAX = 13, 128
 
 SUBSAMPLING = {"4:4:4": JDS_SUB_444, "4:2:2": JDS_SUB_422, "4:2:0": JDS_SUB_420}
 PRECISION = {"exact": JDS_EXACT, "fast": JDS_FAST}
@@ -67,6 +68,8 @@ PROTOTYPES = {
                                       C.POINTER(JdsMetrics)]),
     "jds_sweep": (C.c_int, [C.c_void_p, C.POINTER(JdsParams), C.POINTER(C.c_int32), C.c_int,
                             C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(JdsMetrics)]),
+    "jds_sweep_records": (C.c_int, [C.c_void_p, C.POINTER(JdsParams), C.POINTER(C.c_int32), C.c_int,
+                                    C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "jds_plot_payload": (C.c_int, [C.c_void_p, C.POINTER(JdsParams), C.c_void_p, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                    C.POINTER(JdsMetrics)]),

@@ -77,6 +77,7 @@ struct jds_ctx {
     bool no_fused = false;        // JDS_NO_FUSED=1: fast mode through the staged kernels
     bool l2_chunking = false;     // JDS_L2_CHUNK=1: size launches so a frame sequence stays in L2
     bool stage_timing = false;    // per-kernel CUDA events (jds_ctx_stage_timing)
+    bool async_pending = false;   // jds_sweep_records returned without synchronising
     size_t scratch_budget = (size_t)1 << 30;
 };
 
@@ -290,6 +291,40 @@ static int check_params(const jds_params* p) {
 // ------------------------------------------------------------------------------
 // the launch sequence over `units` units (frames of a batch or sweep points)
 // ------------------------------------------------------------------------------
+// One fp64 record per unit from the device accumulators (jds_sweep_records): the rows a
+// sharded sweep all-gathers, built where the partials already are.  Rows past `units` are
+// marked empty (unit = -1) so that every rank contributes the same number of rows.
+struct RecordQualities {
+    short q[JDS_SWEEP_RECORDS_MAX];
+};
+
+__global__ void k_pack_records(const DevMetrics* __restrict__ m, int units, int capacity, int unit0,
+                               int unit_step, RecordQualities rq, double ssim_count,
+                               double total_coeffs, double luma_blocks, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= capacity) return;
+    double* r = out + (size_t)i * JDS_RECORD_FIELDS;
+    if (i >= units) {
+        r[0] = -1.0;
+        for (int k = 1; k < JDS_RECORD_FIELDS; ++k) r[k] = 0.0;
+        return;
+    }
+    const DevMetrics& d = m[i];
+    r[0] = (double)(unit0 + i * unit_step);
+    r[1] = (double)rq.q[i];
+    r[2] = (double)d.sse_rgb;
+    r[3] = d.sse_y;
+    r[4] = d.ssim_sum[0];
+    r[5] = d.ssim_sum[1];
+    r[6] = d.ssim_sum[2];
+    r[7] = d.ssim_sum[3];
+    r[8] = ssim_count;
+    r[9] = (double)d.coeff_bits;
+    r[10] = (double)d.nnz;
+    r[11] = total_coeffs;
+    r[12] = luma_blocks;
+}
+
 struct UnitJob {
     const jds_params* p;
     Geom g;
@@ -304,6 +339,9 @@ struct UnitJob {
     double* err_rgb;
     int out_loc;
     jds_metrics* metrics;
+    // jds_sweep_records: device-resident fp64 records instead of host structs, no synchronisation
+    double* d_records;
+    int rec_capacity, unit0, unit_step;
 };
 
 // Kernels of one chunk of `n` units on the compute stream.  Returns which stages ran.
@@ -432,6 +470,11 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
     const bool out_host = J.out_loc == JDS_HOST;
 
     JDS_CUDA(cudaSetDevice(c->device));
+    if (c->async_pending) {
+        // an earlier jds_sweep_records may still be reading the pinned table staging buffer
+        JDS_CUDA(cudaStreamSynchronize(c->stream));
+        c->async_pending = false;
+    }
 
     // units per chunk: bounded by the scratch budget; with host buffers also small enough
     // that there are several chunks to overlap
@@ -566,7 +609,7 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
         // the last chunk's results are copied out
         if (u0 == 0) JDS_CUDA(cudaEventRecord(c->ev0, s));
         // per-stage events for the first kTimedChunks chunks of the call
-        cudaEvent_t* evs = (c->stage_timing && chunk_idx < jds_ctx::kTimedChunks)
+        cudaEvent_t* evs = (c->stage_timing && !J.d_records && chunk_idx < jds_ctx::kTimedChunks)
                                ? &c->evs[5 * chunk_idx] : nullptr;
         bool ran[4];
         if ((rc = launch_chunk(c, J, P, n, cs, slot, evs, ran))) return rc;
@@ -601,6 +644,24 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
                                          cudaMemcpyDeviceToHost, s_out));
             if (pipelined) JDS_CUDA(cudaEventRecord(c->ev_out[b], s_out));
         }
+    }
+    if (J.d_records) {
+        // device-resident records, no synchronisation: the caller orders its consumers on
+        // the context's stream (jds_ctx_set_stream) and synchronises once
+        if (pipelined) {
+            JDS_CUDA(cudaStreamSynchronize(s_in));
+            JDS_CUDA(cudaStreamSynchronize(s_out));
+        }
+        RecordQualities rq;
+        for (int i = 0; i < J.units; ++i) rq.q[i] = (short)(J.qualities ? J.qualities[i] : p->quality);
+        const double cnt = (want_ssim && g.H >= 7 && g.W >= 7) ? (double)(g.H - 6) * (double)(g.W - 6) : 0.0;
+        const int cap = J.rec_capacity;
+        k_pack_records<<<(cap + 127) / 128, 128, 0, s>>>(d_metrics, J.units, cap, J.unit0, J.unit_step, rq,
+                                                         cnt, (double)ncoef, (double)g.nblk_y, J.d_records);
+        JDS_CUDA(cudaGetLastError());
+        c->launches++;
+        c->async_pending = true;
+        return JDS_OK;
     }
     JDS_CUDA(cudaMemcpyAsync(h_metrics, d_metrics, sizeof(DevMetrics) * J.units,
                              cudaMemcpyDeviceToHost, s));
@@ -715,6 +776,53 @@ extern "C" int jds_sweep(jds_ctx* c, const jds_params* p, const int32_t* qualiti
     J.recon = recon;
     J.out_loc = out_loc;
     J.metrics = metrics;
+    return run_job(c, J);
+}
+
+// Sweep whose results stay on the device (sharded sweeps, BASELINE config 4): the kernels of
+// jds_sweep, then one fp64 record per quality written to `records` (device memory,
+// `capacity` rows of JDS_RECORD_FIELDS doubles; rows n_q..capacity-1 are marked empty with
+// unit = -1).  Returns WITHOUT synchronising: everything is ordered on the context's stream, so
+// a collective or copy the caller enqueues on the same stream (jds_ctx_set_stream) sees the
+// records, and one synchronisation at the very end replaces the per-call one.
+extern "C" int jds_sweep_records(jds_ctx* c, const jds_params* p, const int32_t* qualities, int n_q,
+                                 const uint8_t* rgb, int rgb_loc, int unit0, int unit_step,
+                                 double* records, int capacity) {
+    if (!c || !rgb || !records || (!qualities && n_q > 0)) return fail(JDS_ERR_INVALID, "NULL argument");
+    if (n_q < 0 || n_q > capacity || capacity < 1 || capacity > JDS_SWEEP_RECORDS_MAX)
+        return fail(JDS_ERR_INVALID, "need 0 <= n_q <= capacity <= %d, got n_q %d capacity %d",
+                    JDS_SWEEP_RECORDS_MAX, n_q, capacity);
+    int rc = check_params(p);
+    if (rc) return rc;
+    for (int i = 0; i < n_q; ++i)
+        if (qualities[i] < 1 || qualities[i] > 100)
+            return fail(JDS_ERR_INVALID, "Quality must be 1-100, got %d", qualities[i]);
+    if (p->outputs & (JDS_OUT_ERR_Y | JDS_OUT_ERR_RGB | JDS_OUT_COEFFS | JDS_OUT_RECON | JDS_OUT_HIST))
+        return fail(JDS_ERR_INVALID, "jds_sweep_records produces metric records only");
+    UnitJob J;
+    memset(&J, 0, sizeof J);
+    if ((rc = make_geom(p->height, p->width, p->subsampling, &J.g))) return rc;
+    if (n_q == 0) {
+        // a rank that owns no point still contributes `capacity` empty rows
+        JDS_CUDA(cudaSetDevice(c->device));
+        RecordQualities rq;
+        k_pack_records<<<(capacity + 127) / 128, 128, 0, c->stream>>>(nullptr, 0, capacity, unit0, unit_step,
+                                                                      rq, 0.0, 0.0, 0.0, records);
+        JDS_CUDA(cudaGetLastError());
+        c->launches++;
+        return JDS_OK;
+    }
+    J.p = p;
+    J.units = n_q;
+    J.qualities = qualities;
+    J.shared_input = true;
+    J.rgb = rgb;
+    J.rgb_loc = rgb_loc;
+    J.out_loc = JDS_DEVICE;
+    J.d_records = records;
+    J.rec_capacity = capacity;
+    J.unit0 = unit0;
+    J.unit_step = unit_step;
     return run_job(c, J);
 }
 

@@ -107,23 +107,29 @@ __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b
 __device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
 __device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __ffma2_rn(b, f2(-1.0f), a); }
 
-// 0.5 * SSIM of one window for both channels of a pair, from the centred sums over its
-// 49 samples:  S = (2 ux uy + C1)(2 vxy + C2) / ((ux^2 + uy^2 + C1)(vx + vy + C2)),
+// 0.5 * SSIM of one window for both channels of a pair, added to `ssum`, from the centred
+// sums over its 49 samples:  S = (2 ux uy + C1)(2 vxy + C2) / ((ux^2 + uy^2 + C1)(vx + vy + C2)),
 // v = 49/48 (E[ab]-E[a]E[b]), written on the raw sums (N = 49, Ux = N ux):
 //   S = 2 A1 A2 / (B1 B2),  A1 = 2 Ux Uy + C1 N^2,  B1 = Ux^2 + Uy^2 + C1 N^2,
 //   A2 = N Sxy - Sx Sy + C2 N (N-1) / 2,  B2 = N Sq - Sx^2 - Sy^2 + C2 N (N-1)
-__device__ __forceinline__ float2 ssim_window_half2(float2 sx, float2 sy, float2 sq, float2 sc) {
+// A2 and B2 are formed NEGATED (packed f32x2 has no operand negation, so every subtraction
+// would cost an instruction): (-A2)(-B2)^-1 has the same value, the constants carry the
+// signs, and the last product is fused into the accumulation - 14 packed instructions and
+// two MUFU.RCP per window pair.  Ux / Uy stay explicit: they are exact small integers on
+// dark content, where an expanded form cancels catastrophically.
+__device__ __forceinline__ float2 ssim_window_half2_acc(float2 sx, float2 sy, float2 sq, float2 sc,
+                                                        float2 ssum) {
     constexpr float N = 49.0f;
     constexpr float C1N2 = 6.5025f * 2401.0f;
     constexpr float K2 = 58.5225f * 49.0f * 48.0f;
     const float2 Ux = __fadd2_rn(sx, f2(128.0f * N)), Uy = __fadd2_rn(sy, f2(128.0f * N));
     const float2 A1 = __ffma2_rn(__fmul2_rn(Ux, Uy), f2(2.0f), f2(C1N2));
     const float2 B1 = __ffma2_rn(Ux, Ux, __ffma2_rn(Uy, Uy, f2(C1N2)));
-    const float2 A2 = __ffma2_rn(sc, f2(N), __ffma2_rn(sx, sub2(f2(0.0f), sy), f2(0.5f * K2)));
-    const float2 u = __ffma2_rn(sx, sx, __fmul2_rn(sy, sy));
-    const float2 B2 = __ffma2_rn(sq, f2(N), sub2(f2(K2), u));
-    const float2 num = __fmul2_rn(A1, A2), den = __fmul2_rn(B1, B2);
-    return __fmul2_rn(num, f2(rcp_approx(den.x), rcp_approx(den.y)));
+    const float2 A2n = __ffma2_rn(sc, f2(-N), __ffma2_rn(sx, sy, f2(-0.5f * K2)));
+    const float2 un = __ffma2_rn(sx, sx, __ffma2_rn(sy, sy, f2(-K2)));
+    const float2 B2n = __ffma2_rn(sq, f2(-N), un);
+    const float2 num = __fmul2_rn(A1, A2n), den = __fmul2_rn(B1, B2n);
+    return __ffma2_rn(num, f2(rcp_approx(den.x), rcp_approx(den.y)), ssum);
 }
 
 __global__ void __launch_bounds__(S_NT, 4)
@@ -244,7 +250,7 @@ k_ssim_strip(int H, int W, int seg_rows, const uint8_t* __restrict__ a_img, size
         acc.sy = __fadd2_rn(acc.sy, h.sy);                                               \
         acc.sq = __fadd2_rn(acc.sq, h.sq);                                               \
         acc.sc = __fadd2_rn(acc.sc, h.sc);                                               \
-        if (EMIT) ssum = __fadd2_rn(ssum, ssim_window_half2(acc.sx, acc.sy, acc.sq, acc.sc)); \
+        if (EMIT) ssum = ssim_window_half2_acc(acc.sx, acc.sy, acc.sq, acc.sc, ssum);       \
         const HSum o = ring[(r + 1) % S_R];                                              \
         acc.sx = sub2(acc.sx, o.sx);                                                     \
         acc.sy = sub2(acc.sy, o.sy);                                                     \

@@ -169,22 +169,68 @@ def reduce_partials(local_sum: np.ndarray, device=None) -> np.ndarray:
     return t.cpu().numpy()
 
 
+def _sweep_device_resident(engine, image, qs, mine, mode, prefilter, precision, device, dist, world):
+    """Device-resident variant of the sharded sweep: the kernels write this rank's records
+    straight into the all-gather's send buffer (``jds_sweep_records``), the collective and
+    the single D2H copy are enqueued on the same stream, and the host synchronises ONCE per
+    sweep - no metric read-back, no host-built rows, no H2D in between."""
+    import torch
+    from . import _native as N
+    dev = torch.device(device)
+    cur = torch.cuda.current_stream(dev)
+    if getattr(engine, "_stream_handle", None) != cur.cuda_stream:
+        engine.use_stream(cur.cuda_stream)      # kernels, collective and copy share one stream
+    nf = len(RECORD_FIELDS)
+    cap = (len(qs) + world - 1) // world
+    key = ("dev", world, cap, str(dev))
+    bufs = _gather_cache.get(key)
+    if bufs is None:
+        d_in = torch.empty((cap, nf), dtype=torch.float64, device=dev)
+        d_out = torch.empty((world * cap, nf), dtype=torch.float64, device=dev) if world > 1 else d_in
+        h_out = torch.empty((world * cap, nf), dtype=torch.float64).pin_memory()
+        bufs = _gather_cache[key] = (d_in, d_out, h_out)
+    d_in, d_out, h_out = bufs
+    keep = engine.sweep_records(image, [qs[i] for i in mine], d_in, mode=mode, prefilter=prefilter,
+                                precision=precision, unit0=(mine[0] if mine else 0), unit_step=world)
+    if world > 1:
+        dist.all_gather_into_tensor(d_out, d_in)
+    h_out.copy_(d_out, non_blocking=True)
+    cur.synchronize()
+    del keep
+    table = h_out.numpy()
+    table = table[table[:, 0] >= 0]
+    table = table[np.argsort(table[:, 0], kind="stable")]
+    if len(table) != len(qs) or not np.array_equal(table[:, 0], np.arange(len(qs))):
+        raise RuntimeError("sharded units do not cover 0..n_units-1 exactly once")
+    return table
+
+
 def sweep_sharded(engine, image, qualities: Sequence[int], mode="4:2:0", prefilter=False, *,
                   precision="fast", device=None) -> List[dict]:
     """Rate-distortion sweep with the points sharded over the ranks (config 4).
-    Every rank returns the full list of per-quality result dicts."""
+    Every rank returns the full list of per-quality result dicts.  With a CUDA ``device``
+    the records never leave the GPU before the all-gather (one synchronisation per sweep)."""
     dist = _dist()
     rank = dist.get_rank() if dist else 0
     world = dist.get_world_size() if dist else 1
     qs = [int(q) for q in qualities]
     mine = shard_indices(len(qs), rank, world)
+    h, w = image.shape[0], image.shape[1]
+    on_gpu = False
+    if device is not None and len(qs) > 0:
+        import torch
+        on_gpu = torch.device(device).type == "cuda"
+    from . import _native as N
+    if on_gpu and (len(qs) + world - 1) // world <= N.JDS_SWEEP_RECORDS_MAX:
+        table = _sweep_device_resident(engine, image, qs, mine, mode, prefilter, precision, device,
+                                       dist, world)
+        return scalars_from_table(table, h, w)
     rows = np.zeros((0, len(RECORD_FIELDS)))
     if mine:
         my_qs = [qs[i] for i in mine]
         outs = engine.sweep(image, my_qs, mode, prefilter, precision=precision)
         rows = records_from_outputs(mine, my_qs, outs)
     table = gather_records(rows, len(qs), device=device)
-    h, w = image.shape[0], image.shape[1]
     return scalars_from_table(table, h, w)
 
 

@@ -175,6 +175,7 @@ class Engine:
     def use_stream(self, cuda_stream: int):
         """Issue this context's work on the caller's cudaStream_t (an int handle)."""
         N.check(self._lib.jds_ctx_set_stream(self._ctx, C.c_void_p(cuda_stream)))
+        self._stream_handle = int(cuda_stream)
 
     def synchronize(self):
         N.check(self._lib.jds_ctx_synchronize(self._ctx))
@@ -392,6 +393,33 @@ class Engine:
             N.check(self._lib.jds_sweep(self._ctx, C.byref(p), qarr, nq, ptr, loc, rp, loc, ms))
         return [RoundTripOutputs(recon[i] if recon is not None else None, None, None, None, ms[i],
                                  (h, w), ms) for i in range(nq)]
+
+    def sweep_records(self, image, qualities: Sequence[int], records, *, mode="4:2:0",
+                      prefilter=False, precision="fast", unit0=0, unit_step=1, want_ssim=True):
+        """Sweep whose metric records stay on the device (``jds_sweep_records``): one row of
+        ``N.JDS_RECORD_FIELDS`` fp64 per quality is written to ``records`` - a CUDA fp64
+        tensor of shape (capacity, 13) - and rows past ``len(qualities)`` are marked empty
+        (unit -1).  Returns WITHOUT synchronising: the work is ordered on this engine's
+        stream (``use_stream``); the caller enqueues its collective / copy on the same
+        stream and synchronises once.  At most ``N.JDS_SWEEP_RECORDS_MAX`` rows per call."""
+        h, w, _ = self._frame_geometry(image)
+        ptr, loc, keep = self._in_ptr(image)
+        qs = [int(q) for q in qualities]
+        for q in qs:
+            CompressionParams(quality=q)
+        if not _is_torch(records) or not records.is_cuda or not records.is_contiguous():
+            raise TypeError("records must be a contiguous CUDA fp64 tensor")
+        cap = int(records.shape[0])
+        if tuple(records.shape[1:]) != (N.JDS_RECORD_FIELDS,) or records.element_size() != 8:
+            raise ValueError(f"records must have shape (capacity, {N.JDS_RECORD_FIELDS}) fp64")
+        flags = N.JDS_OUT_PSNR | (N.JDS_OUT_SSIM if want_ssim else 0)
+        p = self._params(h, w, 50, mode, prefilter, precision, flags)
+        qarr = (C.c_int32 * max(len(qs), 1))(*qs)
+        with self._lock:
+            N.check(self._lib.jds_sweep_records(self._ctx, C.byref(p), qarr, len(qs), ptr, loc,
+                                                int(unit0), int(unit_step),
+                                                C.c_void_p(records.data_ptr()), cap))
+        return keep
 
 
 _engines = {}

@@ -344,6 +344,44 @@ def test_sweep_sharded_single_rank_equals_engine_sweep(J):
             assert a == b or abs(a - b) <= 1e-12 * max(abs(a), abs(b)), (q, k, a, b)
 
 
+def test_sweep_device_resident_records(J):
+    """jds_sweep_records: the records the kernels leave on the device (no synchronisation
+    inside the call) equal the host structs of jds_sweep, empty rows are marked, and
+    distributed.sweep_sharded(device=cuda) - which all-gathers exactly these rows - returns
+    the same table as the host-record path."""
+    import torch
+    from jpeg_dsp_studio_b200 import distributed as D, _native as N
+    img = CS.rand_rgb(56, 144, 208)
+    eng = J.Engine(0)
+    dev = torch.device("cuda", 0)
+    eng.use_stream(torch.cuda.current_stream(dev).cuda_stream)
+    qs = [3, 25, 50, 75, 97]
+    d_img = torch.from_numpy(img).to(dev)
+    rec = torch.full((8, N.JDS_RECORD_FIELDS), 7.0, dtype=torch.float64, device=dev)
+    eng.sweep_records(d_img, qs, rec, mode="4:2:0", unit0=2, unit_step=3)
+    got = rec.cpu().numpy()                      # ordered after the kernels on the same stream
+    outs = eng.sweep(d_img, qs, "4:2:0", False, precision="fast")
+    want = D.records_from_outputs([2 + 3 * i for i in range(5)], qs, outs)
+    assert np.array_equal(got[:5], want)
+    assert np.all(got[5:, 0] == -1.0) and np.all(got[5:, 1:] == 0.0)
+    # a rank that owns no point contributes only empty rows
+    eng.sweep_records(d_img, [], rec)
+    assert np.all(rec.cpu().numpy()[:, 0] == -1.0)
+    # the public sharded sweep: device-resident path vs host-record path, host and device input
+    a = D.sweep_sharded(eng, d_img, qs, "4:2:0", False, precision="fast", device=dev)
+    b = D.sweep_sharded(eng, img, qs, "4:2:0", False, precision="fast")
+    c = D.sweep_sharded(eng, img, qs, "4:2:0", False, precision="fast", device=dev)
+    assert a == b == c
+    # exact mode and a prefiltered 4:2:2 sweep go through the same entry point
+    for mode, pf, prec in (("4:2:2", True, "exact"), ("4:4:4", False, "fast")):
+        x = D.sweep_sharded(eng, d_img, [10, 90], mode, pf, precision=prec, device=dev)
+        y = D.sweep_sharded(eng, img, [10, 90], mode, pf, precision=prec)
+        assert x == y
+    with pytest.raises(ValueError):
+        eng.sweep_records(d_img, [0], rec)
+    eng.close()
+
+
 def test_public_sweep_and_batch_api(J, oracle):
     """quality_sweep / compress_batch (the BatchSweepWorker-shaped and batch entry points of
     engines/pipeline.py) return CompressionResult objects consistent with single calls."""
