@@ -232,6 +232,31 @@ int jds_resize_area(jds_ctx* ctx, const uint8_t* rgb, int rgb_loc, int height, i
                     uint8_t* out, int out_h, int out_w, int out_loc);
 
 /*
+ * Chroma-aliasing demo: one arm of AliasingDemoWorker.run
+ * (gui/dialogs/aliasing_demo_dialog.py:98-166).
+ *   1. _process_with_explicit_subsample(prefilter) (:125-150): OpenCV FLOAT32 arithmetic -
+ *      cvtColor(RGB2YCrCb) of the float image, optional GaussianBlur(5x5, 0.8) of Cb / Cr,
+ *      [::2, ::2] decimation, resize(INTER_LINEAR) back to H x W, cvtColor(YCrCb2RGB),
+ *      clip + truncate to uint8 - bit-identical to OpenCV 4.13 -> `subsampled`
+ *   2. the hot path at 4:4:4, prefilter off, quality `quality` (:152-158) on that frame
+ *      -> `recon` (bit-identical to the reference in JDS_EXACT precision)
+ *   3. compute_metrics(original, recon) (:69-83): m_rgb = squared error / SSIM sums of the RGB
+ *      frames (psnr_rgb, ssim_rgb as for jds_metrics); m_luma = the same sums of OpenCV's
+ *      integer luma Y = (4899 R + 9617 G + 1868 B + 8192) >> 14 replicated to three channels:
+ *      psnr_y from sse_rgb / 3 over H*W samples, ssim_y = ssim_sum[0] / ssim_count
+ *   4. _compute_difference (:162-166): clip(|original - recon| * 10, 0, 255) uint8 -> `diff`
+ * subsampled, recon, diff: H*W*3 uint8 each, may be NULL; frames of at least 8 x 8.
+ */
+int jds_aliasing_demo(jds_ctx* ctx, const uint8_t* rgb, int rgb_loc, int height, int width,
+                      int quality, int prefilter, int precision, uint8_t* subsampled,
+                      uint8_t* recon, uint8_t* diff, int out_loc, jds_metrics* m_rgb,
+                      jds_metrics* m_luma);
+/* step 3 alone: compute_metrics(a, b) (gui/dialogs/aliasing_demo_dialog.py:69-83) for two
+ * uint8 RGB frames (host or device): m_rgb / m_luma as for jds_aliasing_demo */
+int jds_aliasing_metrics(jds_ctx* ctx, const uint8_t* a, const uint8_t* b, int loc, int height,
+                         int width, jds_metrics* m_rgb, jds_metrics* m_luma);
+
+/*
  * Stand-alone 8x8 block operators, exact (reference) arithmetic, host buffers:
  *   op 0 dct2, 1 idct2 (engines/dct_engine.py:7-14), 2 encode_block (-128 then DCT, :17-20),
  *   3 decode_block (IDCT, +128, clip, :23-27): in/out = n_blocks*64 fp64;

@@ -70,6 +70,11 @@ PROTOTYPES = {
                             C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(JdsMetrics)]),
     "jds_sweep_records": (C.c_int, [C.c_void_p, C.POINTER(JdsParams), C.POINTER(C.c_int32), C.c_int,
                                     C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
+    "jds_aliasing_demo": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                    C.POINTER(JdsMetrics), C.POINTER(JdsMetrics)]),
+    "jds_aliasing_metrics": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                       C.POINTER(JdsMetrics), C.POINTER(JdsMetrics)]),
     "jds_plot_payload": (C.c_int, [C.c_void_p, C.POINTER(JdsParams), C.c_void_p, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                    C.POINTER(JdsMetrics)]),

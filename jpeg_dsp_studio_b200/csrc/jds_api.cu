@@ -64,7 +64,7 @@ struct jds_ctx {
     int plan_chunk = 1;
     double stage_ms[4] = {0, 0, 0, 0};   // forward, codec, inverse, ssim (accumulated)
     uint64_t stage_launches[4] = {0, 0, 0, 0};
-    DevBuf planes, in, recon, coeffs, errs, metrics, tables, selected, payload;
+    DevBuf planes, in, recon, coeffs, errs, metrics, tables, selected, payload, alias;
     void* h_metrics = nullptr;   // pinned
     size_t h_metrics_bytes = 0;
     void* h_tables = nullptr;    // pinned
@@ -77,7 +77,14 @@ struct jds_ctx {
     bool no_fused = false;        // JDS_NO_FUSED=1: fast mode through the staged kernels
     bool l2_chunking = false;     // JDS_L2_CHUNK=1: size launches so a frame sequence stays in L2
     bool stage_timing = false;    // per-kernel CUDA events (jds_ctx_stage_timing)
-    bool async_pending = false;   // jds_sweep_records returned without synchronising
+    // jds_sweep_records returns without synchronising: its table uploads are staged in a ring
+    // of pinned slots, each guarded by an event, so back-to-back calls never wait on the stream
+    static constexpr int kTableRing = 4;
+    void* h_tables_ring[kTableRing] = {};
+    size_t h_tables_ring_bytes[kTableRing] = {};
+    cudaEvent_t ev_tables[kTableRing] = {};
+    bool ev_tables_used[kTableRing] = {};
+    int tables_slot = 0;
     size_t scratch_budget = (size_t)1 << 30;
 };
 
@@ -175,11 +182,15 @@ extern "C" int jds_ctx_destroy(jds_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->planes, &c->in, &c->recon, &c->coeffs, &c->errs,
-                      &c->metrics, &c->tables, &c->selected, &c->payload};
+                      &c->metrics, &c->tables, &c->selected, &c->payload, &c->alias};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->h_metrics) cudaFreeHost(c->h_metrics);
     if (c->h_tables) cudaFreeHost(c->h_tables);
+    for (int i = 0; i < jds_ctx::kTableRing; ++i) {
+        if (c->h_tables_ring[i]) cudaFreeHost(c->h_tables_ring[i]);
+        if (c->ev_tables[i]) cudaEventDestroy(c->ev_tables[i]);
+    }
     if (c->h_selected) cudaFreeHost(c->h_selected);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -470,12 +481,6 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
     const bool out_host = J.out_loc == JDS_HOST;
 
     JDS_CUDA(cudaSetDevice(c->device));
-    if (c->async_pending) {
-        // an earlier jds_sweep_records may still be reading the pinned table staging buffer
-        JDS_CUDA(cudaStreamSynchronize(c->stream));
-        c->async_pending = false;
-    }
-
     // units per chunk: bounded by the scratch budget; with host buffers also small enough
     // that there are several chunks to overlap
     const size_t per_unit = planes_elems * esz * (J.shared_input ? 1 : 2) + frame_bytes * 2 +
@@ -527,7 +532,17 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
     if ((rc = ensure(c, c->tables, sizeof(QTables) * (size_t)n_tables_total))) return rc;
     if ((rc = ensure_pinned(&c->h_metrics, &c->h_metrics_bytes, sizeof(DevMetrics) * (size_t)J.units)))
         return rc;
-    if ((rc = ensure_pinned(&c->h_tables, &c->h_tables_bytes, sizeof(QTables) * (size_t)n_tables_total)))
+    int tslot = -1;
+    if (J.d_records) {
+        tslot = c->tables_slot;
+        c->tables_slot = (tslot + 1) % jds_ctx::kTableRing;
+        if (!c->ev_tables[tslot])
+            JDS_CUDA(cudaEventCreateWithFlags(&c->ev_tables[tslot], cudaEventDisableTiming));
+        if (c->ev_tables_used[tslot]) JDS_CUDA(cudaEventSynchronize(c->ev_tables[tslot]));
+        if ((rc = ensure_pinned(&c->h_tables_ring[tslot], &c->h_tables_ring_bytes[tslot],
+                                sizeof(QTables) * (size_t)n_tables_total)))
+            return rc;
+    } else if ((rc = ensure_pinned(&c->h_tables, &c->h_tables_bytes, sizeof(QTables) * (size_t)n_tables_total)))
         return rc;
     const size_t in_slot = frame_bytes * (size_t)fwd_units;
     const size_t recon_slot = frame_bytes * (size_t)chunk;
@@ -543,7 +558,7 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
 
     DevMetrics* d_metrics = (DevMetrics*)c->metrics.p;
     QTables* d_tables = (QTables*)c->tables.p;
-    QTables* h_tables = (QTables*)c->h_tables;
+    QTables* h_tables = (QTables*)(tslot >= 0 ? c->h_tables_ring[tslot] : c->h_tables);
     DevMetrics* h_metrics = (DevMetrics*)c->h_metrics;
     cudaStream_t s = c->stream;
     cudaStream_t s_in = pipelined ? c->s_in : s;
@@ -554,6 +569,10 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
         fill_tables(J.qualities ? J.qualities[i] : p->quality, &h_tables[i]);
     JDS_CUDA(cudaMemcpyAsync(d_tables, h_tables, sizeof(QTables) * n_tables_total,
                              cudaMemcpyHostToDevice, s));
+    if (tslot >= 0) {
+        JDS_CUDA(cudaEventRecord(c->ev_tables[tslot], s));
+        c->ev_tables_used[tslot] = true;
+    }
     JDS_CUDA(cudaMemsetAsync(d_metrics, 0, sizeof(DevMetrics) * J.units, s));
     if (J.shared_input && in_host)
         JDS_CUDA(cudaMemcpyAsync(c->in.p, J.rgb, frame_bytes, cudaMemcpyHostToDevice, s));
@@ -660,7 +679,6 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
                                                          cnt, (double)ncoef, (double)g.nblk_y, J.d_records);
         JDS_CUDA(cudaGetLastError());
         c->launches++;
-        c->async_pending = true;
         return JDS_OK;
     }
     JDS_CUDA(cudaMemcpyAsync(h_metrics, d_metrics, sizeof(DevMetrics) * J.units,
@@ -824,6 +842,148 @@ extern "C" int jds_sweep_records(jds_ctx* c, const jds_params* p, const int32_t*
     J.unit0 = unit0;
     J.unit_step = unit_step;
     return run_job(c, J);
+}
+
+// ------------------------------------------------------------------------------
+// chroma-aliasing demo
+// ------------------------------------------------------------------------------
+// squared errors + SSIM sums of two device-resident uint8 RGB frames into *m (synchronises)
+static int compare_device(jds_ctx* c, const uint8_t* d_a, const uint8_t* d_b, int height, int width,
+                          jds_metrics* m) {
+    const size_t frame_bytes = (size_t)height * width * 3;
+    int rc;
+    if ((rc = ensure(c, c->metrics, sizeof(DevMetrics)))) return rc;
+    if ((rc = ensure_pinned(&c->h_metrics, &c->h_metrics_bytes, sizeof(DevMetrics)))) return rc;
+    cudaStream_t s = c->stream;
+    DevMetrics* dm = (DevMetrics*)c->metrics.p;
+    JDS_CUDA(cudaMemsetAsync(dm, 0, sizeof(DevMetrics), s));
+    const bool ssim_ok = height >= 7 && width >= 7;
+    launch_sse_u8(d_a, d_b, (long long)height * width, dm, c->sm_count, s);
+    c->launches++;
+    if (ssim_ok) {
+        if (!c->legacy_ssim && ssim_strip_supported(height, width, d_a, frame_bytes, d_b, frame_bytes))
+            JDS_CUDA(launch_ssim_strip(height, width, d_a, frame_bytes, d_b, frame_bytes, dm, 1, true,
+                                       false, c->sm_count, s));
+        else
+            launch_ssim(true, height, width, d_a, frame_bytes, d_b, frame_bytes, dm, 1, s);
+        c->launches++;
+    }
+    JDS_CUDA(cudaGetLastError());
+    JDS_CUDA(cudaMemcpyAsync(c->h_metrics, dm, sizeof(DevMetrics), cudaMemcpyDeviceToHost, s));
+    JDS_CUDA(cudaStreamSynchronize(s));
+    const DevMetrics& d = *(const DevMetrics*)c->h_metrics;
+    memset(m, 0, sizeof *m);
+    m->sse_rgb = d.sse_rgb;
+    m->sse_y = d.sse_y;
+    for (int k = 0; k < 4; ++k) m->ssim_sum[k] = d.ssim_sum[k];
+    m->ssim_count = ssim_ok ? (uint64_t)(height - 6) * (uint64_t)(width - 6) : 0;
+    return JDS_OK;
+}
+
+// One arm of AliasingDemoWorker.run (gui/dialogs/aliasing_demo_dialog.py:98-166):
+// _process_with_explicit_subsample(prefilter) - OpenCV float32 YCrCb, optional 5x5 blur,
+// [::2, ::2], bilinear re-enlargement, back to uint8 RGB (jds_alias.cu) - then the hot path at
+// 4:4:4 on that frame (the staged / fused kernels of jds_roundtrip), compute_metrics
+// (RGB and OpenCV's integer luma) against the ORIGINAL frame, and _compute_difference.
+extern "C" int jds_aliasing_demo(jds_ctx* c, const uint8_t* rgb, int rgb_loc, int height, int width,
+                                 int quality, int prefilter, int precision, uint8_t* subsampled,
+                                 uint8_t* recon, uint8_t* diff, int out_loc, jds_metrics* m_rgb,
+                                 jds_metrics* m_luma) {
+    if (!c || !rgb || !m_rgb || !m_luma) return fail(JDS_ERR_INVALID, "NULL argument");
+    if (height < 8 || width < 8)
+        return fail(JDS_ERR_INVALID, "aliasing demo needs frames of at least 8x8, got %dx%d", height, width);
+    if (quality < 1 || quality > 100) return fail(JDS_ERR_INVALID, "Quality must be 1-100, got %d", quality);
+    if (precision != JDS_EXACT && precision != JDS_FAST) return fail(JDS_ERR_INVALID, "bad precision %d", precision);
+    JDS_CUDA(cudaSetDevice(c->device));
+    const size_t n_px = (size_t)height * width, frame_bytes = n_px * 3;
+    // scratch: float planes | subsampled frame | reconstruction | two luma3 frames | input copy
+    const size_t fl_bytes = (alias_scratch_floats(height, width) * sizeof(float) + 255) & ~(size_t)255;
+    const size_t fr = (frame_bytes + 255) & ~(size_t)255;
+    int rc;
+    if ((rc = ensure(c, c->alias, fl_bytes + 5 * fr))) return rc;
+    char* base = (char*)c->alias.p;
+    float* planes = (float*)base;
+    uint8_t* d_sub = (uint8_t*)(base + fl_bytes);
+    uint8_t* d_rec = d_sub + fr;
+    uint8_t* d_la = d_rec + fr;
+    uint8_t* d_lb = d_la + fr;
+    uint8_t* d_in = d_lb + fr;
+    cudaStream_t s = c->stream;
+    const uint8_t* d_rgb = rgb;
+    if (rgb_loc == JDS_HOST) {
+        JDS_CUDA(cudaMemcpyAsync(d_in, rgb, frame_bytes, cudaMemcpyHostToDevice, s));
+        d_rgb = d_in;
+    }
+    c->launches += (uint64_t)launch_alias_subsample(height, width, prefilter, d_rgb, planes, d_sub, s);
+    JDS_CUDA(cudaGetLastError());
+
+    // the hot path at 4:4:4, prefilter off (aliasing_demo_dialog.py:152-158)
+    jds_params p;
+    memset(&p, 0, sizeof p);
+    p.height = height;
+    p.width = width;
+    p.quality = quality;
+    p.subsampling = JDS_SUB_444;
+    p.precision = precision;
+    p.outputs = JDS_OUT_RECON | JDS_OUT_PSNR;
+    jds_metrics unused;
+    UnitJob J;
+    memset(&J, 0, sizeof J);
+    if ((rc = make_geom(height, width, JDS_SUB_444, &J.g))) return rc;
+    J.p = &p;
+    J.units = 1;
+    J.rgb = d_sub;
+    J.rgb_loc = JDS_DEVICE;
+    J.recon = d_rec;
+    J.out_loc = JDS_DEVICE;
+    J.metrics = &unused;
+    if ((rc = run_job(c, J))) return rc;
+
+    // compute_metrics(original, reconstructed) (:69-83)
+    if ((rc = compare_device(c, d_rgb, d_rec, height, width, m_rgb))) return rc;
+    launch_alias_luma3(n_px, d_rgb, d_la, s);
+    launch_alias_luma3(n_px, d_rec, d_lb, s);
+    c->launches += 2;
+    if ((rc = compare_device(c, d_la, d_lb, height, width, m_luma))) return rc;
+
+    const cudaMemcpyKind out_kind = out_loc == JDS_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    if (diff) {
+        launch_alias_diff(frame_bytes, d_rgb, d_rec, d_la, s);      // d_la is free again
+        c->launches++;
+        JDS_CUDA(cudaMemcpyAsync(diff, d_la, frame_bytes, out_kind, s));
+    }
+    if (subsampled) JDS_CUDA(cudaMemcpyAsync(subsampled, d_sub, frame_bytes, out_kind, s));
+    if (recon) JDS_CUDA(cudaMemcpyAsync(recon, d_rec, frame_bytes, out_kind, s));
+    JDS_CUDA(cudaGetLastError());
+    JDS_CUDA(cudaStreamSynchronize(s));
+    return JDS_OK;
+}
+
+// compute_metrics(original, reconstructed) of the aliasing demo on its own
+// (gui/dialogs/aliasing_demo_dialog.py:69-83): RGB sums and OpenCV-integer-luma sums
+extern "C" int jds_aliasing_metrics(jds_ctx* c, const uint8_t* a, const uint8_t* b, int loc,
+                                    int height, int width, jds_metrics* m_rgb, jds_metrics* m_luma) {
+    if (!c || !a || !b || !m_rgb || !m_luma) return fail(JDS_ERR_INVALID, "NULL argument");
+    if (height < 1 || width < 1) return fail(JDS_ERR_INVALID, "bad frame size %dx%d", height, width);
+    JDS_CUDA(cudaSetDevice(c->device));
+    const size_t n_px = (size_t)height * width, frame_bytes = n_px * 3;
+    const size_t fr = (frame_bytes + 255) & ~(size_t)255;
+    int rc;
+    if ((rc = ensure(c, c->alias, 4 * fr))) return rc;
+    uint8_t* base = (uint8_t*)c->alias.p;
+    cudaStream_t s = c->stream;
+    const uint8_t *d_a = a, *d_b = b;
+    if (loc == JDS_HOST) {
+        JDS_CUDA(cudaMemcpyAsync(base + 2 * fr, a, frame_bytes, cudaMemcpyHostToDevice, s));
+        JDS_CUDA(cudaMemcpyAsync(base + 3 * fr, b, frame_bytes, cudaMemcpyHostToDevice, s));
+        d_a = base + 2 * fr;
+        d_b = base + 3 * fr;
+    }
+    if ((rc = compare_device(c, d_a, d_b, height, width, m_rgb))) return rc;
+    launch_alias_luma3(n_px, d_a, base, s);
+    launch_alias_luma3(n_px, d_b, base + fr, s);
+    c->launches += 2;
+    return compare_device(c, base, base + fr, height, width, m_luma);
 }
 
 // GUI plot payload: the round trip plus, instead of the 25 MB coefficient
@@ -1137,31 +1297,7 @@ extern "C" int jds_compare_images(jds_ctx* c, const uint8_t* a, const uint8_t* b
         d_a = (const uint8_t*)c->in.p;
         d_b = (const uint8_t*)c->recon.p;
     }
-    DevMetrics* dm = (DevMetrics*)c->metrics.p;
-    JDS_CUDA(cudaMemsetAsync(dm, 0, sizeof(DevMetrics), s));
-    const bool ssim_ok = height >= 7 && width >= 7;
-    // squared errors in integer / fp64 (PSNR_rgb exact, PSNR_y to fp64 rounding); SSIM sums
-    // from the strip kernel where the layout allows, else from the tile kernel
-    launch_sse_u8(d_a, d_b, (long long)height * width, dm, c->sm_count, s);
-    c->launches++;
-    if (ssim_ok) {
-        if (!c->legacy_ssim && ssim_strip_supported(height, width, d_a, frame_bytes, d_b, frame_bytes))
-            JDS_CUDA(launch_ssim_strip(height, width, d_a, frame_bytes, d_b, frame_bytes, dm, 1, true,
-                                       false, c->sm_count, s));
-        else
-            launch_ssim(true, height, width, d_a, frame_bytes, d_b, frame_bytes, dm, 1, s);
-        c->launches++;
-    }
-    JDS_CUDA(cudaGetLastError());
-    JDS_CUDA(cudaMemcpyAsync(c->h_metrics, dm, sizeof(DevMetrics), cudaMemcpyDeviceToHost, s));
-    JDS_CUDA(cudaStreamSynchronize(s));
-    const DevMetrics& d = *(const DevMetrics*)c->h_metrics;
-    memset(m, 0, sizeof *m);
-    m->sse_rgb = d.sse_rgb;
-    m->sse_y = d.sse_y;
-    for (int k = 0; k < 4; ++k) m->ssim_sum[k] = d.ssim_sum[k];
-    m->ssim_count = ssim_ok ? (uint64_t)(height - 6) * (uint64_t)(width - 6) : 0;
-    return JDS_OK;
+    return compare_device(c, d_a, d_b, height, width, m);
 }
 
 extern "C" int jds_bitrate_partials(jds_ctx* c, const int16_t* coeffs, int loc, uint64_t n,

@@ -59,5 +59,11 @@ void launch_block_ops(int op, long long n_blocks, const double* in, const int16_
 void launch_selected_block(const Geom& g, const uint8_t* rgb, int bx, int by,
                            const QTables* tables, void* out, cudaStream_t s);
 size_t selected_out_bytes();
+// chroma-aliasing demo front end (jds_alias.cu)
+size_t alias_scratch_floats(int H, int W);
+int launch_alias_subsample(int H, int W, int prefilter, const uint8_t* rgb, float* scratch,
+                           uint8_t* out, cudaStream_t s);     // returns the kernels launched
+void launch_alias_luma3(size_t n_px, const uint8_t* rgb, uint8_t* out, cudaStream_t s);
+void launch_alias_diff(size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out, cudaStream_t s);
 
 }  // namespace jds

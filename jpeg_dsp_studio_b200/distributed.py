@@ -169,40 +169,76 @@ def reduce_partials(local_sum: np.ndarray, device=None) -> np.ndarray:
     return t.cpu().numpy()
 
 
-def _sweep_device_resident(engine, image, qs, mine, mode, prefilter, precision, device, dist, world):
-    """Device-resident variant of the sharded sweep: the kernels write this rank's records
-    straight into the all-gather's send buffer (``jds_sweep_records``), the collective and
-    the single D2H copy are enqueued on the same stream, and the host synchronises ONCE per
-    sweep - no metric read-back, no host-built rows, no H2D in between."""
+class SweepHandle:
+    """A sharded sweep in flight (``sweep_sharded_begin``): kernels, all-gather and the D2H
+    copy of the table are enqueued; ``result()`` waits for them and returns the per-quality
+    dicts.  Several handles may be in flight - each owns its buffers until ``result()``."""
+
+    def __init__(self, key, bufs, event, n_units, hw, keep):
+        self._key, self._bufs, self._event = key, bufs, event
+        self._n, self._hw, self._keep, self._table = n_units, hw, keep, None
+
+    def table(self) -> np.ndarray:
+        """The gathered (n_units, F) record table, ordered by unit."""
+        if self._table is None:
+            self._event.synchronize()
+            t = self._bufs[2].numpy()
+            t = t[t[:, 0] >= 0]
+            t = t[np.argsort(t[:, 0], kind="stable")]       # fancy indexing: a copy
+            _gather_pool.setdefault(self._key, []).append(self._bufs)
+            self._bufs = self._keep = None
+            if len(t) != self._n or not np.array_equal(t[:, 0], np.arange(self._n)):
+                raise RuntimeError("sharded units do not cover 0..n_units-1 exactly once")
+            self._table = t
+        return self._table
+
+    def result(self) -> List[dict]:
+        return scalars_from_table(self.table(), *self._hw)
+
+
+_gather_pool = {}
+
+
+def sweep_sharded_begin(engine, image, qualities: Sequence[int], mode="4:2:0", prefilter=False, *,
+                        precision="fast", device=None) -> SweepHandle:
+    """Device-resident sharded sweep, asynchronous half: the kernels write this rank's
+    records straight into the all-gather's send buffer (``jds_sweep_records``), the
+    collective and the single D2H copy follow on the same stream, and NOTHING waits for the
+    GPU here - no metric read-back, no host-built rows, no H2D in between.  A caller that
+    sweeps many frames keeps one sweep in flight while it finalises the previous one."""
     import torch
     from . import _native as N
-    dev = torch.device(device)
+    dist = _dist()
+    rank = dist.get_rank() if dist else 0
+    world = dist.get_world_size() if dist else 1
+    qs = [int(q) for q in qualities]
+    mine = shard_indices(len(qs), rank, world)
+    dev = torch.device(device if device is not None else f"cuda:{engine.device}")
     cur = torch.cuda.current_stream(dev)
     if getattr(engine, "_stream_handle", None) != cur.cuda_stream:
         engine.use_stream(cur.cuda_stream)      # kernels, collective and copy share one stream
     nf = len(RECORD_FIELDS)
-    cap = (len(qs) + world - 1) // world
+    cap = max(1, (len(qs) + world - 1) // world)
+    if cap > N.JDS_SWEEP_RECORDS_MAX:
+        raise ValueError(f"at most {N.JDS_SWEEP_RECORDS_MAX} sweep points per rank and call")
     key = ("dev", world, cap, str(dev))
-    bufs = _gather_cache.get(key)
-    if bufs is None:
+    pool = _gather_pool.setdefault(key, [])
+    if pool:
+        bufs = pool.pop()
+    else:
         d_in = torch.empty((cap, nf), dtype=torch.float64, device=dev)
         d_out = torch.empty((world * cap, nf), dtype=torch.float64, device=dev) if world > 1 else d_in
         h_out = torch.empty((world * cap, nf), dtype=torch.float64).pin_memory()
-        bufs = _gather_cache[key] = (d_in, d_out, h_out)
+        bufs = (d_in, d_out, h_out)
     d_in, d_out, h_out = bufs
     keep = engine.sweep_records(image, [qs[i] for i in mine], d_in, mode=mode, prefilter=prefilter,
                                 precision=precision, unit0=(mine[0] if mine else 0), unit_step=world)
     if world > 1:
         dist.all_gather_into_tensor(d_out, d_in)
     h_out.copy_(d_out, non_blocking=True)
-    cur.synchronize()
-    del keep
-    table = h_out.numpy()
-    table = table[table[:, 0] >= 0]
-    table = table[np.argsort(table[:, 0], kind="stable")]
-    if len(table) != len(qs) or not np.array_equal(table[:, 0], np.arange(len(qs))):
-        raise RuntimeError("sharded units do not cover 0..n_units-1 exactly once")
-    return table
+    ev = torch.cuda.Event()
+    ev.record(cur)
+    return SweepHandle(key, bufs, ev, len(qs), (image.shape[0], image.shape[1]), (keep, image))
 
 
 def sweep_sharded(engine, image, qualities: Sequence[int], mode="4:2:0", prefilter=False, *,
@@ -222,9 +258,8 @@ def sweep_sharded(engine, image, qualities: Sequence[int], mode="4:2:0", prefilt
         on_gpu = torch.device(device).type == "cuda"
     from . import _native as N
     if on_gpu and (len(qs) + world - 1) // world <= N.JDS_SWEEP_RECORDS_MAX:
-        table = _sweep_device_resident(engine, image, qs, mine, mode, prefilter, precision, device,
-                                       dist, world)
-        return scalars_from_table(table, h, w)
+        return sweep_sharded_begin(engine, image, qs, mode, prefilter, precision=precision,
+                                   device=device).result()
     rows = np.zeros((0, len(RECORD_FIELDS)))
     if mine:
         my_qs = [qs[i] for i in mine]

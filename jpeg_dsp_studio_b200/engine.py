@@ -305,6 +305,62 @@ class Engine:
             N.check(self._lib.jds_resize_area(self._ctx, ptr, loc, h, w, optr, int(out_h), int(out_w), loc))
         return out
 
+    # -- chroma-aliasing demo (gui/dialogs/aliasing_demo_dialog.py:98-166) ----
+    def aliasing_demo_arm(self, image, quality=50, prefilter=False, *, precision="exact",
+                          want_subsampled=False, want_diff=True) -> dict:
+        """One arm of the reference's AliasingDemoWorker: explicit float32 chroma subsampling
+        (optionally behind the 5x5 Gaussian), the hot path at 4:4:4, ``compute_metrics``
+        against the original and the x10 difference image.  Returns ``recon``, ``diff``,
+        ``subsampled`` (uint8 H x W x 3 or None) and ``metrics`` (psnr_y, ssim_y, psnr_rgb,
+        ssim_rgb as the reference's ``compute_metrics`` defines them: Y is OpenCV's integer
+        luma)."""
+        h, w, _ = self._frame_geometry(image)
+        ptr, loc, keep = self._in_ptr(image)
+        CompressionParams(quality=int(quality))
+        if loc == N.JDS_DEVICE:
+            import torch
+            mk = lambda: torch.empty((h, w, 3), dtype=torch.uint8, device=keep.device)
+        else:
+            mk = lambda: host_array((h, w, 3), np.uint8)
+        recon = mk()
+        diff = mk() if want_diff else None
+        sub = mk() if want_subsampled else None
+        gp = lambda t: None if t is None else C.c_void_p(t.data_ptr() if _is_torch(t) else t.ctypes.data)
+        m_rgb, m_luma = N.JdsMetrics(), N.JdsMetrics()
+        with self._lock:
+            N.check(self._lib.jds_aliasing_demo(self._ctx, ptr, loc, h, w, int(quality), int(bool(prefilter)),
+                                                _precision_code(precision), gp(sub), gp(recon), gp(diff),
+                                                loc, C.byref(m_rgb), C.byref(m_luma)))
+        metrics = self._aliasing_metrics_dict(m_rgb, m_luma, h, w)
+        return {'recon': recon, 'diff': diff, 'subsampled': sub, 'metrics': metrics}
+
+    @staticmethod
+    def _aliasing_metrics_dict(m_rgb, m_luma, h, w) -> dict:
+        from .utils.metrics import psnr_from_sse
+        n_px = h * w
+        cnt = m_rgb.ssim_count
+        return {
+            'psnr_y': psnr_from_sse(m_luma.sse_rgb // 3, n_px),
+            'ssim_y': float(np.float64(m_luma.ssim_sum[0]) / np.float64(cnt)) if cnt else float('nan'),
+            'psnr_rgb': psnr_from_sse(m_rgb.sse_rgb, 3 * n_px),
+            'ssim_rgb': float((np.array([m_rgb.ssim_sum[0], m_rgb.ssim_sum[1], m_rgb.ssim_sum[2]],
+                                        dtype=np.float64) / np.float64(cnt)).mean()) if cnt else float('nan'),
+        }
+
+    def aliasing_metrics(self, original, reconstructed) -> dict:
+        """The aliasing demo's ``compute_metrics`` (gui/dialogs/aliasing_demo_dialog.py:69-83)."""
+        h, w, _ = self._frame_geometry(original)
+        if tuple(original.shape) != tuple(reconstructed.shape):
+            raise ValueError('Input images must have the same dimensions.')
+        pa, loc, ka = self._in_ptr(original)
+        pb, loc_b, kb = self._in_ptr(reconstructed)
+        if loc != loc_b:
+            raise ValueError('both frames must live on the same side (host or device)')
+        m_rgb, m_luma = N.JdsMetrics(), N.JdsMetrics()
+        with self._lock:
+            N.check(self._lib.jds_aliasing_metrics(self._ctx, pa, pb, loc, h, w, C.byref(m_rgb), C.byref(m_luma)))
+        return self._aliasing_metrics_dict(m_rgb, m_luma, h, w)
+
     def selected_block(self, image, quality, block_row, block_col):
         """IntermediateData.selected_block_* (engines/pipeline.py:126-151) or None."""
         h, w, _ = self._frame_geometry(image)

@@ -99,3 +99,35 @@ SWEEP_QUALITIES = list(range(1, 101))
 
 def sha(a: np.ndarray) -> str:
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+# --- chroma-aliasing demo (gui/dialogs/aliasing_demo_dialog.py) -----------
+@dataclass(frozen=True)
+class AliasingCase:
+    name: str
+    make: Callable[[], np.ndarray]
+    quality: int
+
+    def image(self) -> np.ndarray:
+        return self.make()
+
+
+def _alias_patterns():
+    from jpeg_dsp_studio_b200.engines import aliasing_demo as AD
+    return AD
+
+
+ALIASING_CASES = [
+    # the dialog's three synthetic patterns at its default size and quality (:20-66, Q=50)
+    AliasingCase("stripes256_q50", lambda: _alias_patterns().generate_equiluminance_stripes(256), 50),
+    AliasingCase("chroma_checker256_q50", lambda: _alias_patterns().generate_chroma_checkerboard(256), 50),
+    AliasingCase("checker1px256_q50", lambda: _alias_patterns().generate_1px_checkerboard(256), 50),
+    AliasingCase("checker1px64_q10", lambda: _alias_patterns().generate_1px_checkerboard(64), 10),
+    # loaded images / ROI crops of any size (:398-434): block-aligned, ragged and odd
+    AliasingCase("rand96x128_q50", lambda: rand_rgb(31, 96, 128), 50),
+    AliasingCase("rand57x75_q35", lambda: rand_rgb(32, 57, 75), 35),
+    AliasingCase("rand33x70_q90", lambda: rand_rgb(33, 33, 70), 90),
+    AliasingCase("rand40x9_q50", lambda: rand_rgb(34, 40, 9), 50),
+    AliasingCase("photo200x264_q60", lambda: np.ascontiguousarray(TI.generate_photo(512)[100:300, 40:304]), 60),
+    AliasingCase("photo512_q25", lambda: TI.generate_photo(512), 25),
+]

@@ -148,3 +148,47 @@ extern "C" long emul_division_selftest(long n_per_q) {
     }
     return bad;
 }
+
+// ---- chroma-aliasing demo front end (jds_alias.cuh), one call per kernel thread ----------
+#include "../../jpeg_dsp_studio_b200/csrc/jds_alias.cuh"
+
+extern "C" int emul_alias_subsample(int H, int W, int prefilter, const uint8_t* rgb, uint8_t* out) {
+    const int hs = (H + 1) / 2, ws = (W + 1) / 2;
+    const size_t n = (size_t)H * W;
+    std::vector<float> Y(n), Cr(n), Cb(n), Crs((size_t)hs * ws), Cbs((size_t)hs * ws);
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            const uint8_t* p = rgb + ((size_t)y * W + x) * 3;
+            alias_forward_px((float)p[0], (float)p[1], (float)p[2], x < 8 * (W / 8), Y[(size_t)y * W + x],
+                             Cr[(size_t)y * W + x], Cb[(size_t)y * W + x]);
+        }
+    const float *cr_src = Cr.data(), *cb_src = Cb.data();
+    size_t row_stride = 2 * (size_t)W;
+    int col_stride = 2;
+    if (prefilter) {
+        for (int yo = 0; yo < hs; ++yo)
+            for (int xo = 0; xo < ws; ++xo) {
+                Crs[(size_t)yo * ws + xo] = alias_blur_at(Cr.data(), H, W, 2 * xo, 2 * yo);
+                Cbs[(size_t)yo * ws + xo] = alias_blur_at(Cb.data(), H, W, 2 * xo, 2 * yo);
+            }
+        cr_src = Crs.data();
+        cb_src = Cbs.data();
+        row_stride = (size_t)ws;
+        col_stride = 1;
+    }
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            const float cr = alias_upsample_at(cr_src, row_stride, col_stride, hs, ws, H, W, x, y);
+            const float cb = alias_upsample_at(cb_src, row_stride, col_stride, hs, ws, H, W, x, y);
+            alias_inverse_px(Y[(size_t)y * W + x], cr, cb, out + ((size_t)y * W + x) * 3);
+        }
+    return 0;
+}
+
+extern "C" void emul_alias_luma_diff(size_t n_px, const uint8_t* a, const uint8_t* b, uint8_t* luma_a,
+                                     uint8_t* diff) {
+    for (size_t i = 0; i < n_px; ++i) {
+        luma_a[i] = alias_luma_u8(a[3 * i], a[3 * i + 1], a[3 * i + 2]);
+        for (int k = 0; k < 3; ++k) diff[3 * i + k] = alias_diff_u8(a[3 * i + k], b[3 * i + k]);
+    }
+}
