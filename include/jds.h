@@ -257,6 +257,18 @@ int jds_aliasing_metrics(jds_ctx* ctx, const uint8_t* a, const uint8_t* b, int l
                          int width, jds_metrics* m_rgb, jds_metrics* m_luma);
 
 /*
+ * Entropy-coded size: the reference reports only "Estimated (no entropy coding)"
+ * (utils/metrics.py:51-92) and leaves ZIGZAG_ORDER (utils/constants.py:18-27) unused.  This is
+ * the exact number of bits a baseline JPEG (ITU-T T.81: zig-zag scan, DC differences, run/size
+ * Huffman codes with the Annex K tables - luminance tables for Y, chrominance for Cb/Cr)
+ * spends on `coeffs` (int16, the order of all_quantized_coeffs, jds_coeff_count() values,
+ * host or device) when the three components are coded as non-interleaved scans:
+ * scan_bits[0..2] = Y, Cb, Cr, before byte stuffing and padding.
+ */
+int jds_entropy_bits(jds_ctx* ctx, const int16_t* coeffs, int loc, int height, int width,
+                     int subsampling, uint64_t scan_bits[3]);
+
+/*
  * Stand-alone 8x8 block operators, exact (reference) arithmetic, host buffers:
  *   op 0 dct2, 1 idct2 (engines/dct_engine.py:7-14), 2 encode_block (-128 then DCT, :17-20),
  *   3 decode_block (IDCT, +128, clip, :23-27): in/out = n_blocks*64 fp64;

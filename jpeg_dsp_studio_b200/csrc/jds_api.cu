@@ -986,6 +986,35 @@ extern "C" int jds_aliasing_metrics(jds_ctx* c, const uint8_t* a, const uint8_t*
     return compare_device(c, base, base + fr, height, width, m_luma);
 }
 
+// Exact size of the baseline-JPEG (T.81 Huffman, Annex K tables) scans of a coefficient array
+// in the reference's order (engines/pipeline.py:56,99) - SURVEY 8f #4: the on-wire size the
+// reference's estimate_bitrate_no_entropy (utils/metrics.py:51-92) only approximates.
+extern "C" int jds_entropy_bits(jds_ctx* c, const int16_t* coeffs, int loc, int height, int width,
+                                int subsampling, uint64_t scan_bits[3]) {
+    if (!c || !coeffs || !scan_bits) return fail(JDS_ERR_INVALID, "NULL argument");
+    Geom g;
+    int rc = make_geom(height, width, subsampling, &g);
+    if (rc) return rc;
+    JDS_CUDA(cudaSetDevice(c->device));
+    const size_t ncoef = 64ull * (size_t)(g.nblk_y + 2 * g.nblk_c);
+    if ((rc = ensure(c, c->metrics, sizeof(DevMetrics)))) return rc;
+    if ((rc = ensure_pinned(&c->h_metrics, &c->h_metrics_bytes, sizeof(DevMetrics)))) return rc;
+    cudaStream_t s = c->stream;
+    const int16_t* d_c = coeffs;
+    if (loc == JDS_HOST) {
+        if ((rc = ensure(c, c->coeffs, ncoef * 2))) return rc;
+        JDS_CUDA(cudaMemcpyAsync(c->coeffs.p, coeffs, ncoef * 2, cudaMemcpyHostToDevice, s));
+        d_c = (const int16_t*)c->coeffs.p;
+    }
+    unsigned long long* d_bits = (unsigned long long*)c->metrics.p;
+    JDS_CUDA(launch_entropy_bits(d_c, g.nblk_y, g.nblk_c, d_bits, s));
+    c->launches++;
+    JDS_CUDA(cudaMemcpyAsync(c->h_metrics, d_bits, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    JDS_CUDA(cudaStreamSynchronize(s));
+    for (int k = 0; k < 3; ++k) scan_bits[k] = ((const unsigned long long*)c->h_metrics)[k];
+    return JDS_OK;
+}
+
 // GUI plot payload: the round trip plus, instead of the 25 MB coefficient
 // array and the 66 MB fp64 error maps, what the reference's plots draw from them
 // (gui/compression_tab.py:653-676 -> gui/widgets/mpl_canvas.py:81-130): the count of every

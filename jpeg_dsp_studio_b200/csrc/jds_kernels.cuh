@@ -59,6 +59,10 @@ void launch_block_ops(int op, long long n_blocks, const double* in, const int16_
 void launch_selected_block(const Geom& g, const uint8_t* rgb, int bx, int by,
                            const QTables* tables, void* out, cudaStream_t s);
 size_t selected_out_bytes();
+// baseline-JPEG entropy-coded size of a coefficient array (jds_entropy.cu): bits of the three
+// non-interleaved scans; blocks [0,ny) Y, then nc Cb, then nc Cr
+cudaError_t launch_entropy_bits(const int16_t* coeffs, long long ny, long long nc,
+                                unsigned long long* scan_bits, cudaStream_t s);
 // chroma-aliasing demo front end (jds_alias.cu)
 size_t alias_scratch_floats(int H, int W);
 int launch_alias_subsample(int H, int W, int prefilter, const uint8_t* rgb, float* scratch,

@@ -361,6 +361,31 @@ class Engine:
             N.check(self._lib.jds_aliasing_metrics(self._ctx, pa, pb, loc, h, w, C.byref(m_rgb), C.byref(m_luma)))
         return self._aliasing_metrics_dict(m_rgb, m_luma, h, w)
 
+    # -- entropy-coded size (second half) ------------------------------------
+    def entropy_bits(self, coeffs, height: int, width: int, mode="4:2:0") -> List[int]:
+        """Exact bits of the three baseline-JPEG scans (Y, Cb, Cr; Annex K Huffman tables) of
+        an ``all_quantized_coeffs`` array (int16 NumPy array or torch tensor, host or CUDA)."""
+        sub = _mode_code(mode)
+        n = C.c_uint64()
+        N.check(self._lib.jds_coeff_count(int(height), int(width), sub, C.byref(n)))
+        if _is_torch(coeffs):
+            import torch
+            if coeffs.dtype != torch.int16:
+                raise TypeError(f"coeffs must be int16, got {coeffs.dtype}")
+            t = coeffs.contiguous()
+            ptr, loc, keep, size = C.c_void_p(t.data_ptr()), (N.JDS_DEVICE if t.is_cuda else N.JDS_HOST), t, t.numel()
+        else:
+            a = np.ascontiguousarray(coeffs)
+            if a.dtype != np.int16:
+                raise TypeError(f"coeffs must be int16, got {a.dtype}")
+            ptr, loc, keep, size = C.c_void_p(a.ctypes.data), N.JDS_HOST, a, a.size
+        if size != n.value:
+            raise ValueError(f"expected {n.value} coefficients for {height}x{width} {mode}, got {size}")
+        out = (C.c_uint64 * 3)()
+        with self._lock:
+            N.check(self._lib.jds_entropy_bits(self._ctx, ptr, loc, int(height), int(width), sub, out))
+        return [int(out[0]), int(out[1]), int(out[2])]
+
     def selected_block(self, image, quality, block_row, block_col):
         """IntermediateData.selected_block_* (engines/pipeline.py:126-151) or None."""
         h, w, _ = self._frame_geometry(image)

@@ -1,0 +1,87 @@
+"""Entropy coding (second half) without a GPU: the oracle's baseline-JPEG coder
+(oracle/entropy_port.py) is pinned to an INDEPENDENT implementation - libjpeg-turbo through
+OpenCV: its Huffman tables equal the ones libjpeg writes, and the complete JFIF file it emits
+decodes to the round trip's own reconstruction."""
+
+import numpy as np
+import pytest
+
+from oracle import entropy_port as E
+from oracle import numpy_port as P
+from jpeg_dsp_studio_b200.utils import constants as K
+from jpeg_dsp_studio_b200.utils import test_images as TI
+from jpeg_dsp_studio_b200.utils import metrics as M
+
+
+def test_zigzag_is_the_reference_table():
+    assert np.array_equal(E.ZIGZAG, K.ZIGZAG_ORDER.ravel())
+    assert sorted(E.ZIGZAG.tolist()) == list(range(64))
+
+
+def test_tables_are_complete_prefix_codes():
+    for (kind, tid), (bits, vals) in E.TABLES.items():
+        assert sum(bits) == len(vals) == len(set(vals))
+        code, length = E.CODES[(kind, tid)]
+        words = sorted((int(length[v]), int(code[v])) for v in vals)
+        strs = [format(c, "0%db" % n) for n, c in words]
+        for i, a in enumerate(strs):                      # no code is a prefix of another
+            assert not any(b.startswith(a) for b in strs[i + 1:])
+        assert sum(2.0 ** -n for n, _ in words) < 1.0    # all-ones code word stays reserved
+
+
+def test_tables_equal_libjpeg_turbo():
+    cv2 = pytest.importorskip("cv2")
+    ok, buf = cv2.imencode(".jpg", np.random.default_rng(0).integers(0, 256, (64, 64, 3), dtype=np.uint8))
+    b, i, found = buf.tobytes(), 2, {}
+    while i < len(b):
+        marker, size = b[i + 1], int.from_bytes(b[i + 2:i + 4], "big")
+        if marker == 0xC4:
+            p = b[i + 4:i + 2 + size]
+            while p:
+                n = sum(p[1:17])
+                found[("ac" if p[0] >> 4 else "dc", p[0] & 15)] = (list(p[1:17]), list(p[17:17 + n]))
+                p = p[17 + n:]
+        if marker == 0xDA:
+            break
+        i += 2 + size
+    for k, (bits, vals) in E.TABLES.items():
+        assert found[k] == (list(bits), list(vals)), k
+
+
+@pytest.mark.parametrize("mode", ["4:4:4", "4:2:2", "4:2:0"])
+@pytest.mark.parametrize("q", [5, 50, 95])
+def test_jfif_decodes_to_the_round_trip(mode, q):
+    """libjpeg's integer IDCT / upsampling / colour conversion differ from the reference's
+    float pipeline by a few grey levels at most; a wrong code length, run or sign would give
+    garbage (or no image at all)."""
+    cv2 = pytest.importorskip("cv2")
+    for img in (TI.generate_photo(256)[:96, :144], np.random.default_rng(1).integers(0, 256, (40, 56, 3), dtype=np.uint8)):
+        o = P.compress_reconstruct(img, q, mode, False, want_maps=False)
+        data, bits = E.encode_jfif(o["all_quantized_coeffs"], img.shape[:2], mode, P.scale_quant_matrix(q))
+        assert bits == E.huffman_scan_bits(o["all_quantized_coeffs"], img.shape[:2], mode)
+        dec = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
+        assert dec is not None and dec.shape == img.shape
+        d = dec[..., ::-1].astype(np.int32) - o["reconstructed_image"].astype(np.int32)
+        assert np.abs(d).max() <= 4
+        assert 10 * np.log10(255.0 ** 2 / max(float(np.mean(d * d)), 1e-12)) >= 45.0
+        # the file is the fixed headers + the padded scans + 0xFF stuffing bytes
+        payload = sum((b + 7) // 8 for b in bits)
+        stuffing = len(data) - M.JFIF_HEADER_BYTES - payload
+        assert 0 <= stuffing <= 0.05 * payload + 4
+
+
+def test_extreme_values_and_runs():
+    """largest magnitudes (Q=100 table of ones: DC +-1016..1024, category 11), a lone last
+    coefficient (three ZRL + run 14) and an empty block (EOB only)"""
+    blocks = np.zeros((4, 64), dtype=np.int64)
+    blocks[0, 0] = -1024
+    blocks[1, 0] = 1016                       # diff 2040 -> category 11
+    blocks[1, 63] = -1                        # zig-zag position 63: run 62 = 3 ZRL + 14
+    blocks[2, E.ZIGZAG[1]] = 1023             # size 10
+    _, dcl = E.CODES[("dc", 0)]
+    _, acl = E.CODES[("ac", 0)]
+    want = (dcl[11] + 11 + acl[0]) + (dcl[11] + 11 + 3 * acl[0xF0] + acl[(14 << 4) | 1] + 1) + \
+           (dcl[10] + 10 + acl[0x0A] + 10 + acl[0]) + (dcl[0] + acl[0])
+    assert E.component_scan_bits(blocks, 0) == int(want)
+    data, nbits = E._encode_scan(blocks, 0)
+    assert nbits == int(want)
