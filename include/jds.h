@@ -186,6 +186,13 @@ int jds_sweep_records(jds_ctx* ctx, const jds_params* params, const int32_t* qua
                       const uint8_t* rgb, int rgb_loc, int unit0, int unit_step,
                       double* records, int capacity);
 
+/* jds_roundtrip_batch with device-resident records (rows as for jds_sweep_records, quality =
+ * params->quality, no synchronisation): frames and the optional reconstruction are DEVICE
+ * buffers.  For callers that stream batch after batch and read the metrics at the end. */
+int jds_roundtrip_batch_records(jds_ctx* ctx, const jds_params* params, int n_frames,
+                                const uint8_t* rgb, uint8_t* recon, int unit0, int unit_step,
+                                double* records, int capacity);
+
 /*
  * The six 8x8 arrays of IntermediateData.selected_block_* for luma block
  * (block_row, block_col) (engines/pipeline.py:126-151): original, shifted, dct,

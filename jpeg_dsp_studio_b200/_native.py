@@ -77,6 +77,8 @@ PROTOTYPES = {
                                        C.POINTER(JdsMetrics), C.POINTER(JdsMetrics)]),
     "jds_entropy_bits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.POINTER(C.c_uint64)]),
+    "jds_roundtrip_batch_records": (C.c_int, [C.c_void_p, C.POINTER(JdsParams), C.c_int, C.c_void_p,
+                                              C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "jds_plot_payload": (C.c_int, [C.c_void_p, C.POINTER(JdsParams), C.c_void_p, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                    C.POINTER(JdsMetrics)]),

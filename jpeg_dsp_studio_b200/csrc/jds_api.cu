@@ -844,6 +844,39 @@ extern "C" int jds_sweep_records(jds_ctx* c, const jds_params* p, const int32_t*
     return run_job(c, J);
 }
 
+// jds_roundtrip_batch whose metric records stay on the device (same contract as
+// jds_sweep_records: rows of JDS_RECORD_FIELDS doubles, no synchronisation).  Frames and the
+// optional reconstruction are DEVICE buffers; a caller streaming batches enqueues step after
+// step (and, sharded over GPUs, one all-reduce of the rows per step) and synchronises once.
+extern "C" int jds_roundtrip_batch_records(jds_ctx* c, const jds_params* p, int n_frames,
+                                           const uint8_t* rgb, uint8_t* recon, int unit0,
+                                           int unit_step, double* records, int capacity) {
+    if (!c || !rgb || !records) return fail(JDS_ERR_INVALID, "NULL argument");
+    if (n_frames < 1 || n_frames > capacity || capacity > JDS_SWEEP_RECORDS_MAX)
+        return fail(JDS_ERR_INVALID, "need 1 <= n_frames <= capacity <= %d, got n_frames %d capacity %d",
+                    JDS_SWEEP_RECORDS_MAX, n_frames, capacity);
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (p->quality < 1 || p->quality > 100)
+        return fail(JDS_ERR_INVALID, "Quality must be 1-100, got %d", p->quality);
+    if (p->outputs & (JDS_OUT_ERR_Y | JDS_OUT_ERR_RGB | JDS_OUT_COEFFS | JDS_OUT_HIST))
+        return fail(JDS_ERR_INVALID, "jds_roundtrip_batch_records produces recon and metric records only");
+    UnitJob J;
+    memset(&J, 0, sizeof J);
+    if ((rc = make_geom(p->height, p->width, p->subsampling, &J.g))) return rc;
+    J.p = p;
+    J.units = n_frames;
+    J.rgb = rgb;
+    J.rgb_loc = JDS_DEVICE;
+    J.recon = recon;
+    J.out_loc = JDS_DEVICE;
+    J.d_records = records;
+    J.rec_capacity = capacity;
+    J.unit0 = unit0;
+    J.unit_step = unit_step;
+    return run_job(c, J);
+}
+
 // ------------------------------------------------------------------------------
 // chroma-aliasing demo
 // ------------------------------------------------------------------------------

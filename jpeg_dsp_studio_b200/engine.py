@@ -502,6 +502,36 @@ class Engine:
                                                 C.c_void_p(records.data_ptr()), cap))
         return keep
 
+    def batch_records(self, frames, records, quality=50, mode="4:2:0", prefilter=False, *,
+                      precision="fast", recon_out=None, unit0=0, unit_step=1, want_ssim=True):
+        """``roundtrip_batch`` for CUDA tensors whose metric records stay on the device
+        (``jds_roundtrip_batch_records``; rows as in ``distributed.RECORD_FIELDS``).  Returns
+        WITHOUT synchronising - see ``sweep_records``."""
+        shape = tuple(frames.shape)
+        if len(shape) != 4 or shape[-1] != 3:
+            raise ValueError(f"expected N x H x W x 3 frames, got shape {shape}")
+        n, h, w, _ = shape
+        ptr, loc, keep = self._in_ptr(frames)
+        if loc != N.JDS_DEVICE:
+            raise TypeError("frames must be a CUDA uint8 tensor")
+        if not _is_torch(records) or not records.is_cuda or not records.is_contiguous():
+            raise TypeError("records must be a contiguous CUDA fp64 tensor")
+        if tuple(records.shape[1:]) != (N.JDS_RECORD_FIELDS,) or records.element_size() != 8:
+            raise ValueError(f"records must have shape (capacity, {N.JDS_RECORD_FIELDS}) fp64")
+        CompressionParams(quality=int(quality))
+        flags = N.JDS_OUT_PSNR | (N.JDS_OUT_SSIM if want_ssim else 0) | (N.JDS_OUT_RECON if recon_out is not None else 0)
+        p = self._params(h, w, quality, mode, prefilter, precision, flags)
+        rp = None
+        if recon_out is not None:
+            if not recon_out.is_cuda or tuple(recon_out.shape) != shape:
+                raise ValueError("recon_out must be a CUDA uint8 tensor of the frames' shape")
+            rp = C.c_void_p(recon_out.data_ptr())
+        with self._lock:
+            N.check(self._lib.jds_roundtrip_batch_records(self._ctx, C.byref(p), n, ptr, rp, int(unit0),
+                                                          int(unit_step), C.c_void_p(records.data_ptr()),
+                                                          int(records.shape[0])))
+        return keep
+
 
 _engines = {}
 _engines_lock = threading.Lock()

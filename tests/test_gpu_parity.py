@@ -392,6 +392,34 @@ def test_sweep_device_resident_records(J):
     eng.close()
 
 
+def test_batch_device_resident_records(J):
+    """jds_roundtrip_batch_records: streamed steps without host synchronisation leave the same
+    records (and the same reconstruction) as the synchronising batch call"""
+    import torch
+    from jpeg_dsp_studio_b200 import distributed as D, _native as N
+    eng = J.Engine(0)
+    dev = torch.device("cuda", 0)
+    eng.use_stream(torch.cuda.current_stream(dev).cuda_stream)
+    frames = np.stack([CS.rand_rgb(70 + k, 64, 96) for k in range(5)])
+    d = torch.from_numpy(frames).to(dev)
+    recs = [torch.zeros((6, N.JDS_RECORD_FIELDS), dtype=torch.float64, device=dev) for _ in range(3)]
+    recon = torch.empty_like(d)
+    for r, q in zip(recs, (30, 50, 80)):                     # three steps in flight, one sync
+        eng.batch_records(d, r, q, "4:2:2", False, precision="fast", recon_out=recon, unit0=1, unit_step=2)
+    torch.cuda.synchronize(dev)
+    for r, q in zip(recs, (30, 50, 80)):
+        outs = eng.roundtrip_batch(d, q, "4:2:2", False, precision="fast")
+        want = D.records_from_outputs([1 + 2 * i for i in range(5)], [q] * 5, outs)
+        got = r.cpu().numpy()
+        assert np.array_equal(got[:5, [0, 1, 2, 8, 9, 10, 11, 12]], want[:, [0, 1, 2, 8, 9, 10, 11, 12]])
+        assert np.allclose(got[:5, 3:8], want[:, 3:8], rtol=1e-12)
+        assert got[5, 0] == -1.0
+    assert np.array_equal(recon.cpu().numpy(), np.stack([o.recon.cpu().numpy() for o in outs]))
+    with pytest.raises(TypeError):
+        eng.batch_records(frames, recs[0])
+    eng.close()
+
+
 def test_public_sweep_and_batch_api(J, oracle):
     """quality_sweep / compress_batch (the BatchSweepWorker-shaped and batch entry points of
     engines/pipeline.py) return CompressionResult objects consistent with single calls."""
