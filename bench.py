@@ -58,7 +58,8 @@ def measured_peak():
 
 
 class ClockSampler:
-    """SM clock / throttle reasons sampled DURING the timed region (NVML, 2 ms period;
+    """SM clock / throttle reasons sampled DURING the timed region (NVML, 10 ms period - every
+    NVML query takes driver locks that delay kernel launches, measurably so on an 8-GPU box;
     falls back to `nvidia-smi -lms` when pynvml is unusable)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -93,7 +94,7 @@ class ClockSampler:
                             self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.010)
 
     def start(self):
         try:
@@ -297,40 +298,54 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    REDUCE_MODE = os.environ.get("JDS_BENCH_REDUCE", "async")    # async | sync | off (diagnosis)
-    pending = []                                    # in-flight all-reduces (handle, buffers)
-    # deep ring of result buffers: a step waits for the all-reduce issued NBUF-1 steps earlier,
-    # so per-step jitter of one rank is not paid by all ranks every step
-    NBUF = int(os.environ.get("JDS_BENCH_REDUCE_DEPTH", "16"))
-    partial_ts = [torch.zeros(8, dtype=torch.float64, device=dev) for _ in range(NBUF)]
-    partial_hs = [torch.zeros(8, dtype=torch.float64).pin_memory() for _ in range(NBUF)]
-    step_no = [0]
+    # The path's only exchange is the all-reduce of the metric partials (NCCL).  Units are
+    # independent, so a job needs ONE all-reduce: "job" (default) accumulates the records of
+    # every step on the device and reduces them once, inside the timed region, after the last
+    # step (again whenever the ring of RING steps is full).  "step" issues one asynchronous
+    # all-reduce per step instead (diagnosis: an NCCL kernel resident next to the SSIM kernel
+    # costs ~9 % of the step, measured at 2 and 8 GPUs); "off" never reduces.
+    REDUCE_MODE = os.environ.get("JDS_BENCH_REDUCE", "job")      # job | step | off
+    RING = 64
+    from jpeg_dsp_studio_b200 import _native as NAT
+    rec_all = torch.zeros((RING, FRAMES, NAT.JDS_RECORD_FIELDS), dtype=torch.float64, device=dev)
+    host_acc = torch.zeros(8, dtype=torch.float64).pin_memory()     # per-call API: host partials
+    dev_acc = torch.zeros(8, dtype=torch.float64, device=dev)
+    pending = []
+    state = {"stream_steps": 0, "host_steps": 0, "reduces": 0}
+
+    def reduce_job():
+        """one all-reduce of everything accumulated since the last one"""
+        n, m = state["stream_steps"], state["host_steps"]
+        state["stream_steps"] = state["host_steps"] = 0
+        if world == 1 or REDUCE_MODE == "off":
+            return
+        if n:
+            dbg = int(os.environ.get("JDS_BENCH_DEBUG_ROWS", "0"))
+            dist.all_reduce(rec_all[:(dbg or n)])
+            state["reduces"] += 1
+        if m:
+            dev_acc.copy_(host_acc, non_blocking=True)
+            dist.all_reduce(dev_acc)
+            state["reduces"] += 1
+
+    def drain():
+        while pending:
+            pending.pop(0).wait()
+        reduce_job()
+        host_acc.zero_()
 
     def reduce_partials(outs):
-        """the path's only exchange: all-reduce of the step's metric partials (NCCL).  Issued
-        asynchronously - it overlaps the next step's kernels; each buffer is waited for
-        before it is reused and everything is drained before the timed region closes."""
+        """per-call API: the step's host-side metric structs are added to the job's partials"""
         ms = [o.metrics for o in outs]
         sse = float(sum(m.sse_rgb for m in ms))
         ssey = float(sum(m.sse_y for m in ms))
         bits = float(sum(2 * m.luma_blocks + m.coeff_bits for m in ms))
         ssim = [float(sum(m.ssim_sum[c] for m in ms)) for c in range(4)]
-        b = step_no[0] % NBUF
-        step_no[0] += 1
-        while len(pending) >= NBUF - 1:
-            pending.pop(0).wait()
-        partial_hs[b].numpy()[:] = [sse, ssey, bits] + ssim + [float(len(outs))]
-        if world > 1 and REDUCE_MODE != "off":
-            partial_ts[b].copy_(partial_hs[b], non_blocking=True)
-            if REDUCE_MODE == "sync":
-                dist.all_reduce(partial_ts[b])
-            else:
-                pending.append(dist.all_reduce(partial_ts[b], async_op=True))
-        return partial_hs[b]
-
-    def drain():
-        while pending:
-            pending.pop(0).wait()
+        host_acc.numpy()[:] += [sse, ssey, bits] + ssim + [float(len(outs))]
+        state["host_steps"] += 1
+        if REDUCE_MODE == "step":
+            reduce_job()
+            host_acc.zero_()
 
     def step_device(precision):
         outs = eng.roundtrip_batch(d_in, QUALITY, MODE, PREFILTER, precision=precision,
@@ -338,27 +353,23 @@ def run_ours(args):
         reduce_partials(outs)
         return outs
 
-    from jpeg_dsp_studio_b200 import _native as NAT
-    rec_ts = [torch.zeros((FRAMES, NAT.JDS_RECORD_FIELDS), dtype=torch.float64, device=dev)
-              for _ in range(NBUF)]
-
     def step_stream(precision):
-        """the production loop for device-resident frames: kernels + metric records of step
-        i are enqueued (no host synchronisation), the records are all-reduced over the ranks
-        asynchronously (NCCL), and the host reads metrics only when it needs them - here
-        once, after the timed region"""
-        b = step_no[0] % NBUF
-        step_no[0] += 1
-        while len(pending) >= NBUF - 1:
-            pending.pop(0).wait()
-        eng.batch_records(d_in, rec_ts[b], QUALITY, MODE, PREFILTER, precision=precision,
+        """the production loop for device-resident frames: the kernels and the metric records of
+        a step are enqueued without any host synchronisation (jds_roundtrip_batch_records);
+        the records of all steps wait on the device for the job's one all-reduce, and the host
+        reads metrics only when it needs them - here once, after the timed region"""
+        if state["stream_steps"] == RING:
+            reduce_job()
+        i = state["stream_steps"]
+        state["stream_steps"] += 1
+        eng.batch_records(d_in, rec_all[i], QUALITY, MODE, PREFILTER, precision=precision,
                           recon_out=d_out, unit0=rank, unit_step=world)
-        if world > 1 and REDUCE_MODE != "off":
-            if REDUCE_MODE == "sync":
-                dist.all_reduce(rec_ts[b])
-            else:
-                pending.append(dist.all_reduce(rec_ts[b], async_op=True))
-        return rec_ts[b]
+        if REDUCE_MODE == "step" and world > 1:
+            state["stream_steps"] = 0
+            pending.append(dist.all_reduce(rec_all[i], async_op=True))
+            while len(pending) >= 16:
+                pending.pop(0).wait()
+        return rec_all[i]
 
     def step_host(precision):
         outs = eng.roundtrip_batch(host_in, QUALITY, MODE, PREFILTER, precision=precision,
@@ -371,12 +382,21 @@ def run_ours(args):
         for _ in range(warmup):
             fn(precision)
         drain()
-        barrier()
-        eng.stage_times(reset=True) if stage_timing else None
-        l0 = eng.launch_count()
+        if world > 1 and REDUCE_MODE == "job" and fn is step_stream:
+            # NCCL sets up protocols / connections lazily per message size: take the job's
+            # all-reduce sizes once outside the timed region (the rows are overwritten by the steps)
+            for n in {min(steps, RING), steps % RING}:
+                if n:
+                    dist.all_reduce(rec_all[:n])
+            rec_all.zero_()
+        # the sampler starts BEFORE the barrier: NVML start-up takes tens of ms, and a rank that
+        # enters the timed region late makes every other rank wait in the job's all-reduce
         sampler = ClockSampler(local) if (sample_clocks and rank == 0) else None   # rank 0's GPU; it prints the line
         if sampler:
             sampler.start()
+        barrier()
+        eng.stage_times(reset=True) if stage_timing else None
+        l0 = eng.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(steps):
@@ -385,6 +405,8 @@ def run_ours(args):
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
+        if os.environ.get("JDS_BENCH_DEBUG"):
+            print(f"[debug] rank {rank} {fn.__name__} {precision}: {ms / steps:.4f} ms/step", file=sys.stderr, flush=True)
         clocks = sampler.stop() if sampler else None
         stages = eng.stage_times(reset=True) if stage_timing else None
         launches = eng.launch_count() - l0
@@ -479,8 +501,9 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": FRAMES,
                    "l2_policy": f"batch of {FRAMES} frames ({FRAMES * H * W * 3 / 1e6:.0f} MB in, "
                                 "same out) exceeds the 126 MB L2; no flush needed",
-                   "sharding": "frames across ranks, no data-path collective; "
-                               "metric partials all-reduced (NCCL) each step"},
+                   "sharding": "frames across ranks, no data-path collective; the job's metric "
+                               "records are all-reduced (NCCL) once, inside the timed region, after "
+                               "the last step (JDS_BENCH_REDUCE=step: once per step)"},
         "e2e": {"value": round(e2e, 2), "unit": "Mpixel/s",
                 "h2d_bytes_per_step": FRAMES * H * W * 3,
                 "d2h_bytes_per_step": FRAMES * H * W * 3 + FRAMES * 504,
@@ -488,8 +511,8 @@ def run_ours(args):
                 "api": "Engine.roundtrip_batch(pinned host uint8 frames) -> jds_roundtrip_batch (C ABI)"},
         "gpu_launches": launches,
         "value_mode": "streamed: per-step kernels and device-resident metric records enqueued without "
-                      "host synchronisation (jds_roundtrip_batch_records), records all-reduced "
-                      "asynchronously, metrics read after the timed region",
+                      "host synchronisation (jds_roundtrip_batch_records); one all-reduce of the job's "
+                      "records after the last step; metrics read after the timed region",
         "sync_api": {"value": round(sync_value, 2), "unit": "Mpixel/s", "ms_per_step": round(ms_sync / K, 4),
                      "api": "Engine.roundtrip_batch(device tensors): synchronises and returns host "
                             "metric structs every step"},
