@@ -22,8 +22,20 @@
 //     bits of the Y sums; the Y accumulators are rebuilt from the ring every chunk so
 //     rounding cannot drift down a strip.
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 #include "jds_kernels.cuh"
+
+// tuning knobs (defaults = the measured best; tools/ssim_variants.sh builds the others)
+#ifndef JDS_SSIM_REBUILD_EVERY
+#define JDS_SSIM_REBUILD_EVERY 1     // chunks between rebuilds of the non-integer (B,Y) accumulators
+#endif
+#ifndef JDS_SSIM_SPLIT_Q
+#define JDS_SSIM_SPLIT_Q 0           // pass 1: separate x^2 / y^2 chains (more ILP, one more add per window)
+#endif
+#ifndef JDS_SSIM_CTAS_PER_SM
+#define JDS_SSIM_CTAS_PER_SM 0       // 0: pick the vertical segmentation by the wave model below; n: aim at n CTAs per SM
+#endif
 
 namespace jds {
 
@@ -113,10 +125,25 @@ __device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __ffma2_rn(b
 //   S = 2 A1 A2 / (B1 B2),  A1 = 2 Ux Uy + C1 N^2,  B1 = Ux^2 + Uy^2 + C1 N^2,
 //   A2 = N Sxy - Sx Sy + C2 N (N-1) / 2,  B2 = N Sq - Sx^2 - Sy^2 + C2 N (N-1)
 // A2 and B2 are formed NEGATED (packed f32x2 has no operand negation, so every subtraction
-// would cost an instruction): (-A2)(-B2)^-1 has the same value, the constants carry the
-// signs, and the last product is fused into the accumulation - 14 packed instructions and
-// two MUFU.RCP per window pair.  Ux / Uy stay explicit: they are exact small integers on
-// dark content, where an expanded form cancels catastrophically.
+// would cost an instruction): (-A2)(-B2)^-1 has the same value, the constants carry the signs,
+// and the last product is fused into the accumulation.  Ux / Uy stay explicit: they are exact
+// small integers on dark content, where an expanded form cancels catastrophically.
+//
+// Cancellation.  On flat content far from mid-grey Sx Sy ~ N Sxy ~ 4e7 while their difference
+// is a few hundred: formed naively in fp32 (ulp 4 at 4e7) the covariance term is off by up to
+// 5e-5 of C2 N (N-1) / 2 with a systematic sign, which showed as 1.6e-5 in the mean SSIM of a
+// dark frame (tolerance 1e-5).  The compensated form below is exact for the integer channels:
+//   p  = RN(Sx Sy),  e = Sx Sy - p            (one FMA: the exact rounding error)
+//   N Sxy - p                                 (one FMA: the exact value is small, so no rounding)
+//   A2 = (N Sxy - p) - e + C2 N (N-1) / 2
+//   B2 = 2 A2 + D,   D = N Sum (x-y)^2 - (Sum (x-y))^2 = N (Sq - 2 Sxy) - (Sx - Sy)^2
+// (vx + vy = 2 vxy + var(x - y); the constants match because C2 N (N-1) = 2 * C2 N (N-1) / 2);
+// D involves only the DIFFERENCE of the images, which is small whenever SSIM matters.
+// B1 reuses the squared difference: Ux^2 + Uy^2 = 2 Ux Uy + (Ux - Uy)^2.
+// 19 packed instructions and two MUFU.RCP per window pair (14 for the naive form).
+#ifndef JDS_SSIM_COMPENSATED
+#define JDS_SSIM_COMPENSATED 1
+#endif
 __device__ __forceinline__ float2 ssim_window_half2_acc(float2 sx, float2 sy, float2 sq, float2 sc,
                                                         float2 ssum) {
     constexpr float N = 49.0f;
@@ -124,10 +151,24 @@ __device__ __forceinline__ float2 ssim_window_half2_acc(float2 sx, float2 sy, fl
     constexpr float K2 = 58.5225f * 49.0f * 48.0f;
     const float2 Ux = __fadd2_rn(sx, f2(128.0f * N)), Uy = __fadd2_rn(sy, f2(128.0f * N));
     const float2 A1 = __ffma2_rn(__fmul2_rn(Ux, Uy), f2(2.0f), f2(C1N2));
+#if JDS_SSIM_COMPENSATED
+    const float2 nsx = __fmul2_rn(sx, f2(-1.0f));
+    const float2 p = __fmul2_rn(sx, sy);
+    const float2 en = __ffma2_rn(nsx, sy, p);                        // p - Sx Sy, exact
+    const float2 c1n = __fadd2_rn(__ffma2_rn(sc, f2(-N), p), f2(-0.5f * K2));   // p - N Sxy - K2/2
+    const float2 A2n = __ffma2_rn(en, f2(-1.0f), c1n);               // -(N Sxy - Sx Sy + K2/2)
+    const float2 sdn = __fadd2_rn(nsx, sy);                          // Sy - Sx = Uy - Ux
+    const float2 sd2 = __fmul2_rn(sdn, sdn);
+    const float2 B1 = __fadd2_rn(A1, sd2);                           // Ux^2 + Uy^2 = 2 Ux Uy + (Ux - Uy)^2
+    const float2 sdd = __ffma2_rn(sc, f2(-2.0f), sq);                // Sum (x-y)^2
+    const float2 Dn = __ffma2_rn(sdd, f2(-N), sd2);                  // -D
+    const float2 B2n = __ffma2_rn(A2n, f2(2.0f), Dn);
+#else
     const float2 B1 = __ffma2_rn(Ux, Ux, __ffma2_rn(Uy, Uy, f2(C1N2)));
     const float2 A2n = __ffma2_rn(sc, f2(-N), __ffma2_rn(sx, sy, f2(-0.5f * K2)));
     const float2 un = __ffma2_rn(sx, sx, __ffma2_rn(sy, sy, f2(-K2)));
     const float2 B2n = __ffma2_rn(sq, f2(-N), un);
+#endif
     const float2 num = __fmul2_rn(A1, A2n), den = __fmul2_rn(B1, B2n);
     return __ffma2_rn(num, f2(rcp_approx(den.x), rcp_approx(den.y)), ssum);
 }
@@ -277,6 +318,9 @@ k_ssim_strip(int H, int W, int seg_rows, const uint8_t* __restrict__ a_img, size
             const bool own_all = p1_c0 + S_SEG <= own_px;
             float2 xs[S_SEG + 6], ys[S_SEG + 6];
             float2 wx = f2(0.f), wy = f2(0.f), wq = f2(0.f), wc = f2(0.f), sse = f2(0.f);
+#if JDS_SSIM_SPLIT_Q
+            float2 wq2 = f2(0.f);
+#endif
 #pragma unroll
             for (int i2 = 0; i2 < (S_SEG + 6) / 2; ++i2) {
                 const int off = (i2 & 1) * S_FHALF + (i2 >> 1);
@@ -293,18 +337,33 @@ k_ssim_strip(int H, int W, int seg_rows, const uint8_t* __restrict__ a_img, size
                     }
                     wx = __fadd2_rn(wx, xs[i]);
                     wy = __fadd2_rn(wy, ys[i]);
+#if JDS_SSIM_SPLIT_Q
+                    wq = __ffma2_rn(xs[i], xs[i], wq);
+                    wq2 = __ffma2_rn(ys[i], ys[i], wq2);
+#else
                     wq = __ffma2_rn(xs[i], xs[i], __ffma2_rn(ys[i], ys[i], wq));
+#endif
                     wc = __ffma2_rn(xs[i], ys[i], wc);
                     if (i >= 6) {
                         const int j = i - 6;
                         sm.hxy[p1_row][p1_pair * S_OW + p1_c0 + j] = make_float4(wx.x, wx.y, wy.x, wy.y);
+#if JDS_SSIM_SPLIT_Q
+                        const float2 wqs = __fadd2_rn(wq, wq2);
+                        sm.hqc[p1_row][p1_pair * S_OW + p1_c0 + j] = make_float4(wqs.x, wqs.y, wc.x, wc.y);
+#else
                         sm.hqc[p1_row][p1_pair * S_OW + p1_c0 + j] = make_float4(wq.x, wq.y, wc.x, wc.y);
+#endif
                         if (j < S_SEG - 1) {
                             const float2 ox = xs[j], oy = ys[j];
                             const float2 nox = sub2(f2(0.f), ox), noy = sub2(f2(0.f), oy);
                             wx = __fadd2_rn(wx, nox);
                             wy = __fadd2_rn(wy, noy);
+#if JDS_SSIM_SPLIT_Q
+                            wq = __ffma2_rn(nox, ox, wq);
+                            wq2 = __ffma2_rn(noy, oy, wq2);
+#else
                             wq = __ffma2_rn(nox, ox, __ffma2_rn(noy, oy, wq));
+#endif
                             wc = __ffma2_rn(nox, oy, wc);
                         }
                     }
@@ -319,7 +378,7 @@ k_ssim_strip(int H, int W, int seg_rows, const uint8_t* __restrict__ a_img, size
 
         // ---- pass 2: vertical sliding sum + SSIM; then prep of the next chunk -------------
         {
-            if (pair == 1) {
+            if (pair == 1 && (JDS_SSIM_REBUILD_EVERY == 1 || (c % JDS_SSIM_REBUILD_EVERY) == 0)) {
                 // rebuild the accumulators from the ring: the Y sums are not integers and
                 // must not drift down the strip (warp-uniform branch)
                 acc.sx = acc.sy = acc.sq = acc.sc = f2(0.f);
@@ -421,14 +480,35 @@ cudaError_t launch_ssim_strip(int H, int W, const uint8_t* a, size_t a_stride, c
         }
     }
     const int strips = (W + S_OW - 1) / S_OW;
-    // vertical segments: enough CTAs to fill the machine (3 per SM x ~3 waves), but at
-    // least 126 rows each so the 6-row overlap stays below 5 %
-    int want_ctas = sm_count * 12;
-    int segs = (want_ctas + strips * units - 1) / (strips * units);
-    if (segs < 1) segs = 1;
-    int seg_rows = (H + segs - 1) / segs;
-    if (seg_rows < 126) seg_rows = 126;
-    seg_rows = (seg_rows + S_R - 1) / S_R * S_R;
+    // Vertical segments per strip.  More segments = more CTAs to balance over the 4 x sm_count
+    // resident slots, but every segment re-reads 6 rows and pays a fixed prologue; fewer = a
+    // long ragged tail.  At least 126 rows per segment.
+    int segs, seg_rows;
+    auto rows_for = [&](int n) { return ((H + n - 1) / n + S_R - 1) / S_R * S_R; };
+#if JDS_SSIM_CTAS_PER_SM > 0
+    {
+        const int want_ctas = sm_count * JDS_SSIM_CTAS_PER_SM;
+        segs = (want_ctas + strips * units - 1) / (strips * units);
+        if (segs < 1) segs = 1;
+        seg_rows = rows_for(segs);
+        if (seg_rows < 126) seg_rows = 126;
+    }
+#else
+    {
+        // time ~ work x (1 + c / r) / slots + (r + c) / 2  (r rows per segment, c ~ 28 row-times of
+        // overlap + prologue per CTA, last term = average ragged tail) is flat around
+        // r* = sqrt(2 c x work / slots); take the segment count just below it (measured on
+        // 16 x 4K: 4 segments 1.40 ms, 2 segments 1.44 ms, 3 segments 1.43 ms)
+        const double slots = 4.0 * sm_count;
+        const double work = (double)strips * units * H;
+        double r_opt = sqrt(2.0 * 28.0 * work / slots);
+        if (r_opt < 126.0) r_opt = 126.0;
+        segs = (int)((double)H / r_opt);
+        if (segs < 1) segs = 1;
+        seg_rows = rows_for(segs);
+        if (seg_rows < 126) seg_rows = 126;
+    }
+#endif
     segs = (H + seg_rows - 1) / seg_rows;
     dim3 grid(strips, segs, units);
     k_ssim_strip<<<grid, S_NT, smem, s>>>(H, W, seg_rows, a, a_stride, b, b_stride, metrics,

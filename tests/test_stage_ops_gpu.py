@@ -124,3 +124,21 @@ def test_estimate_bitrate_no_entropy(oracle):
     nz = q64[q64 != 0]
     bits = 2 * 4 + 6 * nz.size + int(np.sum(np.ceil(np.log2(np.abs(nz) + 1)) + 1)) if nz.size else 2 * 4
     assert got['estimated_bits'] == bits
+
+
+@pytest.mark.parametrize("lo,hi", [(0, 6), (250, 256), (0, 2), (126, 131), (0, 256)])
+def test_ssim_accuracy_far_from_mid_grey(lo, hi):
+    """fp32 window sums are centred at 128: on flat content near black / white the covariance
+    and variance terms are small differences of ~4e7-sized products.  The compensated formula
+    (jds_ssim.cu) keeps the integer channels exact (was 1.6e-5 on a dark frame) and Y within
+    the 1e-5 tolerance."""
+    from jpeg_dsp_studio_b200.utils.metrics import compute_psnr_ssim
+    from oracle import numpy_port as P
+    rng = np.random.default_rng(lo * 1000 + hi)
+    a = rng.integers(lo, hi, (272, 480, 3), dtype=np.uint8)
+    b = np.clip(a.astype(np.int16) + rng.integers(-1, 2, a.shape), 0, 255).astype(np.uint8)
+    g, o = compute_psnr_ssim(a, b), P.psnr_ssim(a, b)
+    assert abs(g["ssim_rgb"] - o["ssim_rgb"]) <= 1e-6
+    assert abs(g["ssim_y"] - o["ssim_y"]) <= 1e-5
+    assert g["psnr_rgb"] == o["psnr_rgb"]
+    assert abs(g["psnr_y"] - o["psnr_y"]) <= 1e-9
