@@ -25,6 +25,7 @@
 #include <math.h>
 #include <stdint.h>
 #include "jds_kernels.cuh"
+#include "jds_ssim_formula.cuh"
 
 // tuning knobs (defaults = the measured best; tools/ssim_variants.sh builds the others)
 #ifndef JDS_SSIM_REBUILD_EVERY
@@ -119,58 +120,10 @@ __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b
 __device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
 __device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __ffma2_rn(b, f2(-1.0f), a); }
 
-// 0.5 * SSIM of one window for both channels of a pair, added to `ssum`, from the centred
-// sums over its 49 samples:  S = (2 ux uy + C1)(2 vxy + C2) / ((ux^2 + uy^2 + C1)(vx + vy + C2)),
-// v = 49/48 (E[ab]-E[a]E[b]), written on the raw sums (N = 49, Ux = N ux):
-//   S = 2 A1 A2 / (B1 B2),  A1 = 2 Ux Uy + C1 N^2,  B1 = Ux^2 + Uy^2 + C1 N^2,
-//   A2 = N Sxy - Sx Sy + C2 N (N-1) / 2,  B2 = N Sq - Sx^2 - Sy^2 + C2 N (N-1)
-// A2 and B2 are formed NEGATED (packed f32x2 has no operand negation, so every subtraction
-// would cost an instruction): (-A2)(-B2)^-1 has the same value, the constants carry the signs,
-// and the last product is fused into the accumulation.  Ux / Uy stay explicit: they are exact
-// small integers on dark content, where an expanded form cancels catastrophically.
-//
-// Cancellation.  On flat content far from mid-grey Sx Sy ~ N Sxy ~ 4e7 while their difference
-// is a few hundred: formed naively in fp32 (ulp 4 at 4e7) the covariance term is off by up to
-// 5e-5 of C2 N (N-1) / 2 with a systematic sign, which showed as 1.6e-5 in the mean SSIM of a
-// dark frame (tolerance 1e-5).  The compensated form below is exact for the integer channels:
-//   p  = RN(Sx Sy),  e = Sx Sy - p            (one FMA: the exact rounding error)
-//   N Sxy - p                                 (one FMA: the exact value is small, so no rounding)
-//   A2 = (N Sxy - p) - e + C2 N (N-1) / 2
-//   B2 = 2 A2 + D,   D = N Sum (x-y)^2 - (Sum (x-y))^2 = N (Sq - 2 Sxy) - (Sx - Sy)^2
-// (vx + vy = 2 vxy + var(x - y); the constants match because C2 N (N-1) = 2 * C2 N (N-1) / 2);
-// D involves only the DIFFERENCE of the images, which is small whenever SSIM matters.
-// B1 reuses the squared difference: Ux^2 + Uy^2 = 2 Ux Uy + (Ux - Uy)^2.
-// 19 packed instructions and two MUFU.RCP per window pair (14 for the naive form).
-#ifndef JDS_SSIM_COMPENSATED
-#define JDS_SSIM_COMPENSATED 1
-#endif
+// the per-window formula lives in jds_ssim_formula.cuh (shared with the CPU emulation)
 __device__ __forceinline__ float2 ssim_window_half2_acc(float2 sx, float2 sy, float2 sq, float2 sc,
                                                         float2 ssum) {
-    constexpr float N = 49.0f;
-    constexpr float C1N2 = 6.5025f * 2401.0f;
-    constexpr float K2 = 58.5225f * 49.0f * 48.0f;
-    const float2 Ux = __fadd2_rn(sx, f2(128.0f * N)), Uy = __fadd2_rn(sy, f2(128.0f * N));
-    const float2 A1 = __ffma2_rn(__fmul2_rn(Ux, Uy), f2(2.0f), f2(C1N2));
-#if JDS_SSIM_COMPENSATED
-    const float2 nsx = __fmul2_rn(sx, f2(-1.0f));
-    const float2 p = __fmul2_rn(sx, sy);
-    const float2 en = __ffma2_rn(nsx, sy, p);                        // p - Sx Sy, exact
-    const float2 c1n = __fadd2_rn(__ffma2_rn(sc, f2(-N), p), f2(-0.5f * K2));   // p - N Sxy - K2/2
-    const float2 A2n = __ffma2_rn(en, f2(-1.0f), c1n);               // -(N Sxy - Sx Sy + K2/2)
-    const float2 sdn = __fadd2_rn(nsx, sy);                          // Sy - Sx = Uy - Ux
-    const float2 sd2 = __fmul2_rn(sdn, sdn);
-    const float2 B1 = __fadd2_rn(A1, sd2);                           // Ux^2 + Uy^2 = 2 Ux Uy + (Ux - Uy)^2
-    const float2 sdd = __ffma2_rn(sc, f2(-2.0f), sq);                // Sum (x-y)^2
-    const float2 Dn = __ffma2_rn(sdd, f2(-N), sd2);                  // -D
-    const float2 B2n = __ffma2_rn(A2n, f2(2.0f), Dn);
-#else
-    const float2 B1 = __ffma2_rn(Ux, Ux, __ffma2_rn(Uy, Uy, f2(C1N2)));
-    const float2 A2n = __ffma2_rn(sc, f2(-N), __ffma2_rn(sx, sy, f2(-0.5f * K2)));
-    const float2 un = __ffma2_rn(sx, sx, __ffma2_rn(sy, sy, f2(-K2)));
-    const float2 B2n = __ffma2_rn(sq, f2(-N), un);
-#endif
-    const float2 num = __fmul2_rn(A1, A2n), den = __fmul2_rn(B1, B2n);
-    return __ffma2_rn(num, f2(rcp_approx(den.x), rcp_approx(den.y)), ssum);
+    return ssim_window_half_acc<Pair2>(sx, sy, sq, sc, ssum);
 }
 
 __global__ void __launch_bounds__(S_NT, 4)

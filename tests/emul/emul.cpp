@@ -192,3 +192,17 @@ extern "C" void emul_alias_luma_diff(size_t n_px, const uint8_t* a, const uint8_
         for (int k = 0; k < 3; ++k) diff[3 * i + k] = alias_diff_u8(a[3 * i + k], b[3 * i + k]);
     }
 }
+
+// ---- SSIM window formula of k_ssim_strip (jds_ssim_formula.cuh) ---------------------------
+#include "../../jpeg_dsp_studio_b200/csrc/jds_ssim_formula.cuh"
+
+// n windows; sums are the centred (x - 128) fp32 window sums the kernel forms; out = SSIM
+extern "C" void emul_ssim_strip_formula(int n, const float* sx, const float* sy, const float* sq,
+                                        const float* sc, float* out) {
+    for (int i = 0; i < n; ++i) {
+        const Pair2::V r = ssim_window_half_acc<Pair2>(Pair2::splat(sx[i]), Pair2::splat(sy[i]),
+                                                       Pair2::splat(sq[i]), Pair2::splat(sc[i]),
+                                                       Pair2::splat(0.0f));
+        out[i] = 2.0f * r.x;
+    }
+}
