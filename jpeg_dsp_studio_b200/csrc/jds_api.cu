@@ -823,7 +823,7 @@ extern "C" int jds_sweep_records(jds_ctx* c, const jds_params* p, const int32_t*
     if (n_q == 0) {
         // a rank that owns no point still contributes `capacity` empty rows
         JDS_CUDA(cudaSetDevice(c->device));
-        RecordQualities rq;
+        RecordQualities rq = {};
         k_pack_records<<<(capacity + 127) / 128, 128, 0, c->stream>>>(nullptr, 0, capacity, unit0, unit_step,
                                                                       rq, 0.0, 0.0, 0.0, records);
         JDS_CUDA(cudaGetLastError());

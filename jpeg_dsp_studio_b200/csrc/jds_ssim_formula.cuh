@@ -12,7 +12,7 @@
 
 namespace jds {
 
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)      // nvcc, both passes: the packed device flavour
 struct Pair2 {
     typedef float2 V;
     static __device__ __forceinline__ V splat(float a) { return make_float2(a, a); }
@@ -26,7 +26,7 @@ struct Pair2 {
         return r;
     }
 };
-#else
+#else                        // plain C++ (tests/emul)
 struct HostPair {
     float x, y;
 };
@@ -62,8 +62,13 @@ struct Pair2 {
 // D involves only the DIFFERENCE of the images, which is small whenever SSIM matters.
 // B1 reuses the squared difference: Ux^2 + Uy^2 = 2 Ux Uy + (Ux - Uy)^2.
 // 19 packed instructions and two MUFU.RCP per window pair (14 for the naive form).
+#if defined(__CUDACC__)
+#define JDS_FORMULA_FN __device__ __forceinline__
+#else
+#define JDS_FORMULA_FN inline
+#endif
 template <class P>
-JDS_HD typename P::V ssim_window_half_acc(typename P::V sx, typename P::V sy, typename P::V sq,
+JDS_FORMULA_FN typename P::V ssim_window_half_acc(typename P::V sx, typename P::V sy, typename P::V sq,
                                           typename P::V sc, typename P::V ssum) {
     typedef typename P::V V;
     constexpr float N = 49.0f;
