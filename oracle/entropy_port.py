@@ -249,3 +249,67 @@ def encode_jfif(coeffs, shape, mode, qtable):
         scan_bits.append(nbits)
     out += b"\xFF\xD9"
     return bytes(out), scan_bits
+
+
+# ---------------------------------------------------------------------------
+# decoder (round-trip check of the coder above; libjpeg is the independent check)
+# ---------------------------------------------------------------------------
+def decode_scan(data, n_blocks, table_id):
+    """Inverse of ``_encode_scan``: entropy-coded bytes of one scan -> (n_blocks, 64) raster
+    coefficients.  Removes the 0xFF00 stuffing, walks the canonical codes bit by bit."""
+    raw = bytearray()
+    i = 0
+    while i < len(data):
+        raw.append(data[i])
+        if data[i] == 0xFF:
+            assert data[i + 1] == 0x00, "marker inside entropy-coded data"
+            i += 1
+        i += 1
+    bits = np.unpackbits(np.frombuffer(bytes(raw), dtype=np.uint8))
+    pos = 0
+
+    def lookup(kind):
+        code, length = CODES[(kind, table_id)]
+        table = {(int(length[s]), int(code[s])): s for s in range(256) if length[s]}
+        return table
+
+    dc_t, ac_t = lookup("dc"), lookup("ac")
+
+    def symbol(table):
+        nonlocal pos
+        c = 0
+        for ln in range(1, 17):
+            c = (c << 1) | int(bits[pos])
+            pos += 1
+            if (ln, c) in table:
+                return table[(ln, c)]
+        raise ValueError("invalid Huffman code")
+
+    def amplitude(size):
+        nonlocal pos
+        if size == 0:
+            return 0
+        v = 0
+        for _ in range(size):
+            v = (v << 1) | int(bits[pos])
+            pos += 1
+        return v if v >= (1 << (size - 1)) else v - (1 << size) + 1
+
+    out = np.zeros((n_blocks, 64), dtype=np.int64)
+    pred = 0
+    for b in range(n_blocks):
+        pred += amplitude(symbol(dc_t))
+        out[b, ZIGZAG[0]] = pred
+        k = 1
+        while k < 64:
+            s = symbol(ac_t)
+            run, size = s >> 4, s & 15
+            if size == 0:
+                if run == 15:
+                    k += 16
+                    continue
+                break                          # EOB
+            k += run
+            out[b, ZIGZAG[k]] = amplitude(size)
+            k += 1
+    return out, pos

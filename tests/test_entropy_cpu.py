@@ -85,3 +85,20 @@ def test_extreme_values_and_runs():
     assert E.component_scan_bits(blocks, 0) == int(want)
     data, nbits = E._encode_scan(blocks, 0)
     assert nbits == int(want)
+
+
+def test_coder_round_trips_its_own_bitstream():
+    """encode -> decode returns the coefficients exactly and consumes exactly the counted bits"""
+    rng = np.random.default_rng(11)
+    for table_id in (0, 1):
+        blocks = np.zeros((40, 64), dtype=np.int64)
+        dense = rng.integers(-1023, 1024, (40, 64))
+        keep = rng.random((40, 64)) < rng.choice([0.02, 0.2, 0.9], size=(40, 1))
+        blocks[keep] = dense[keep]
+        blocks[:, 0] = rng.integers(-1024, 1017, 40)
+        blocks[7] = 0
+        blocks[8, 63] = 5                                   # zig-zag tail after a long run
+        data, nbits = E._encode_scan(blocks, table_id)
+        back, used = E.decode_scan(data, 40, table_id)
+        assert np.array_equal(back, blocks)
+        assert used == nbits == E.component_scan_bits(blocks, table_id)
