@@ -292,6 +292,17 @@ def run_ours(args):
     d_in = host_in.to(dev, non_blocking=False)
     d_out = torch.empty_like(d_in)
     px_per_step = FRAMES * H * W
+    # streamed steps alternate between two contexts on two streams: the ragged last wave of one
+    # step's kernels is filled by the next step's (each context has its own scratch and output)
+    N_STREAMS = max(1, min(4, int(os.environ.get("JDS_BENCH_STREAMS", "3"))))
+    engines, streams, d_outs = [eng], [stream], [d_out]
+    for _ in range(N_STREAMS - 1):
+        s_k = torch.cuda.Stream(dev)
+        eng_k = J.Engine(local)
+        eng_k.use_stream(s_k.cuda_stream)
+        engines.append(eng_k)
+        streams.append(s_k)
+        d_outs.append(torch.empty_like(d_in))
 
     def barrier():
         if world > 1:
@@ -320,17 +331,27 @@ def run_ours(args):
         if world == 1 or REDUCE_MODE == "off":
             return
         if n:
-            dbg = int(os.environ.get("JDS_BENCH_DEBUG_ROWS", "0"))
-            dist.all_reduce(rec_all[:(dbg or n)])
+            join_streams()
+            dist.all_reduce(rec_all[:n])
             state["reduces"] += 1
         if m:
             dev_acc.copy_(host_acc, non_blocking=True)
             dist.all_reduce(dev_acc)
             state["reduces"] += 1
 
+    def join_streams():
+        """the main stream waits for the second one (before a collective / the closing event)"""
+        for s_ in streams[1:]:
+            stream.wait_stream(s_)
+
+    def fork_streams():
+        for s_ in streams[1:]:
+            s_.wait_stream(stream)
+
     def drain():
         while pending:
             pending.pop(0).wait()
+        join_streams()
         reduce_job()
         host_acc.zero_()
 
@@ -362,8 +383,9 @@ def run_ours(args):
             reduce_job()
         i = state["stream_steps"]
         state["stream_steps"] += 1
-        eng.batch_records(d_in, rec_all[i], QUALITY, MODE, PREFILTER, precision=precision,
-                          recon_out=d_out, unit0=rank, unit_step=world)
+        k = i % len(engines)
+        engines[k].batch_records(d_in, rec_all[i], QUALITY, MODE, PREFILTER, precision=precision,
+                                 recon_out=d_outs[k], unit0=rank, unit_step=world)
         if REDUCE_MODE == "step" and world > 1:
             state["stream_steps"] = 0
             pending.append(dist.all_reduce(rec_all[i], async_op=True))
@@ -396,9 +418,10 @@ def run_ours(args):
             sampler.start()
         barrier()
         eng.stage_times(reset=True) if stage_timing else None
-        l0 = eng.launch_count()
+        l0 = sum(e.launch_count() for e in engines)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
+        fork_streams()
         for _ in range(steps):
             outs = fn(precision)
         drain()
@@ -409,7 +432,7 @@ def run_ours(args):
             print(f"[debug] rank {rank} {fn.__name__} {precision}: {ms / steps:.4f} ms/step", file=sys.stderr, flush=True)
         clocks = sampler.stop() if sampler else None
         stages = eng.stage_times(reset=True) if stage_timing else None
-        launches = eng.launch_count() - l0
+        launches = sum(e.launch_count() for e in engines) - l0
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -420,6 +443,9 @@ def run_ours(args):
     ms, _, launches, clocks, last_rec = timed(step_stream, "fast", K, Wm, sample_clocks=True)
     value = world * px_per_step * K / (ms / 1e3) / 1e6
     rec_host = last_rec.cpu().numpy()               # the metrics of the last step, read once
+    if os.environ.get("JDS_BENCH_ONLY_HEADLINE"):
+        print(f"[headline] streams {N_STREAMS}: {ms / K:.4f} ms/step {value:.1f} Mpixel/s", file=sys.stderr, flush=True)
+        return None
     # the same batch through the synchronising per-call API (returns host structs every step)
     ms_sync, _, _, _, outs = timed(step_device, "fast", K, Wm)
     sync_value = world * px_per_step * K / (ms_sync / 1e3) / 1e6
@@ -511,8 +537,9 @@ def run_ours(args):
                 "api": "Engine.roundtrip_batch(pinned host uint8 frames) -> jds_roundtrip_batch (C ABI)"},
         "gpu_launches": launches,
         "value_mode": "streamed: per-step kernels and device-resident metric records enqueued without "
-                      "host synchronisation (jds_roundtrip_batch_records); one all-reduce of the job's "
-                      "records after the last step; metrics read after the timed region",
+                      "host synchronisation (jds_roundtrip_batch_records), steps alternating over "
+                      f"{N_STREAMS} context(s) / stream(s); one all-reduce of the job's records after the "
+                      "last step; metrics read after the timed region",
         "sync_api": {"value": round(sync_value, 2), "unit": "Mpixel/s", "ms_per_step": round(ms_sync / K, 4),
                      "api": "Engine.roundtrip_batch(device tensors): synchronises and returns host "
                             "metric structs every step"},
