@@ -22,9 +22,10 @@ roofline = dominant kernel vs measured HBM peak; cpu_baseline = the oracle port 
 on this box's host cores on a bounded sample; exact = the fp64 bit-exact mode on the
 same workload.
 
---impl reference: the reference algorithm on the host CPU (oracle/numpy_port.py, the
-bit-exact NumPy restatement - the reference itself is Python and needs /root/reference,
-which does not exist on the GPU box), one process per host core, same metric/config.
+--impl reference: the reference's own CPU implementation on the host cores - the unmodified
+engines/pipeline.py::compress_reconstruct staged under oracle/_ref by oracle/make_ref.py
+(kind "reference"; the bit-exact NumPy port oracle/numpy_port.py beside it, and alone with kind
+"port" when nothing is staged), one process per host core, same metric/config.
 """
 
 import argparse
@@ -196,27 +197,64 @@ def make_frames(rank, n):
 # ------------------------------------------------------------------------------------
 # CPU arms (oracle port = the checker; here only as the timed CPU baseline)
 # ------------------------------------------------------------------------------------
-def _cpu_one_frame(seed):
+def _frame(seed):
     import numpy as np
+    return np.random.default_rng(seed).integers(0, 256, (H, W, 3), dtype=np.uint8)
+
+
+def _cpu_one_frame(seed):
+    """one 4K frame through the oracle port (oracle/numpy_port.py)"""
     from oracle import numpy_port as P
-    img = np.random.default_rng(seed).integers(0, 256, (H, W, 3), dtype=np.uint8)
+    img = _frame(seed)
     t0 = time.perf_counter()
     o = P.compress_reconstruct(img, QUALITY, MODE, PREFILTER, want_maps=False)
     return time.perf_counter() - t0, o["psnr_y"]
 
 
-def cpu_baseline_sample(n_frames=2):
-    """Oracle port, one process, n_frames 4K frames (about 15-25 s)."""
-    times = [_cpu_one_frame(4000 + k)[0] for k in range(n_frames)]
-    sec = sum(times)
-    return {"value": round(n_frames * H * W / sec / 1e6, 4), "unit": "Mpixel/s", "cores": 1,
-            "kind": "port",
-            "sample": f"{n_frames} of the workload's 4K frames through oracle/numpy_port.py "
-                      f"(bit-exact NumPy restatement of the reference), 1 process, {sec:.1f} s"}
+def reference_staged():
+    """True when the unmodified reference is importable here: /root/reference in the build
+    container, oracle/_ref/reference (staged by oracle/make_ref.py) on the GPU box."""
+    try:
+        from oracle import reference_shim as R
+        return R.available()
+    except Exception:
+        return False
+
+
+def _ref_one_frame(seed):
+    """one 4K frame through the UNMODIFIED reference's engines/pipeline.py::compress_reconstruct
+    (imported by oracle/reference_shim.py with the skimage stand-in)"""
+    from oracle import reference_shim as R
+    ref = R.load()
+    img = _frame(seed)
+    params = ref.CompressionParams(quality=QUALITY, subsampling_mode=MODE, use_prefilter=PREFILTER)
+    t0 = time.perf_counter()
+    res, _ = ref.compress_reconstruct(img, params)
+    return time.perf_counter() - t0, res.psnr_y
+
+
+def cpu_baseline_sample():
+    """The CPU figure printed beside the GPU one (rank 0, N=1): the reference AS IS on one 4K
+    frame of the workload in one process (about 20-30 s; SURVEY 8d "baseline of record"), with
+    the bit-exact NumPy port on two frames beside it.  Without a staged reference the port is
+    the baseline (kind "port")."""
+    t_port = [_cpu_one_frame(4000 + k)[0] for k in range(2)]
+    port = {"value": round(2 * H * W / sum(t_port) / 1e6, 4), "unit": "Mpixel/s", "cores": 1,
+            "sample": f"2 of the workload's 4K frames through oracle/numpy_port.py, 1 process, {sum(t_port):.1f} s"}
+    if reference_staged():
+        sec, _ = _ref_one_frame(4000)
+        return {"value": round(H * W / sec / 1e6, 4), "unit": "Mpixel/s", "cores": 1, "kind": "reference",
+                "sample": f"1 of the workload's 4K frames through the unmodified reference "
+                          f"(engines/pipeline.py::compress_reconstruct, skimage stand-in), 1 Python "
+                          f"process (OpenCV's own threads as the reference leaves them), {sec:.1f} s",
+                "port": port}
+    port["kind"] = "port"
+    return port
 
 
 def run_reference(args):
-    """--impl reference: the reference algorithm on the host cores."""
+    """--impl reference: the reference's own CPU implementation on the host cores, one process
+    per core, each step = one 4K frame per process (a bounded sample of the workload)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -231,19 +269,33 @@ def run_reference(args):
     except Exception:
         avail_gb = 64.0
     procs = max(1, min(ncpu, 32, int(avail_gb // 6)))     # ~5 GB peak per 4K frame in fp64
-    steps, warmup = max(1, args.steps), max(0, args.warmup)
-    # bounded: each step = `procs` frames in parallel (one per process); cap total work
-    steps = min(steps, 3)
-    warmup = min(warmup, 1)
+    as_is = reference_staged()
+    worker = _ref_one_frame if as_is else _cpu_one_frame
+    # bounded: the reference needs 20-30 s per 4K frame (the port 5 s), so cap the steps
+    steps = min(max(1, args.steps), 2 if as_is else 3)
+    warmup = min(max(0, args.warmup), 0 if as_is else 1)
     ctx = mp.get_context("spawn")
+    os.environ.setdefault("OMP_NUM_THREADS", "1")         # one core per process: cv2 / BLAS threads off
+    os.environ.setdefault("OPENCV_FOR_THREADS_NUM", "1")
     with ctx.Pool(procs) as pool:
+        pool.map(_frame, [1] * procs)                      # start the workers (imports) untimed
         for _ in range(warmup):
-            pool.map(_cpu_one_frame, [4000 + k for k in range(procs)])
+            pool.map(worker, [4000 + k for k in range(procs)])
         t0 = time.perf_counter()
         for s in range(steps):
-            pool.map(_cpu_one_frame, [4000 + k for k in range(procs)])
+            pool.map(worker, [4000 + k for k in range(procs)])
         sec = time.perf_counter() - t0
+        port_line = None
+        if as_is:                                          # the port beside it, one step
+            t1 = time.perf_counter()
+            pool.map(_cpu_one_frame, [4000 + k for k in range(procs)])
+            sp = time.perf_counter() - t1
+            port_line = {"value": round(procs * H * W / sp / 1e6, 4), "unit": "Mpixel/s", "cores": procs,
+                         "sample": f"1 step x {procs} 4K frames, oracle/numpy_port.py, {sp:.1f} s"}
     mpx = steps * procs * H * W / sec / 1e6
+    kind = "reference" if as_is else "port"
+    what = ("the unmodified reference (engines/pipeline.py::compress_reconstruct, skimage stand-in)"
+            if as_is else "oracle/numpy_port.py (bit-exact restatement; no staged reference here)")
     line = {
         "impl": "reference", "metric": "4K round-trip Mpixel/s (incl. PSNR/SSIM/bpp)",
         "value": round(mpx, 4), "unit": "Mpixel/s", "n_gpus": args.gpus, "steps": steps,
@@ -251,9 +303,10 @@ def run_reference(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD.replace("fast fp32 mode", "reference fp64 arithmetic on host CPU"),
                    "step": f"{procs} frames, one per process"},
-        "cpu_baseline": {"value": round(mpx, 4), "unit": "Mpixel/s", "cores": procs, "kind": "port",
-                         "sample": f"{steps} steps x {procs} 4K frames, oracle/numpy_port.py in "
-                                   f"{procs} processes ({ncpu} host cores visible), {sec:.1f} s"},
+        "cpu_baseline": {"value": round(mpx, 4), "unit": "Mpixel/s", "cores": procs, "kind": kind,
+                         "sample": f"{steps} steps x {procs} 4K frames, {what} in "
+                                   f"{procs} processes ({ncpu} host cores visible), {sec:.1f} s",
+                         "port": port_line},
         "e2e": {"value": round(mpx, 4), "unit": "Mpixel/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }
@@ -465,6 +518,25 @@ def run_ours(args):
     ms_x, stages_x, _, _, outs_x = timed(step_device, "exact", Kx, 1, stage_timing=True)
     eng.set_stage_timing(False)
     exact_value = world * px_per_step * Kx / (ms_x / 1e3) / 1e6
+    # the bit-exact mode through the same host->host call (H2D + D2H inside the timed region)
+    ms_xe, _, _, _, _ = timed(step_host, "exact", Kx, 1)
+    exact_e2e = world * px_per_step * Kx / (ms_xe / 1e3) / 1e6
+
+    # north_star: the fp32 mode "must report its round-half mismatch rate" - frame 0 of this
+    # rank's batch, fast against exact: quantised coefficients (round-half decisions) and pixels
+    fa = eng.roundtrip(d_in[0], QUALITY, MODE, PREFILTER, precision="fast", want_coeffs=True)
+    xa = eng.roundtrip(d_in[0], QUALITY, MODE, PREFILTER, precision="exact", want_coeffs=True)
+    mismatch = {"coeff": float((fa.coeffs != xa.coeffs).double().mean().item()),
+                "pixel": float((fa.recon != xa.recon).double().mean().item()),
+                "d_psnr_y_db": abs(fa.scalars["psnr_y"] - xa.scalars["psnr_y"]),
+                "d_ssim_y": abs(fa.scalars["ssim_y"] - xa.scalars["ssim_y"]),
+                "d_ssim_rgb": abs(fa.scalars["ssim_rgb"] - xa.scalars["ssim_rgb"]),
+                "frame": "frame 0 of rank 0's batch, fast vs exact mode (exact = bit-identical to the reference)"}
+    del fa, xa
+
+    # BASELINE config 4 inside the same launch: the 100-point sweep, points sharded over the
+    # ranks (strong scaling) - SCALE_rNN.json then carries north_star's ">= 7x on 8 GPUs"
+    sweep_rec = measure_sweep(eng, dev, stream, world, rank, max(3, min(K, 10)), 3)
 
     # uniform-random RGB is the worst case for coefficient density; also report a
     # natural-statistics input (generate_photo(512) tiled to 4K, each frame shifted) at N=1
@@ -509,15 +581,23 @@ def run_ours(args):
     # to the pixels of one launch here); null when no capture exists for that kernel
     traffic, traffic_src = None, None
     kmap = {"ssim": "k_ssim_strip", "block_codec": "k_fast_luma", "forward_colour": "k_fast_chroma"}
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        per_px = tj[kmap[dom]]["dram_bytes_per_pixel"]
-        traffic = round(per_px * px_per_step / launches_per_step, 0)
-        traffic_src = tj["source"]
-    except Exception:
-        pass
+    path_traffic = None
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", name)))
+            per_px = tj[kmap[dom]]["dram_bytes_per_pixel"]
+            traffic = round(per_px * px_per_step / launches_per_step, 0)
+            traffic_src = tj["source"]
+            wp = tj.get("whole_path")
+            if wp:
+                path_traffic = {"bytes_per_step": round(wp["dram_bytes_per_pixel"] * px_per_step, 0),
+                                "dram_bytes_per_pixel": wp["dram_bytes_per_pixel"],
+                                "algorithmic_bytes_per_pixel": BYTES_PER_PX, "source": wp.get("source")}
+            break
+        except Exception:
+            continue
     # the CPU baseline is timed on rank 0 at N=1 only (it takes ~15 s of host time)
-    cpu = cpu_baseline_sample(2) if world == 1 else None
+    cpu = cpu_baseline_sample() if world == 1 else None
     o0 = outs[0]
     line = {
         "metric": "4K round-trip Mpixel/s (incl. PSNR/SSIM/bpp)",
@@ -553,11 +633,19 @@ def run_ours(args):
                      "whole_path": {"kernel_ms_per_step": round(kern_ms_step, 4),
                                     "achieved": round(path_gbs, 1),
                                     "frac": round(path_gbs / peak, 4),
+                                    "traffic": path_traffic,
                                     "stages_ms_per_step": {k: round(v["ms"] / Kp, 4) for k, v in stages.items()}}},
         "cpu_baseline": cpu,
         "natural_statistics": natural,
+        "fast_mode_mismatch": mismatch,
+        "sweep": sweep_rec,
         "exact_mode": {"value": round(exact_value, 2), "unit": "Mpixel/s", "dtype": "f64",
                        "ms_per_step": round(ms_x / Kx, 4), "steps": Kx,
+                       "e2e": {"value": round(exact_e2e, 2), "unit": "Mpixel/s",
+                               "ms_per_step": round(ms_xe / Kx, 4),
+                               "h2d_bytes_per_step": FRAMES * H * W * 3,
+                               "d2h_bytes_per_step": FRAMES * H * W * 3 + FRAMES * 504,
+                               "api": "Engine.roundtrip_batch(pinned host frames, precision='exact')"},
                        "hbm_frac_whole_path": round(alg_bytes_step / (kern_ms_step_x / 1e3) / 1e9 / peak, 4),
                        "stages_ms_per_step": {k: round(v["ms"] / Kx, 4) for k, v in stages_x.items()}},
         "results_frame0": {"psnr_y": o0.scalars["psnr_y"], "ssim_y": o0.scalars["ssim_y"],
@@ -570,28 +658,20 @@ def run_ours(args):
     return line
 
 
-def run_sweep(args):
-    """--workload sweep: BASELINE.json config 4 - a 100-point quality sweep (Q=1..100) of one
-    4K frame, 4:2:0, points sharded round-robin over the ranks (STRONG scaling: total work
-    fixed), one all_gather of the metric records per sweep.  value = sweep points x pixels
-    per second, whole job."""
+def measure_sweep(eng, dev, stream, world, rank, K, Wm):
+    """BASELINE.json config 4: a 100-point quality sweep (Q=1..100) of one 4K frame, 4:2:0,
+    fast mode, metrics only, points dealt round-robin to the ranks (STRONG scaling), one
+    all_gather of the device-resident records per sweep.  Three figures, each the max over ranks:
+      single_sweep    K sweeps strictly one after the other, CUDA events around the whole loop
+                      (host finalisation of every table inside): the latency a GUI sweep sees
+      single_device   the same sweeps, but each one's own CUDA-event span (first kernel ->
+                      records gathered and copied to the host) summed: the device time of a sweep
+      pipelined       consecutive sweeps overlapped (a folder of frames)
+    Returns the record on rank 0, None elsewhere."""
     import numpy as np
     import torch
     import torch.distributed as dist
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    os.environ.setdefault("JDS_SCRATCH_MB", "8192")
-    import jpeg_dsp_studio_b200 as J
     from jpeg_dsp_studio_b200 import distributed as D
-    eng = J.Engine(local)
-    stream = torch.cuda.current_stream(dev)
-    eng.use_stream(stream.cuda_stream)
     img = np.random.default_rng(4).integers(0, 256, (H, W, 3), dtype=np.uint8)
     d_img = torch.from_numpy(img).to(dev)
     qs = list(range(1, 101))
@@ -601,8 +681,16 @@ def run_sweep(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    dev_spans = []
+
     def step():
-        return D.sweep_sharded(eng, d_img, qs, MODE, PREFILTER, precision="fast", device=dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        h = D.sweep_sharded_begin(eng, d_img, qs, MODE, PREFILTER, precision="fast", device=dev)
+        b.record(stream)
+        table = h.result()
+        dev_spans.append((a, b))
+        return table
 
     def timed(run_steps, K):
         barrier()
@@ -633,39 +721,238 @@ def run_sweep(args):
             prev = h
         return prev.result()
 
-    K, Wm = args.steps, max(args.warmup, 3)
     one_at_a_time(Wm)
     pipelined(Wm)
+    dev_spans.clear()
     l0 = eng.launch_count()
     ms_lat, table_lat = timed(one_at_a_time, K)
     launches = eng.launch_count() - l0
+    t = torch.tensor([sum(a.elapsed_time(b) for a, b in dev_spans)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev = float(t.item())
     ms, table = timed(pipelined, K)
     for a, b in zip(table, table_lat):      # same table either way (SSIM sums: atomic order only)
         assert a["estimated_bits"] == b["estimated_bits"] and a["psnr_rgb"] == b["psnr_rgb"]
         assert abs(a["ssim_y"] - b["ssim_y"]) < 1e-9
+    del d_img
+    if rank != 0:
+        return None
+    px = len(qs) * H * W
+    return {
+        "workload": "100-point quality sweep Q=1..100 of one random 4K frame, 4:2:0, fast fp32 mode, "
+                    "metrics only (BASELINE config 4)",
+        "scaling": "strong", "n_gpus": world, "points": len(qs), "sweeps_timed": K,
+        "sharding": "sweep points round-robin over ranks; one all_gather of the device-resident "
+                    "records per sweep",
+        "single_sweep": {"ms_per_sweep": round(ms_lat / K, 4),
+                         "value": round(px * K / (ms_lat / 1e3) / 1e6, 2), "unit": "Mpixel/s",
+                         "note": "one sweep at a time: enqueue, all_gather, D2H, synchronise, finalise "
+                                 "the table on the host, then the next (latency of one GUI sweep)"},
+        "single_device": {"ms_per_sweep": round(ms_dev / K, 4),
+                          "value": round(px * K / (ms_dev / 1e3) / 1e6, 2), "unit": "Mpixel/s",
+                          "note": "the same isolated sweeps, each timed by its own CUDA-event pair on the "
+                                  "stream (kernels + all_gather + D2H of the records), host work excluded"},
+        "pipelined": {"ms_per_sweep": round(ms / K, 4), "value": round(px * K / (ms / 1e3) / 1e6, 2),
+                      "unit": "Mpixel/s",
+                      "note": "consecutive sweeps pipelined (one in flight while the previous table is finalised)"},
+        "gpu_launches": launches,
+        "rd_table_sample": {"q10": table[9], "q50": table[49], "q90": table[89]},
+    }
+
+
+def run_sweep(args):
+    """--workload sweep: config 4 on its own (see measure_sweep); value = the pipelined figure."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    os.environ.setdefault("JDS_SCRATCH_MB", "8192")
+    import jpeg_dsp_studio_b200 as J
+    eng = J.Engine(local)
+    stream = torch.cuda.current_stream(dev)
+    eng.use_stream(stream.cuda_stream)
+    K, Wm = args.steps, max(args.warmup, 3)
+    rec = measure_sweep(eng, dev, stream, world, rank, K, Wm)
+    line = None
     if rank == 0:
-        px = len(qs) * H * W
         line = {
-            "metric": "4K round-trip Mpixel/s (incl. PSNR/SSIM/bpp)", "value": round(px * K / (ms / 1e3) / 1e6, 2),
-            "unit": "Mpixel/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": round(ms / K, 4),
+            "metric": "4K round-trip Mpixel/s (incl. PSNR/SSIM/bpp)", "value": rec["pipelined"]["value"],
+            "unit": "Mpixel/s", "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": rec["pipelined"]["ms_per_sweep"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "100-point quality sweep Q=1..100 of one random 4K frame, 4:2:0, "
-                                   "fast fp32 mode, metrics only (BASELINE config 4)",
-                       "sharding": "sweep points round-robin over ranks; one all_gather of the "
-                                   "device-resident records per sweep",
-                       "pipelining": "value: consecutive sweeps pipelined (one in flight while the "
-                                     "previous table is finalised); single_sweep: strictly one at a time"},
-            "gpu_launches": launches,
-            "single_sweep": {"ms_per_sweep": round(ms_lat / K, 4),
-                             "value": round(px * K / (ms_lat / 1e3) / 1e6, 2), "unit": "Mpixel/s",
-                             "note": "one sweep at a time: enqueue, all_gather, D2H, synchronise, "
-                                     "finalise the table, then the next (latency of one GUI sweep)"},
-            "rd_table_sample": {"q10": table[9], "q50": table[49], "q90": table[89]},
+            "config": {"workload": rec["workload"], "sharding": rec["sharding"],
+                       "pipelining": "value: consecutive sweeps pipelined; single_sweep: strictly one at a time"},
+            "gpu_launches": rec["gpu_launches"],
+            "single_sweep": rec["single_sweep"], "single_device": rec["single_device"],
+            "rd_table_sample": rec["rd_table_sample"],
         }
     if world > 1:
         dist.destroy_process_group()
-    return line if rank == 0 else None
+    return line
+
+
+def run_configs(args):
+    """--workload configs: the other BASELINE.json configurations on this GPU / these GPUs, each
+    with its throughput, its fraction of the HBM roofline (algorithmic bytes of THAT config,
+    optional outputs included) and a CPU figure beside it:
+      cfg2  1920x1080 random, Q=50, 4:4:4 (k_fast_444)
+      cfg3  3840x2160 random, Q=75, 4:2:0 + prefilter, with coefficients + histogram + error map
+      cfg5  1024 x 1080p, Q=30, 4:2:2, frames sharded over the ranks (aggregate + GB/s per GPU)
+    Inputs cycle through more distinct frames than fit the 126 MB L2."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    os.environ.setdefault("JDS_SCRATCH_MB", "8192")
+    import jpeg_dsp_studio_b200 as J
+    from jpeg_dsp_studio_b200 import _native as NAT
+    eng = J.Engine(local)
+    stream = torch.cuda.current_stream(dev)
+    eng.use_stream(stream.cuda_stream)
+    peak, peak_src = measured_peak()
+    K = max(3, min(args.steps, 20))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, n, warm=2):
+        for i in range(warm):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(n):
+            fn(i)
+        e1.record(stream)
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / n
+
+    def rec(ms, px, bytes_px, note, **extra):
+        gbs = bytes_px * px / (ms / 1e3) / 1e9
+        out = {"ms": round(ms, 4), "value": round(px / (ms / 1e3) / 1e6, 2), "unit": "Mpixel/s",
+               "algorithmic_bytes_per_pixel": bytes_px, "achieved_gbs": round(gbs, 1),
+               "hbm_frac": round(gbs / peak, 4), "note": note}
+        out.update(extra)
+        return out
+
+    def cpu_figure(h, w, seed, q, mode, pf):
+        """the oracle port (and the staged reference, if any) on ONE frame of the config"""
+        from oracle import numpy_port as P
+        img = np.random.default_rng(seed).integers(0, 256, (h, w, 3), dtype=np.uint8)
+        t0 = time.perf_counter()
+        P.compress_reconstruct(img, q, mode, pf, want_maps=True)
+        tp = time.perf_counter() - t0
+        out = {"port_mpixel_s": round(h * w / tp / 1e6, 4), "cores": 1}
+        if reference_staged():
+            from oracle import reference_shim as R
+            ref = R.load()
+            t0 = time.perf_counter()
+            ref.compress_reconstruct(img, ref.CompressionParams(quality=q, subsampling_mode=mode, use_prefilter=pf))
+            out["reference_mpixel_s"] = round(h * w / (time.perf_counter() - t0) / 1e6, 4)
+        return out
+
+    results = {}
+    # ---- cfg2: 1080p 4:4:4, batches of 32 distinct frames (199 MB in + 199 MB out > L2) ----
+    h2, w2, n2 = 1080, 1920, 32
+    f2 = torch.from_numpy(np.stack([np.random.default_rng(2 + 7 * k).integers(0, 256, (h2, w2, 3), dtype=np.uint8)
+                                    for k in range(n2)])).to(dev)
+    o2 = torch.empty_like(f2)
+    r2 = torch.zeros((n2, NAT.JDS_RECORD_FIELDS), dtype=torch.float64, device=dev)
+    cfg2 = {}
+    for prec in ("fast", "exact"):
+        ms = timed(lambda i: eng.batch_records(f2, r2, 50, "4:4:4", False, precision=prec, recon_out=o2), K if prec == "fast" else 3)
+        cfg2[prec] = rec(ms, n2 * h2 * w2, 6.0, f"{n2} frames per call, device resident, recon + PSNR/SSIM/bpp")
+    one = eng.roundtrip(f2[0], 50, "4:4:4", False, precision="fast")
+    cfg2["results_frame0"] = {k: one.scalars[k] for k in ("psnr_y", "ssim_y", "bpp")}
+    del f2, o2
+    results["cfg2_1080p_q50_444"] = cfg2
+
+    # ---- cfg3: 4K Q75 4:2:0 + prefilter, GUI outputs; 8 distinct frames cycle (199 MB > L2) ----
+    f3 = torch.from_numpy(np.stack([np.random.default_rng(3 + 11 * k).integers(0, 256, (H, W, 3), dtype=np.uint8)
+                                    for k in range(8)])).to(dev)
+    px3 = H * W
+    cfg3 = {}
+    for prec in ("fast", "exact"):
+        n = K if prec == "fast" else 3
+        ms = timed(lambda i: eng.roundtrip(f3[i % 8], 75, "4:2:0", True, precision=prec), n)
+        cfg3[f"{prec}_recon_only"] = rec(ms, px3, 6.0, "per-call API (synchronises), recon + metrics")
+        ms = timed(lambda i: eng.roundtrip(f3[i % 8], 75, "4:2:0", True, precision=prec, want_coeffs=True, want_hist=True), n)
+        cfg3[f"{prec}_coeffs_hist"] = rec(ms, px3, 9.0, "recon + int16 coefficients (3 B/px) + 50-bin histogram")
+        ms = timed(lambda i: eng.roundtrip(f3[i % 8], 75, "4:2:0", True, precision=prec, want_coeffs=True, want_hist=True,
+                                           want_error_maps=True), n)
+        cfg3[f"{prec}_all_intermediates"] = rec(ms, px3, 25.0, "recon + coefficients + histogram + both fp64 error maps "
+                                                "(8 B/px each): what IntermediateData holds")
+        ms = timed(lambda i: eng.plot_payload(f3[i % 8], 75, "4:2:0", True, precision=prec), n)
+        cfg3[f"{prec}_plot_payload"] = rec(ms, px3, 10.0, "recon + uint8 error heat map (1 B/px) + per-value coefficient "
+                                           "counts: what the GUI plots draw (coefficients stay on the device, 3 B/px)")
+    ms = timed(lambda i: eng.selected_block(f3[i % 8], 75, 0, 0), K)
+    cfg3["selected_block_dct_ms"] = round(ms, 4)
+    del f3
+    results["cfg3_4k_q75_420_pf"] = cfg3
+
+    # ---- cfg5: 1024 x 1080p Q30 4:2:2 sharded by frame; 64 distinct frames per rank, tiled ----
+    total5 = 1024
+    mine = len(range(rank, total5, world))
+    base = torch.from_numpy(np.stack([np.random.default_rng(5000 + rank + world * k).integers(0, 256, (h2, w2, 3), dtype=np.uint8)
+                                      for k in range(64)])).to(dev)
+    per_call = 64
+    o5 = torch.empty_like(base)
+    r5 = torch.zeros((per_call, NAT.JDS_RECORD_FIELDS), dtype=torch.float64, device=dev)
+    calls = (mine + per_call - 1) // per_call
+
+    def job(i):
+        for c in range(calls):
+            n = min(per_call, mine - c * per_call)
+            eng.batch_records(base[:n], r5[:n], 30, "4:2:2", False, precision="fast", recon_out=o5[:n],
+                              unit0=rank, unit_step=world)
+        if world > 1:
+            dist.all_reduce(r5)              # the job's one metric exchange
+    ms5 = timed(job, 3, warm=1)
+    px5 = total5 * h2 * w2
+    cfg5 = rec(ms5, px5, 6.0, f"{total5} frames over {world} GPU(s): {mine} per rank in calls of {per_call} "
+               "(64 distinct frames per rank, re-used: 398 MB in + 398 MB out per call > L2), device resident, "
+               "one all-reduce of the records per job")
+    cfg5["gbs_per_gpu"] = round(6.0 * px5 / world / (ms5 / 1e3) / 1e9, 1)
+    cfg5["hbm_frac_per_gpu"] = round(cfg5["gbs_per_gpu"] / peak, 4)
+    cfg5["hbm_frac"] = cfg5["hbm_frac_per_gpu"]
+    del base, o5
+    results["cfg5_1024x1080p_q30_422"] = cfg5
+
+    line = None
+    if rank == 0:
+        if world == 1:
+            results["cfg2_1080p_q50_444"]["cpu"] = cpu_figure(h2, w2, 2, 50, "4:4:4", False)
+            results["cfg3_4k_q75_420_pf"]["cpu"] = cpu_figure(H, W, 3, 75, "4:2:0", True)
+            results["cfg5_1024x1080p_q30_422"]["cpu"] = cpu_figure(h2, w2, 5000, 30, "4:2:2", False)
+        line = {"metric": "Mpixel/s of the other BASELINE configs (round trip incl. PSNR/SSIM/bpp)",
+                "value": results["cfg5_1024x1080p_q30_422"]["value"], "unit": "Mpixel/s", "n_gpus": world,
+                "steps": K, "warmup": 2, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "peak_gbs": peak, "peak_source": peak_src,
+                "config": {"workload": "BASELINE configs 2, 3, 5; value = cfg5 aggregate"},
+                "configs": results}
+    if world > 1:
+        dist.destroy_process_group()
+    return line
 
 
 def main():
@@ -674,15 +961,16 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="batch", choices=["batch", "sweep"],
-                    help="batch = the headline (8 x 4K frames per GPU, weak scaling); "
-                         "sweep = BASELINE config 4 (100-point sweep, strong scaling)")
+    ap.add_argument("--workload", default="batch", choices=["batch", "sweep", "configs"],
+                    help="batch = the headline (16 x 4K frames per GPU, weak scaling; carries the sweep "
+                         "sub-record); sweep = BASELINE config 4 alone (100-point sweep, strong "
+                         "scaling); configs = BASELINE configs 2, 3 and 5")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
         return
     with StdoutToStderr():
-        line = run_sweep(args) if args.workload == "sweep" else run_ours(args)
+        line = {"sweep": run_sweep, "configs": run_configs}.get(args.workload, run_ours)(args)
     if line is not None:
         print(json.dumps(line), flush=True)
 

@@ -114,6 +114,12 @@ int jds_ctx_destroy(jds_ctx* ctx);
 /* use the caller's cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); 0 = default */
 int jds_ctx_set_stream(jds_ctx* ctx, void* cuda_stream);
 int jds_ctx_synchronize(jds_ctx* ctx);
+/* stream ordering against the caller's own streams (cudaEvent_t handles, same device):
+ * wait_event - everything this context enqueues afterwards waits for the event (frames the
+ * caller produced on another stream); record_event - records the event behind the context's
+ * work so far (results of the non-synchronising *_records entry points) */
+int jds_ctx_wait_event(jds_ctx* ctx, void* cuda_event);
+int jds_ctx_record_event(jds_ctx* ctx, void* cuda_event);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int jds_ctx_launch_count(jds_ctx* ctx, uint64_t* launches);
 

@@ -54,6 +54,8 @@ PROTOTYPES = {
     "jds_ctx_destroy": (C.c_int, [C.c_void_p]),
     "jds_ctx_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "jds_ctx_synchronize": (C.c_int, [C.c_void_p]),
+    "jds_ctx_wait_event": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "jds_ctx_record_event": (C.c_int, [C.c_void_p, C.c_void_p]),
     "jds_ctx_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "jds_ctx_stage_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]),
     "jds_ctx_stage_timing": (C.c_int, [C.c_void_p, C.c_int]),

@@ -159,6 +159,14 @@ extern "C" int jds_ctx_create(int device, jds_ctx** out) {
         return fail(JDS_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(e));
     }
     c->own_stream = true;
+    // kernel attributes and constant tables of this device (no lazily initialised statics)
+    e = fused_configure_device();
+    if (e == cudaSuccess) e = ssim_configure_device();
+    if (e == cudaSuccess) e = entropy_configure_device();
+    if (e != cudaSuccess) {
+        jds_ctx_destroy(c);
+        return fail(JDS_ERR_CUDA, "kernel setup failed: %s", cudaGetErrorString(e));
+    }
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     {
         int l2 = 0;
@@ -218,6 +226,24 @@ extern "C" int jds_ctx_set_stream(jds_ctx* c, void* cuda_stream) {
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     c->stream = (cudaStream_t)cuda_stream;
     c->own_stream = false;
+    return JDS_OK;
+}
+
+// Order the context's stream after / before work of another stream of the same device (a
+// cudaEvent_t handle, e.g. torch.cuda.Event().cuda_event): wait_event makes every later kernel
+// of this context wait for the event (inputs produced on the caller's stream), record_event
+// records it behind everything enqueued so far (results of the non-synchronising entry points).
+extern "C" int jds_ctx_wait_event(jds_ctx* c, void* cuda_event) {
+    if (!c || !cuda_event) return fail(JDS_ERR_INVALID, "NULL argument");
+    JDS_CUDA(cudaSetDevice(c->device));
+    JDS_CUDA(cudaStreamWaitEvent(c->stream, (cudaEvent_t)cuda_event, 0));
+    return JDS_OK;
+}
+
+extern "C" int jds_ctx_record_event(jds_ctx* c, void* cuda_event) {
+    if (!c || !cuda_event) return fail(JDS_ERR_INVALID, "NULL argument");
+    JDS_CUDA(cudaSetDevice(c->device));
+    JDS_CUDA(cudaEventRecord((cudaEvent_t)cuda_event, c->stream));
     return JDS_OK;
 }
 
@@ -517,7 +543,16 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
     // L2-sized launch sequences: alternate chunks over two compute streams so the wave tail
     // and launch gaps of one frame's kernels are filled by the next frame's (fast mode only;
     // off while per-kernel timing is on, which wants kernels one at a time)
-    const bool dual = c->l2_chunking && !exact && !c->stage_timing && J.units > chunk;
+    // Only the fused kernels have per-stream scratch (chroma planes per slot, recon / coeff
+    // scratch per slot below); the staged fallback shares its fwd / rec planes, so it never
+    // runs on two streams (chunk k+1 overwrote what chunk k's SSIM kernel still read).
+    const uint8_t* probe_in = in_host ? (const uint8_t*)nullptr : J.rgb;
+    const uint8_t* probe_out = (want_recon && !out_host) ? J.recon : (const uint8_t*)nullptr;
+    const bool will_fuse = !exact && !c->no_fused && !want_ey && !want_ergb &&
+                           fused_supported(g, p->prefilter, probe_in, frame_bytes, probe_out, frame_bytes) &&
+                           ssim_strip_supported(g.H, g.W, probe_in, frame_bytes, probe_out, frame_bytes);
+    const bool dual = c->l2_chunking && will_fuse && !c->stage_timing && J.units > chunk;
+    const int nscr = (pipelined || dual) ? 2 : 1;        // recon / coefficient scratch slots
 
     int rc;
     const int fwd_units = J.shared_input ? 1 : chunk;
@@ -548,11 +583,11 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
     const size_t recon_slot = frame_bytes * (size_t)chunk;
     const size_t coeff_slot = ncoef * 2 * (size_t)chunk;
     if (in_host && (rc = ensure(c, c->in, in_slot * (J.shared_input ? 1 : nbuf)))) return rc;
-    if ((!want_recon || out_host) && (rc = ensure(c, c->recon, recon_slot * nbuf))) return rc;
+    if ((!want_recon || out_host) && (rc = ensure(c, c->recon, recon_slot * nscr))) return rc;
     // the histogram is taken from the coefficient buffer: scratch when the caller wants the
     // histogram but not the coefficients themselves (or wants them on the host)
     const bool coeff_scratch = (want_coeffs && out_host) || (want_hist && !want_coeffs);
-    if (coeff_scratch && (rc = ensure(c, c->coeffs, coeff_slot * nbuf))) return rc;
+    if (coeff_scratch && (rc = ensure(c, c->coeffs, coeff_slot * nscr))) return rc;
     if ((want_ey || want_ergb) && out_host && (rc = ensure(c, c->errs, (size_t)g.H * g.W * 8 * 2)))
         return rc;
 
@@ -588,6 +623,7 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
         const int n = (J.units - u0 < chunk) ? (J.units - u0) : chunk;
         const int b = chunk_idx % nbuf;
         const int slot = dual ? (chunk_idx & 1) : 0;
+        const int sb = pipelined ? b : slot;               // output scratch slot of this chunk
         cudaStream_t cs = slot ? c->stream2 : s;           // compute stream of this chunk
         ChunkPtrs P;
         P.first_chunk = (u0 == 0);
@@ -613,10 +649,10 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
         }
         // --- outputs ---
         P.d_recon = (want_recon && !out_host) ? J.recon + (size_t)u0 * frame_bytes
-                                              : (uint8_t*)c->recon.p + (size_t)b * recon_slot;
+                                              : (uint8_t*)c->recon.p + (size_t)sb * recon_slot;
         P.d_coeffs = nullptr;
         if (coeff_scratch)
-            P.d_coeffs = (int16_t*)((char*)c->coeffs.p + (size_t)b * coeff_slot);
+            P.d_coeffs = (int16_t*)((char*)c->coeffs.p + (size_t)sb * coeff_slot);
         else if (want_coeffs)
             P.d_coeffs = J.coeffs + (size_t)u0 * ncoef;
         P.d_ey = want_ey ? (out_host ? (double*)c->errs.p : J.err_y) : nullptr;

@@ -149,17 +149,14 @@ k_entropy_bits(const int16_t* __restrict__ coeffs, long long ny, long long nc,
     if (tid < 3 && s_sum[tid]) atomicAdd(&scan_bits[tid], s_sum[tid]);
 }
 
+// once per context (jds_ctx_create): the Annex K code lengths in constant memory of this device
+cudaError_t entropy_configure_device() {
+    const HuffLengths h = make_lengths();
+    return cudaMemcpyToSymbol(c_huff, &h, sizeof h);
+}
+
 cudaError_t launch_entropy_bits(const int16_t* coeffs, long long ny, long long nc,
                                 unsigned long long* scan_bits, cudaStream_t s) {
-    static bool uploaded[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!uploaded[dev & 63]) {
-        const HuffLengths h = make_lengths();
-        cudaError_t e = cudaMemcpyToSymbol(c_huff, &h, sizeof h);
-        if (e != cudaSuccess) return e;
-        uploaded[dev & 63] = true;
-    }
     cudaError_t e = cudaMemsetAsync(scan_bits, 0, 3 * sizeof(unsigned long long), s);
     if (e != cudaSuccess) return e;
     const long long total = ny + 2 * nc;

@@ -884,20 +884,29 @@ bool fused_supported(const Geom& g, int prefilter, const void* rgb, size_t rgb_s
 
 size_t fused_chroma_plane_floats(const Geom& g) { return g.sub ? (size_t)2 * g.plane_c : 0; }
 
-// opt in to > 48 KB dynamic shared memory once per kernel instantiation and device
-template <class K>
-static cudaError_t set_smem(K kernel, size_t bytes) {
-    static unsigned long long done_mask = 0;          // one static per instantiation of K... per kernel pointer below
-    static K done_kernel = nullptr;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (done_kernel == kernel && (done_mask >> (dev & 63)) & 1ull) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e == cudaSuccess) {
-        if (done_kernel != kernel) { done_kernel = kernel; done_mask = 0; }
-        done_mask |= 1ull << (dev & 63);
-    }
-    return e;
+// Opt in to > 48 KB dynamic shared memory for every instantiation.  Called once per context
+// from jds_ctx_create (the attribute is per device and the call is idempotent, so there is no
+// shared mutable state between contexts / threads - the launch paths below set nothing).
+cudaError_t fused_configure_device() {
+    cudaError_t e;
+#define JDS_SET(K, BYTES)                                                                       \
+    if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES))) != cudaSuccess) return e
+    JDS_SET((k_fast_chroma<1, false>), sizeof(ChromaSmem<1>));
+    JDS_SET((k_fast_chroma<1, true>), sizeof(ChromaSmem<1>));
+    JDS_SET((k_fast_chroma<2, false>), sizeof(ChromaSmem<2>));
+    JDS_SET((k_fast_chroma<2, true>), sizeof(ChromaSmem<2>));
+    JDS_SET((k_fast_chroma_pf<1, false>), sizeof(ChromaPfSmem<1>));
+    JDS_SET((k_fast_chroma_pf<1, true>), sizeof(ChromaPfSmem<1>));
+    JDS_SET((k_fast_chroma_pf<2, false>), sizeof(ChromaPfSmem<2>));
+    JDS_SET((k_fast_chroma_pf<2, true>), sizeof(ChromaPfSmem<2>));
+    JDS_SET((k_fast_luma<1, false>), sizeof(LumaSmem<1>));
+    JDS_SET((k_fast_luma<1, true>), sizeof(LumaSmem<1>));
+    JDS_SET((k_fast_luma<2, false>), sizeof(LumaSmem<2>));
+    JDS_SET((k_fast_luma<2, true>), sizeof(LumaSmem<2>));
+    JDS_SET((k_fast_444<false>), sizeof(F444Smem));
+    JDS_SET((k_fast_444<true>), sizeof(F444Smem));
+#undef JDS_SET
+    return cudaSuccess;
 }
 
 cudaError_t launch_fused_chroma(const Geom& g, int prefilter, const uint8_t* rgb, size_t rgb_stride,
@@ -905,12 +914,9 @@ cudaError_t launch_fused_chroma(const Geom& g, int prefilter, const uint8_t* rgb
                                 int table_stride, int16_t* coeffs, size_t coeff_stride,
                                 DevMetrics* metrics, int units, cudaStream_t s) {
     dim3 grid((g.nbx_c + CA_BX - 1) / CA_BX, (g.nby_c + CA_BY - 1) / CA_BY, units);
-    cudaError_t e;
     if (prefilter) {
 #define JDS_LAUNCH_PF(SUBV, CO)                                                                 \
     do {                                                                                        \
-        e = set_smem(k_fast_chroma_pf<SUBV, CO>, sizeof(ChromaPfSmem<SUBV>));                    \
-        if (e != cudaSuccess) return e;                                                          \
         k_fast_chroma_pf<SUBV, CO><<<grid, CA_NT, sizeof(ChromaPfSmem<SUBV>), s>>>(              \
             g, rgb, rgb_stride, cplanes, cplane_stride, tables, table_stride, coeffs,            \
             coeff_stride, metrics);                                                              \
@@ -922,8 +928,6 @@ cudaError_t launch_fused_chroma(const Geom& g, int prefilter, const uint8_t* rgb
     }
 #define JDS_LAUNCH_CA(SUBV, CO)                                                                 \
     do {                                                                                        \
-        e = set_smem(k_fast_chroma<SUBV, CO>, sizeof(ChromaSmem<SUBV>));                         \
-        if (e != cudaSuccess) return e;                                                          \
         k_fast_chroma<SUBV, CO><<<grid, CA_NT, sizeof(ChromaSmem<SUBV>), s>>>(                   \
             g, rgb, rgb_stride, cplanes, cplane_stride, tables, table_stride, coeffs,            \
             coeff_stride, metrics);                                                              \
@@ -939,17 +943,12 @@ cudaError_t launch_fused_luma(const Geom& g, const uint8_t* rgb, size_t rgb_stri
                               int table_stride, int16_t* coeffs, size_t coeff_stride,
                               uint8_t* recon, size_t recon_stride, DevMetrics* metrics, int units,
                               cudaStream_t s) {
-    cudaError_t e;
     if (g.sub == 0) {
         dim3 grid((g.nbx_y + F4_BX - 1) / F4_BX, (g.nby_y + F4_BY - 1) / F4_BY, units);
         if (coeffs) {
-            e = set_smem(k_fast_444<true>, sizeof(F444Smem));
-            if (e != cudaSuccess) return e;
             k_fast_444<true><<<grid, F4_NT, sizeof(F444Smem), s>>>(
                 g, rgb, rgb_stride, tables, table_stride, coeffs, coeff_stride, recon, recon_stride, metrics);
         } else {
-            e = set_smem(k_fast_444<false>, sizeof(F444Smem));
-            if (e != cudaSuccess) return e;
             k_fast_444<false><<<grid, F4_NT, sizeof(F444Smem), s>>>(
                 g, rgb, rgb_stride, tables, table_stride, coeffs, coeff_stride, recon, recon_stride, metrics);
         }
@@ -958,8 +957,6 @@ cudaError_t launch_fused_luma(const Geom& g, const uint8_t* rgb, size_t rgb_stri
     dim3 grid((g.nbx_y + LU_BX - 1) / LU_BX, (g.nby_y + LU_BY - 1) / LU_BY, units);
 #define JDS_LAUNCH_LU(SUBV, CO)                                                                 \
     do {                                                                                        \
-        e = set_smem(k_fast_luma<SUBV, CO>, sizeof(LumaSmem<SUBV>));                             \
-        if (e != cudaSuccess) return e;                                                          \
         k_fast_luma<SUBV, CO><<<grid, LU_NT, sizeof(LumaSmem<SUBV>), s>>>(                       \
             g, rgb, rgb_stride, cplanes, cplane_stride, tables, table_stride, coeffs,            \
             coeff_stride, recon, recon_stride, metrics);                                         \

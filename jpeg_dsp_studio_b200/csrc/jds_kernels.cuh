@@ -5,6 +5,13 @@
 
 namespace jds {
 
+// Per-device one-time setup, called from jds_ctx_create for the context's device: dynamic
+// shared-memory opt-ins / carve-outs and constant tables.  Idempotent and free of shared
+// mutable state, so contexts on different threads / devices never race.
+cudaError_t fused_configure_device();      // jds_fused.cu
+cudaError_t ssim_configure_device();       // jds_ssim.cu
+cudaError_t entropy_configure_device();    // jds_entropy.cu
+
 // strides are in elements of the buffer's type, per unit (0 = shared by all units)
 void launch_forward(bool exact, const Geom& g, int prefilter, const uint8_t* rgb,
                     size_t rgb_stride, void* fwd, size_t fwd_stride, int units, cudaStream_t s);

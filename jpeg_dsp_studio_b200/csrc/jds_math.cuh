@@ -95,6 +95,7 @@ JDS_HD int reflect_index(int i, int n) {
 }
 // cv2 BORDER_REFLECT_101 for a 3-tap filter (offsets -1 / n only)
 JDS_HD int reflect101(int i, int n) {
+    if (n == 1) return 0;               // OpenCV's borderInterpolate: a 1-sample axis repeats it
     if (i < 0) return -i;
     if (i >= n) return 2 * (n - 1) - i;
     return i;

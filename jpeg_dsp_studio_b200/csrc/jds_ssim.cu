@@ -406,6 +406,16 @@ k_ssim_strip(int H, int W, int seg_rows, const uint8_t* __restrict__ a_img, size
 
 size_t ssim_strip_smem_bytes() { return sizeof(SsimSmem); }
 
+// once per context (jds_ctx_create): dynamic shared memory opt-in and the largest carve-out so
+// that four 54 KB CTAs fit an SM; idempotent, no state shared between contexts
+cudaError_t ssim_configure_device() {
+    cudaError_t e = cudaFuncSetAttribute(k_ssim_strip, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(SsimSmem));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_ssim_strip, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                cudaSharedmemCarveoutMaxShared);
+}
+
 bool ssim_strip_supported(int H, int W, const void* a, size_t a_stride, const void* b,
                           size_t b_stride) {
     if (H < 7 || W < 7 || (W % 16) != 0) return false;
@@ -417,21 +427,6 @@ cudaError_t launch_ssim_strip(int H, int W, const uint8_t* a, size_t a_stride, c
                               size_t b_stride, DevMetrics* metrics, int units, bool want_ssim,
                               bool want_sse, int sm_count, cudaStream_t s) {
     const size_t smem = sizeof(SsimSmem);
-    {
-        static unsigned long long done_mask = 0;      // per device: the attribute is set once
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (!((done_mask >> (dev & 63)) & 1ull)) {
-            cudaError_t e = cudaFuncSetAttribute(k_ssim_strip, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)smem);
-            if (e != cudaSuccess) return e;
-            // ask for the largest shared-memory carve-out so four 54 KB CTAs fit an SM
-            e = cudaFuncSetAttribute(k_ssim_strip, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                     cudaSharedmemCarveoutMaxShared);
-            if (e != cudaSuccess) return e;
-            done_mask |= 1ull << (dev & 63);
-        }
-    }
     const int strips = (W + S_OW - 1) / S_OW;
     // Vertical segments per strip.  More segments = more CTAs to balance over the 4 x sm_count
     // resident slots, but every segment re-reads 6 rows and pays a fixed prologue; fewer = a

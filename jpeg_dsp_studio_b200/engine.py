@@ -195,8 +195,35 @@ class Engine:
         return N.JdsParams(int(h), int(w), int(quality), _mode_code(mode), int(bool(prefilter)),
                            _precision_code(precision), int(outputs), 0)
 
-    @staticmethod
-    def _in_ptr(image):
+    def _order_after_torch(self, t):
+        """A CUDA tensor handed to this engine was produced on torch's current stream of its
+        device, while the context issues its kernels on its own stream: make the context's
+        stream wait for what torch has enqueued so far (an event, no host synchronisation).
+        Nothing to do when the context already runs on that stream (``use_stream``)."""
+        import torch
+        if t.device.index != self.device:
+            raise ValueError(f"tensor lives on cuda:{t.device.index} but this engine is bound to "
+                             f"cuda:{self.device} (use get_engine({t.device.index}))")
+        cur = torch.cuda.current_stream(t.device)
+        if getattr(self, "_stream_handle", None) == cur.cuda_stream:
+            return
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        N.check(self._lib.jds_ctx_wait_event(self._ctx, C.c_void_p(ev.cuda_event)))
+
+    def _order_torch_after(self, device_tensor):
+        """After a NON-synchronising entry point: torch's current stream waits for the
+        context's stream, so the caller may consume the results with ordinary torch ops."""
+        import torch
+        cur = torch.cuda.current_stream(device_tensor.device)
+        if getattr(self, "_stream_handle", None) == cur.cuda_stream:
+            return
+        ev = torch.cuda.Event()
+        ev.record(cur)                 # creates the underlying cudaEvent_t
+        N.check(self._lib.jds_ctx_record_event(self._ctx, C.c_void_p(ev.cuda_event)))
+        cur.wait_event(ev)
+
+    def _in_ptr(self, image):
         """(pointer, location, keepalive) for a uint8 NumPy array or torch tensor."""
         if _is_torch(image):
             import torch
@@ -204,6 +231,8 @@ class Engine:
                 raise TypeError(f"image tensor must be uint8, got {image.dtype}")
             t = image.contiguous()
             loc = N.JDS_DEVICE if t.is_cuda else N.JDS_HOST
+            if t.is_cuda:
+                self._order_after_torch(t)
             return C.c_void_p(t.data_ptr()), loc, t
         a = np.ascontiguousarray(image)
         if a.dtype != np.uint8:
@@ -374,6 +403,8 @@ class Engine:
                 raise TypeError(f"coeffs must be int16, got {coeffs.dtype}")
             t = coeffs.contiguous()
             ptr, loc, keep, size = C.c_void_p(t.data_ptr()), (N.JDS_DEVICE if t.is_cuda else N.JDS_HOST), t, t.numel()
+            if t.is_cuda:
+                self._order_after_torch(t)
         else:
             a = np.ascontiguousarray(coeffs)
             if a.dtype != np.int16:
@@ -500,6 +531,7 @@ class Engine:
             N.check(self._lib.jds_sweep_records(self._ctx, C.byref(p), qarr, len(qs), ptr, loc,
                                                 int(unit0), int(unit_step),
                                                 C.c_void_p(records.data_ptr()), cap))
+        self._order_torch_after(records)
         return keep
 
     def batch_records(self, frames, records, quality=50, mode="4:2:0", prefilter=False, *,
@@ -530,6 +562,7 @@ class Engine:
             N.check(self._lib.jds_roundtrip_batch_records(self._ctx, C.byref(p), n, ptr, rp, int(unit0),
                                                           int(unit_step), C.c_void_p(records.data_ptr()),
                                                           int(records.shape[0])))
+        self._order_torch_after(records)
         return keep
 
 

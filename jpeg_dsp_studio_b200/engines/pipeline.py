@@ -10,7 +10,7 @@ select the arithmetic mode and the device.
 """
 
 import time
-from typing import Optional, Sequence, Tuple
+from typing import Callable, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -123,17 +123,38 @@ def compress_reconstruct(
 def quality_sweep(image_rgb, base_params: CompressionParams,
                   qualities: Sequence[int] = tuple(range(10, 91, 10)), *,
                   precision: str = "fast", device: Optional[int] = None,
-                  keep_images: bool = False):
+                  keep_images: bool = False,
+                  progress: Optional[Callable[[int, int], None]] = None,
+                  progress_points: int = 0):
     """Rate-distortion sweep: the loop of ``BatchSweepWorker.run`` (gui/worker.py:55-74)
     as one call.  Returns ``[(quality, CompressionResult), ...]`` like the worker's
     ``finished`` payload; ``reconstructed_image`` is ``None`` unless ``keep_images``
     (the sweep's consumers read only bpp/PSNR/SSIM: gui/compression_tab.py:752-754,
-    gui/main_window.py:286-293)."""
+    gui/main_window.py:286-293).
+
+    ``progress(done, total)`` mirrors the worker's ``progress`` signal (gui/worker.py:44,70):
+    it is called once per finished quality point, in order.  The points are then computed in
+    groups of ``progress_points`` (default: a tenth of the sweep, at least one) so that a GUI
+    sees movement while the device works; without a callback the sweep is one native call."""
     image_checked = _validate(image_rgb, base_params)
     eng = get_engine(device)
+    qualities = list(qualities)
     t0 = time.perf_counter()
-    outs = eng.sweep(image_checked, list(qualities), base_params.subsampling_mode,
-                     base_params.use_prefilter, precision=precision, want_recon=keep_images)
+    if progress is None or not qualities:
+        outs = eng.sweep(image_checked, qualities, base_params.subsampling_mode,
+                         base_params.use_prefilter, precision=precision, want_recon=keep_images)
+    else:
+        for q in qualities:
+            CompressionParams(quality=int(q))       # fail before the first group, like one call would
+        total = len(qualities)
+        group = int(progress_points) if progress_points and progress_points > 0 else max(1, -(-total // 10))
+        outs = []
+        for g0 in range(0, total, group):
+            part = eng.sweep(image_checked, qualities[g0:g0 + group], base_params.subsampling_mode,
+                             base_params.use_prefilter, precision=precision, want_recon=keep_images)
+            outs.extend(part)
+            for i in range(g0, g0 + len(part)):
+                progress(i + 1, total)
     wall_ms = (time.perf_counter() - t0) * 1000.0
     results = []
     for q, o in zip(qualities, outs):

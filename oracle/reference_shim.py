@@ -1,7 +1,8 @@
 """Import the UNMODIFIED reference from /root/reference (TEST INFRASTRUCTURE).
 
-Only works where ``/root/reference`` exists (the build container; never the GPU
-box).  The reference's ``utils/metrics.py:5`` imports ``skimage.metrics`` at module
+Works where ``/root/reference`` exists (the build container) or where ``oracle/make_ref.py``
+has staged its hot-path files under ``oracle/_ref/reference`` (the GPU box: bench.py's
+``--impl reference`` / ``cpu_baseline`` legs only - the ``-m gpu`` tests never read either).  The reference's ``utils/metrics.py:5`` imports ``skimage.metrics`` at module
 top, so ``oracle.skimage_standin`` is registered first.  The reference's top-level
 package names (``engines``, ``models``, ``utils``) are removed from ``sys.modules``
 again after loading so they cannot shadow this repo's drop-in packages of the same
@@ -14,7 +15,16 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("JDS_REFERENCE_ROOT", "/root/reference")
+def _default_root():
+    """/root/reference in the build container, else the copy oracle/make_ref.py staged under
+    oracle/_ref/reference (git-ignored; it travels to the GPU box with the snapshot)."""
+    if os.path.isfile("/root/reference/engines/pipeline.py"):
+        return "/root/reference"
+    staged = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "reference")
+    return staged if os.path.isfile(os.path.join(staged, "engines", "pipeline.py")) else "/root/reference"
+
+
+REFERENCE_ROOT = os.environ.get("JDS_REFERENCE_ROOT") or _default_root()
 _TOP = ("engines", "models", "utils")
 _cache = None
 

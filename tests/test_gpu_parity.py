@@ -445,6 +445,38 @@ def test_public_sweep_and_batch_api(J, oracle):
         assert r.bpp == ref["bpp"] and r.compression_ratio == ref["compression_ratio"]
     with pytest.raises(ValueError):
         J.quality_sweep(img, base, [0, 50])
+    # BatchSweepWorker's progress signal (gui/worker.py:44,70): once per point, in order
+    seen = []
+    rd_p = J.quality_sweep(img, base, range(10, 91, 20), precision="exact",
+                           progress=lambda i, n: seen.append((i, n)), progress_points=2)
+    assert seen == [(1, 5), (2, 5), (3, 5), (4, 5), (5, 5)]
+    for (q0, r0), (q1, r1) in zip(rd, rd_p):
+        assert q0 == q1 and r0.psnr_rgb == r1.psnr_rgb and r0.bpp == r1.bpp
+    seen.clear()
+    with pytest.raises(ValueError):
+        J.quality_sweep(img, base, [50, 101], progress=lambda i, n: seen.append(i))
+    assert seen == []
+
+
+def test_cuda_tensor_inputs_are_ordered_after_torch(J):
+    """a CUDA tensor produced on torch's current stream is read by a context that
+    runs on its own stream - the engine must order itself behind torch (event), and must refuse a
+    tensor that lives on another device."""
+    import torch
+    eng = J.Engine(0)               # own stream, never bound to torch's
+    base = torch.from_numpy(CS.rand_rgb(5, 1080, 1920)).cuda()
+    want = eng.roundtrip(base, 50, "4:2:0", False, precision="fast").recon.cpu().numpy()
+    for rep in range(4):
+        big = torch.empty((64, 1080, 1920, 3), dtype=torch.uint8, device="cuda")
+        for _ in range(3):
+            big.random_(0, 256)      # keeps torch's stream busy right before the hand-over
+        frame = big[rep].copy_(base, non_blocking=True)
+        got = eng.roundtrip(frame, 50, "4:2:0", False, precision="fast").recon
+        assert np.array_equal(got.cpu().numpy(), want)
+    if torch.cuda.device_count() > 1:
+        with pytest.raises(ValueError):
+            eng.roundtrip(base.to("cuda:1"), 50, "4:2:0", False, precision="fast")
+    eng.close()
 
 
 PF_CASES = [
