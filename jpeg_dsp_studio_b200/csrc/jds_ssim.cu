@@ -1,4 +1,4 @@
-// jds_ssim.cu - strip-streaming SSIM / SSE kernel (sm_100a).
+// jds_ssim.cu - strip-streaming SSIM / SSE kernel (sm_100a), second generation.
 //
 // Computes, for R, G, B and BT.601 Y of two uint8 RGB images (original,
 // reconstructed): the sum of the 7x7-window SSIM map over all windows inside the
@@ -6,21 +6,30 @@
 // of squared differences for PSNR (utils/metrics.py:11,20).
 //
 // Design (DESIGN.md "k_ssim_strip"):
-//   * a CTA owns a vertical strip of 64 window columns (70 pixel columns) and walks
-//     down it 7 rows at a time; nothing is recomputed vertically.
-//   * rows arrive by TMA bulk copies (cp.async.bulk + mbarrier), double buffered.
+//   * a CTA owns a vertical strip of 64 window columns (70 pixel columns, 80 loaded) and
+//     walks down it 7 rows at a time; nothing is recomputed vertically.
+//   * rows arrive by TMA: ONE cp.async.bulk.tensor (3-D tensor map over bytes x rows x
+//     units, box 240 B x 7 rows, SASS UTMALDG) per image and chunk, double buffered, issued
+//     by one thread two chunks ahead; out-of-image rows / columns are zero-filled by the TMA
+//     unit, so the kernel has no edge cases on the load side.
 //   * the four channels are processed as two PAIRS - (R,G) and (B,Y) - and every
 //     floating-point operation is a packed f32x2 instruction (FADD2/FMUL2/FFMA2, new on
 //     sm_100): one issue slot does the work for both channels of the pair.
-//   * prep: bytes -> centred (x-128) fp32, channel pairs interleaved, plus BT.601 Y.
 //   * pass 1 (horizontal): a thread owns (row, pair, 8-window segment) and forms the
-//     7-tap window sums of x, y, x^2+y^2, xy by running prefix differences in
-//     registers; results go to shared memory (32 B per row, pair, column).
+//     7-tap window sums of x, y, x^2+y^2, xy by running differences in registers.  The
+//     (R,G) threads read the RAW BYTES of their 14 pixels straight from the TMA tile (PRMT
+//     into 2^23+v, one packed add centres both channels) - no staging pass, no float copy
+//     of these two channels in shared memory; the (B,Y) threads read centred fp32 (B,Y)
+//     pairs that `prep` derived from the bytes (BT.601 luma needs all three channels).
 //   * pass 2 (vertical): a thread owns (column, pair), keeps the last 7 horizontal
 //     sums in a register ring, slides the 7-row sum and evaluates the SSIM formula.
+//   * prep of chunk c+1 is spread over the two barrier intervals of chunk c so that the
+//     (R,G) warps (byte conversion in pass 1) and the (B,Y) warps carry the same load;
+//     the (B,Y) planes are double buffered for that.
 //   * centring makes the fp32 sums of the integer channels exact and keeps the low
 //     bits of the Y sums; the Y accumulators are rebuilt from the ring every chunk so
 //     rounding cannot drift down a strip.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -29,13 +38,25 @@
 
 // tuning knobs (defaults = the measured best; tools/ssim_variants.sh builds the others)
 #ifndef JDS_SSIM_REBUILD_EVERY
-#define JDS_SSIM_REBUILD_EVERY 1     // chunks between rebuilds of the non-integer (B,Y) accumulators
-#endif
-#ifndef JDS_SSIM_SPLIT_Q
-#define JDS_SSIM_SPLIT_Q 0           // pass 1: separate x^2 / y^2 chains (more ILP, one more add per window)
+#define JDS_SSIM_REBUILD_EVERY 2     // chunks between rebuilds of the non-integer (B,Y) accumulators (1: 1.208, 2: 1.199, 4: 1.195 ms)
 #endif
 #ifndef JDS_SSIM_CTAS_PER_SM
 #define JDS_SSIM_CTAS_PER_SM 0       // 0: pick the vertical segmentation by the wave model below; n: aim at n CTAs per SM
+#endif
+#ifndef JDS_SSIM_ST64
+#define JDS_SSIM_ST64 0              // 1: pass-1 results leave as 8-byte stores (no MOVs, twice the store instructions: 1.210 vs 1.208 ms)
+#endif
+#ifndef JDS_SSIM_PREP_SPLIT
+#define JDS_SSIM_PREP_SPLIT 0        // 1: spread prep(c+1) over both barrier intervals of chunk c
+#endif
+#ifndef JDS_SSIM_PAIRBAR
+#define JDS_SSIM_PAIRBAR 0           // 1: pass 1 -> pass 2 hand-over by a 64-thread named barrier per channel pair (measured slower: 1.28 vs 1.21 ms)
+#endif
+#ifndef JDS_SSIM_PREP_BY1
+#define JDS_SSIM_PREP_BY1 160        // with PAIRBAR: prep tasks [0, n) go to the (B,Y) threads, the rest to (R,G)
+#endif
+#ifndef JDS_SSIM_SSE_FROM_SUMS
+#define JDS_SSIM_SSE_FROM_SUMS 1     // squared error of a task's 8 pixels from its first window's sums + pixel 7
 #endif
 
 namespace jds {
@@ -47,24 +68,26 @@ constexpr int S_R = 7;               // rows per chunk == window height
 constexpr int S_NT = 128;            // threads per CTA = 64 columns x 2 channel pairs
 constexpr int S_SEG = 8;             // windows per pass-1 task
 constexpr int S_NSEG = S_OW / S_SEG; // 8
+constexpr int S_PG = (S_OW + 6 + 3) / 4;   // 18 groups of 4 pixels: the 72 columns pass 1 reads
+constexpr int S_TILEB = 1792;        // bytes reserved per TMA tile (7 x 240 = 1680, rounded to 128)
 
 // Shared-memory rows are padded so that consecutive ROWS start 16 bytes apart modulo 128:
 // a quarter-warp that walks 8 rows at the same column then hits 8 different bank groups.
-constexpr int S_FHALF = S_LW / 4;      // float4 per half row of fpl (even / odd pixel pairs)
-constexpr int S_FPITCH = 2 * S_FHALF + 1; // float4 row pitch of fpl: 81 * 16 B = 10 * 128 + 16
-constexpr int S_HPITCH = 2 * S_OW + 1; // float4 row pitch of hxy / hqc: 129 * 16 B = 16 * 128 + 16
+constexpr int S_BHALF = S_PG;              // float4 per half row of `by` (even / odd pixel pairs)
+constexpr int S_BPITCH = 2 * S_BHALF + 1;  // 37 float4 = 592 B = 4 * 128 + 80
+constexpr int S_HPITCH = 2 * S_OW + 1;     // float4 row pitch of hxy / hqc: 129 * 16 B = 16 * 128 + 16
 
 struct HSum {                        // window sums of one (row, pair, column)
     float2 sx, sy, sq, sc;           // .x = first channel of the pair, .y = second
 };
 
 struct SsimSmem {
-    alignas(128) uint8_t raw[2][2][S_R][S_ROWB];   // [buffer][image][row][byte]
-    // centred fp32 samples [image][pair][row]: each float4 holds two pixels x two channels
-    // (c0 p, c1 p, c0 p+1, c1 p+1); even pixel-pairs in [0, 40), odd pixel-pairs in [40, 80)
-    alignas(16) float4 fpl[2][2][S_R][S_FPITCH];
-    alignas(16) float4 hxy[S_R][S_HPITCH];         // horizontal sums (sx, sy) [row][pair*64+col]
-    alignas(16) float4 hqc[S_R][S_HPITCH];         // horizontal sums (sq, sc)
+    alignas(128) uint8_t raw[2][2][S_TILEB];        // [buffer][image]: 7 rows x 240 B, as the TMA writes them
+    // centred fp32 (B, Y) pairs [buffer][image][row]: each float4 holds two pixels
+    // (B p, Y p, B p+1, Y p+1); even pixel-pairs in [0, 18), odd pixel-pairs in [18, 36)
+    alignas(16) float4 by[2][2][S_R][S_BPITCH];
+    alignas(16) float4 hxy[S_R][S_HPITCH];          // horizontal sums (sx, sy) [row][pair*64+col]
+    alignas(16) float4 hqc[S_R][S_HPITCH];          // horizontal sums (sq, sc)
     alignas(8) unsigned long long bar[2];
     double red_ssim[4][2];
     double red_sse[4][4];
@@ -94,31 +117,41 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
         "r"(parity)
         : "memory");
 }
-// TMA bulk copy global -> shared, completion counted on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes,
-                                         unsigned long long* bar) {
+// TMA tile load global -> shared through a tensor map, completion counted on an mbarrier
+// (SASS: UTMALDG).  Coordinates: byte column, row, unit.
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int x, int y, int z,
+                                            unsigned long long* bar) {
     asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
         : "memory");
 }
 
-__device__ __forceinline__ int hswz(int col) { return col ^ ((col >> 3) & 7); }
-
-// byte `b` (0..3) of `w` as (value - 128) in fp32: 0x4B0000vv is 2^23 + vv
+// byte `B` (0..3) of `w` as 2^23 + value in fp32 bits (0x4B0000vv)
+template <int B>
+__device__ __forceinline__ float byte_biased(uint32_t w) {
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440 | B));
+}
+// byte `B` (0..3) of `w` as (value - 128) in fp32
 template <int B>
 __device__ __forceinline__ float byte_centered(uint32_t w) {
-    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440 | B)) - 8388736.0f;
+    return byte_biased<B>(w) - 8388736.0f;
 }
 
-__device__ __forceinline__ float rcp_approx(float x) {        // MUFU.RCP, no range fix-up
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
 __device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __ffma2_rn(b, f2(-1.0f), a); }
+
+// 8-byte shared-memory accesses straight from / into a packed register pair
+__device__ __forceinline__ void st_shared_f2(uint32_t addr, float2 v) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ float2 ld_shared_f2(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+    return v;
+}
 
 // the per-window formula lives in jds_ssim_formula.cuh (shared with the CPU emulation)
 __device__ __forceinline__ float2 ssim_window_half2_acc(float2 sx, float2 sy, float2 sq, float2 sc,
@@ -126,16 +159,110 @@ __device__ __forceinline__ float2 ssim_window_half2_acc(float2 sx, float2 sy, fl
     return ssim_window_half_acc<Pair2>(sx, sy, sq, sc, ssum);
 }
 
+// (R, G) of pixel I of a 14-pixel segment held as 12 words of raw bytes, centred, as one pair
+template <int I>
+__device__ __forceinline__ float2 rg_centered(const uint32_t (&w)[12]) {
+    constexpr int br = 3 * I, bg = 3 * I + 1;
+    const float2 v = f2(byte_biased<(br & 3)>(w[br >> 2]), byte_biased<(bg & 3)>(w[bg >> 2]));
+    return __fadd2_rn(v, f2(-8388736.0f));
+}
+
+// Pass 1 for one (row, segment) of channel pair PAIR: sliding 7-tap sums over 14 pixels ->
+// 8 windows x (sx, sy, sq, sc) into hxy / hqc; returns the squared error of the 8 pixels the
+// task owns (exact: integer channels / small sums).  Pixels are converted (PAIR 0: raw bytes
+// of the TMA tile) or loaded (PAIR 1: the prepared (B,Y) plane) just before they enter the
+// window and dropped 7 steps later, so only a short history is live.
+template <int PAIR>
+__device__ __forceinline__ float2 pass1_task(SsimSmem& sm, int buf, int p1_row, int p1_seg) {
+    float2 xs[S_SEG + 6], ys[S_SEG + 6];
+    uint32_t wa[12], wb[12];
+    const float4 *qa = nullptr, *qb = nullptr;
+    if (PAIR == 0) {
+        // raw bytes of pixels 8*seg .. 8*seg+13 of this row: 42 bytes from byte 24*seg,
+        // six 8-byte loads per image (a half-warp = 2 segments x 8 rows: conflict free)
+        const uint2* pa = reinterpret_cast<const uint2*>(&sm.raw[buf][0][p1_row * S_ROWB + 24 * p1_seg]);
+        const uint2* pb = reinterpret_cast<const uint2*>(&sm.raw[buf][1][p1_row * S_ROWB + 24 * p1_seg]);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const uint2 a = pa[k], b = pb[k];
+            wa[2 * k] = a.x; wa[2 * k + 1] = a.y;
+            wb[2 * k] = b.x; wb[2 * k + 1] = b.y;
+        }
+    } else {
+        // pixel-pair index of the segment's first pixel is 4 * seg (even): pairs alternate
+        // between the even and the odd half of the row
+        qa = &sm.by[buf][0][p1_row][2 * p1_seg];
+        qb = &sm.by[buf][1][p1_row][2 * p1_seg];
+    }
+    float2 wx = f2(0.f), wy = f2(0.f), wq = f2(0.f), wc = f2(0.f), sse = f2(0.f);
+    const uint32_t hx_dst = smem_u32(&sm.hxy[p1_row][PAIR * S_OW + S_SEG * p1_seg]);
+    const uint32_t hq_dst = smem_u32(&sm.hqc[p1_row][PAIR * S_OW + S_SEG * p1_seg]);
+#if JDS_SSIM_ST64
+    const uint32_t st_swap = (p1_seg & 1) * 8;
+#define P1_STORE(j)                                                                      \
+            st_shared_f2(hx_dst + 16 * (j) + st_swap, wx);                               \
+            st_shared_f2(hx_dst + 16 * (j) + (8 - st_swap), wy);                         \
+            st_shared_f2(hq_dst + 16 * (j) + st_swap, wq);                               \
+            st_shared_f2(hq_dst + 16 * (j) + (8 - st_swap), wc);
+#else
+#define P1_STORE(j)                                                                      \
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hx_dst + 16 * (j)), \
+                         "f"(wx.x), "f"(wx.y), "f"(wy.x), "f"(wy.y) : "memory");         \
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hq_dst + 16 * (j)), \
+                         "f"(wq.x), "f"(wq.y), "f"(wc.x), "f"(wc.y) : "memory");
+#endif
+#define JDS_P1_PIXEL(I)                                                                  \
+    {                                                                                    \
+        constexpr int i = (I);                                                           \
+        if (PAIR == 0) {                                                                 \
+            xs[i] = rg_centered<i>(wa);                                                  \
+            ys[i] = rg_centered<i>(wb);                                                  \
+        } else if ((i & 1) == 0) {                                                       \
+            constexpr int i2 = i >> 1;                                                   \
+            constexpr int off = (i2 & 1) * S_BHALF + (i2 >> 1);                          \
+            const float4 a = qa[off], b = qb[off];                                       \
+            xs[i] = f2(a.x, a.y); xs[i + 1] = f2(a.z, a.w);                              \
+            ys[i] = f2(b.x, b.y); ys[i + 1] = f2(b.z, b.w);                              \
+        }                                                                                \
+        if (JDS_SSIM_SSE_FROM_SUMS ? (i == S_SEG - 1) : (i < S_SEG)) {                   \
+            const float2 d = sub2(xs[i], ys[i]);                                         \
+            sse = __ffma2_rn(d, d, sse);                                                 \
+        }                                                                                \
+        wx = __fadd2_rn(wx, xs[i]);                                                      \
+        wy = __fadd2_rn(wy, ys[i]);                                                      \
+        wq = __ffma2_rn(xs[i], xs[i], __ffma2_rn(ys[i], ys[i], wq));                     \
+        wc = __ffma2_rn(xs[i], ys[i], wc);                                               \
+        if (i >= 6) {                                                                    \
+            constexpr int j = i >= 6 ? i - 6 : 0;                                        \
+            /* pixels 0..6 are window 0: sum (x-y)^2 = sq - 2 sc; pixel 7 was added above */ \
+            if (JDS_SSIM_SSE_FROM_SUMS && j == 0) sse = __fadd2_rn(sse, __ffma2_rn(wc, f2(-2.0f), wq)); \
+            P1_STORE(j)                                                                  \
+            if (j < S_SEG - 1) {                                                         \
+                const float2 ox = xs[j], oy = ys[j];                                     \
+                const float2 nox = sub2(f2(0.f), ox), noy = sub2(f2(0.f), oy);           \
+                wx = __fadd2_rn(wx, nox);                                                \
+                wy = __fadd2_rn(wy, noy);                                                \
+                wq = __ffma2_rn(nox, ox, __ffma2_rn(noy, oy, wq));                       \
+                wc = __ffma2_rn(nox, oy, wc);                                            \
+            }                                                                            \
+        }                                                                                \
+    }
+    JDS_P1_PIXEL(0) JDS_P1_PIXEL(1) JDS_P1_PIXEL(2) JDS_P1_PIXEL(3) JDS_P1_PIXEL(4)
+    JDS_P1_PIXEL(5) JDS_P1_PIXEL(6) JDS_P1_PIXEL(7) JDS_P1_PIXEL(8) JDS_P1_PIXEL(9)
+    JDS_P1_PIXEL(10) JDS_P1_PIXEL(11) JDS_P1_PIXEL(12) JDS_P1_PIXEL(13)
+#undef P1_STORE
+#undef JDS_P1_PIXEL
+    return sse;
+}
+
 __global__ void __launch_bounds__(S_NT, 4)
-k_ssim_strip(int H, int W, int seg_rows, const uint8_t* __restrict__ a_img, size_t a_stride,
-             const uint8_t* __restrict__ b_img, size_t b_stride, DevMetrics* __restrict__ metrics,
-             int want_ssim, int want_sse) {
+k_ssim_strip(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+             int H, int W, int seg_rows, int a_unit_step, int b_unit_step,
+             DevMetrics* __restrict__ metrics, int want_ssim, int want_sse) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SsimSmem& sm = *reinterpret_cast<SsimSmem*>(smem_raw);
     const int tid = threadIdx.x;
     const int unit = blockIdx.z;
-    const uint8_t* A = a_img + (size_t)unit * a_stride;
-    const uint8_t* B = b_img + (size_t)unit * b_stride;
     const int x0 = blockIdx.x * S_OW;
     // rows: this CTA owns pixel rows [py0, py1) for the squared error and the window
     // rows [py0, min(py1, H-6)) for SSIM; it reads pixel rows [py0, min(py1 + 6, H))
@@ -144,9 +271,7 @@ k_ssim_strip(int H, int W, int seg_rows, const uint8_t* __restrict__ a_img, size
     const int in_end = min(py1 + 6, H);
     const int n_rows = in_end - py0;
     const int n_chunks = (n_rows + S_R - 1) / S_R;
-    const int load_px = min(S_LW, W - x0);          // multiple of 16
-    const int own_px = min(S_OW, W - x0);           // pixels whose error this strip owns
-    const uint32_t row_bytes = (uint32_t)load_px * 3u;
+    const int own_px = min(S_OW, W - x0);           // pixels whose error this strip owns (multiple of 16)
     const int nwin_x = W - 6 - x0;                  // window columns available from x0
 
     if (tid == 0) {
@@ -157,21 +282,15 @@ k_ssim_strip(int H, int W, int seg_rows, const uint8_t* __restrict__ a_img, size
     __syncthreads();
 
     auto issue = [&](int chunk) {
-        // one warp issues the chunk's bulk copies (2 images x 7 rows), lane i -> row i
+        // one thread: two tile loads (original, reconstruction) of 7 rows x 240 bytes; rows past
+        // the image and columns past its right edge arrive as zeros
         const int buf = chunk & 1;
         const int y0 = py0 + chunk * S_R;
-        const int nr = min(S_R, in_end - y0);
-        if (tid == 0) mbar_expect_tx(&sm.bar[buf], row_bytes * 2u * (uint32_t)nr);
-        __syncwarp();
-        if (tid < 2 * S_R) {
-            const int img = tid / S_R, r = tid % S_R;
-            if (r < nr) {
-                const uint8_t* src = (img ? B : A) + ((size_t)(y0 + r) * W + x0) * 3;
-                bulk_g2s(&sm.raw[buf][img][r][0], src, row_bytes, &sm.bar[buf]);
-            }
-        }
+        mbar_expect_tx(&sm.bar[buf], 2u * S_R * S_ROWB);
+        tma_load_3d(&sm.raw[buf][0][0], &map_a, x0 * 3, y0, unit * a_unit_step, &sm.bar[buf]);
+        tma_load_3d(&sm.raw[buf][1][0], &map_b, x0 * 3, y0, unit * b_unit_step, &sm.bar[buf]);
     };
-    if (tid < 32) {
+    if (tid == 0) {
         issue(0);
         if (n_chunks > 1) issue(1);
     }
@@ -180,6 +299,11 @@ k_ssim_strip(int H, int W, int seg_rows, const uint8_t* __restrict__ a_img, size
     const int col = tid & (S_OW - 1);
     const int pair = tid >> 6;                      // warps 0,1: (R,G); warps 2,3: (B,Y)
     const int hidx = pair * S_OW + col;
+#if JDS_SSIM_ST64
+    // the two 8-byte halves of a 16-byte slot swap places in odd segments so that the 16 lanes
+    // of a half-warp (two segments x eight rows) store to 16 different bank pairs
+    const uint32_t h_swap = ((col >> 3) & 1) * 8;
+#endif
     HSum ring[S_R];
 #pragma unroll
     for (int i = 0; i < S_R; ++i) ring[i].sx = ring[i].sy = ring[i].sq = ring[i].sc = f2(0.f);
@@ -191,54 +315,68 @@ k_ssim_strip(int H, int W, int seg_rows, const uint8_t* __restrict__ a_img, size
     // quarter-warp is 7 rows of one segment: conflict free with the padded row pitches
     const int p1_row = tid & 7;
     const int p1_seg = (tid >> 3) & (S_NSEG - 1);
-    const int p1_pair = tid >> 6;
     const bool p1_active = p1_row < S_R;
-    const int p1_c0 = S_SEG * p1_seg;
+    const bool own_seg = S_SEG * p1_seg < own_px;            // own_px is a multiple of 16: whole segments
     double sse_a = 0.0, sse_b = 0.0;                // squared error of the pair's channels
 
-    // prep: bytes -> centred fp32, pairs (R,G) and (B,Y) interleaved; task = 4 pixels
-    auto prep = [&](int chunk) {
+    // prep: (B, Y) of both images, bytes -> centred fp32; task = 4 pixels of one (image, row).
+    // Tasks tl, tl + ts, ... below t1.
+    auto prep_tasks = [&](int chunk, int tl, int t1, int ts) {
         const int buf = chunk & 1;
-        const int nrp = min(S_R, in_end - (py0 + chunk * S_R));
-        mbar_wait(&sm.bar[buf], (uint32_t)((chunk >> 1) & 1));
-        // only the 72 columns pass 1 reads (64 windows + 6, rounded to a group of 4) are
-        // converted: 2 x 7 x 18 = 252 tasks = two rounds of the 128 threads
-        constexpr int PG = (S_OW + 6 + 3) / 4;
-        for (int task = tid; task < 2 * S_R * PG; task += S_NT) {
-            const int img = task / (S_R * PG);
-            const int rem = task % (S_R * PG);
-            const int r = rem / PG, g4 = rem % PG;
-            if (r < nrp) {
-                const uint32_t* w = reinterpret_cast<const uint32_t*>(&sm.raw[buf][img][r][12 * g4]);
-                const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
-                const float R0 = byte_centered<0>(w0), G0 = byte_centered<1>(w0), B0 = byte_centered<2>(w0);
-                const float R1 = byte_centered<3>(w0), G1 = byte_centered<0>(w1), B1 = byte_centered<1>(w1);
-                const float R2 = byte_centered<2>(w1), G2 = byte_centered<3>(w1), B2 = byte_centered<0>(w2);
-                const float R3 = byte_centered<1>(w2), G3 = byte_centered<2>(w2), B3 = byte_centered<3>(w2);
-                const float Y0 = fmaf(0.299f, R0, fmaf(0.587f, G0, 0.114f * B0));
-                const float Y1 = fmaf(0.299f, R1, fmaf(0.587f, G1, 0.114f * B1));
-                const float Y2 = fmaf(0.299f, R2, fmaf(0.587f, G2, 0.114f * B2));
-                const float Y3 = fmaf(0.299f, R3, fmaf(0.587f, G3, 0.114f * B3));
-                // pixels 4*g4 .. 4*g4+3 = pixel-pairs 2*g4 (even half) and 2*g4+1 (odd half):
-                // consecutive threads store consecutive float4 -> no bank conflicts
-                sm.fpl[img][0][r][g4] = make_float4(R0, G0, R1, G1);
-                sm.fpl[img][0][r][S_FHALF + g4] = make_float4(R2, G2, R3, G3);
-                sm.fpl[img][1][r][g4] = make_float4(B0, Y0, B1, Y1);
-                sm.fpl[img][1][r][S_FHALF + g4] = make_float4(B2, Y2, B3, Y3);
-            }
+        for (int task = tl; task < t1; task += ts) {
+            const int img = task / (S_R * S_PG);
+            const int rem = task - img * (S_R * S_PG);
+            const int r = rem / S_PG, g4 = rem - r * S_PG;
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(&sm.raw[buf][img][r * S_ROWB + 12 * g4]);
+            const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+            const float R0 = byte_centered<0>(w0), G0 = byte_centered<1>(w0), B0 = byte_centered<2>(w0);
+            const float R1 = byte_centered<3>(w0), G1 = byte_centered<0>(w1), B1 = byte_centered<1>(w1);
+            const float R2 = byte_centered<2>(w1), G2 = byte_centered<3>(w1), B2 = byte_centered<0>(w2);
+            const float R3 = byte_centered<1>(w2), G3 = byte_centered<2>(w2), B3 = byte_centered<3>(w2);
+            const float Y0 = fmaf(0.299f, R0, fmaf(0.587f, G0, 0.114f * B0));
+            const float Y1 = fmaf(0.299f, R1, fmaf(0.587f, G1, 0.114f * B1));
+            const float Y2 = fmaf(0.299f, R2, fmaf(0.587f, G2, 0.114f * B2));
+            const float Y3 = fmaf(0.299f, R3, fmaf(0.587f, G3, 0.114f * B3));
+            // pixels 4*g4 .. 4*g4+3 = pixel-pairs 2*g4 (even half) and 2*g4+1 (odd half):
+            // consecutive threads store consecutive float4 -> no bank conflicts
+            sm.by[buf][img][r][g4] = make_float4(B0, Y0, B1, Y1);
+            sm.by[buf][img][r][S_BHALF + g4] = make_float4(B2, Y2, B3, Y3);
         }
     };
-    prep(0);
+    constexpr int N_PREP = 2 * S_R * S_PG;          // 252 tasks per chunk
+#if JDS_SSIM_PREP_SPLIT
+    // (B,Y) threads: tasks [0,128) after their pass 1 (two each) and [192,252) after pass 2;
+    // (R,G) threads: tasks [128,192) after pass 2 (one each)
+    constexpr int PREP_A = 128, PREP_B0 = 192;
+#endif
+
+    // chunk 0: everyone waits for the first tiles and prepares (B,Y)
+    mbar_wait(&sm.bar[0], 0u);
+    prep_tasks(0, tid, N_PREP, S_NT);
     __syncthreads();
 
     // one vertical step of pass 2: take row r's horizontal sums, emit (optionally), drop the
     // row that leaves the 7-row window
-#define JDS_P2_STEP(r, EMIT)                                                             \
+#if JDS_SSIM_ST64
+    const uint32_t p2_xy = smem_u32(&sm.hxy[0][hidx]), p2_qc = smem_u32(&sm.hqc[0][hidx]);
+#define JDS_P2_LOAD(r, h)                                                                \
+    {                                                                                    \
+        const uint32_t ro = (uint32_t)(r) * (S_HPITCH * 16);                             \
+        h.sx = ld_shared_f2(p2_xy + ro + h_swap); h.sy = ld_shared_f2(p2_xy + ro + (8 - h_swap)); \
+        h.sq = ld_shared_f2(p2_qc + ro + h_swap); h.sc = ld_shared_f2(p2_qc + ro + (8 - h_swap)); \
+    }
+#else
+#define JDS_P2_LOAD(r, h)                                                                \
     {                                                                                    \
         const float4 h0 = sm.hxy[r][hidx], h1 = sm.hqc[r][hidx];                         \
-        HSum h;                                                                          \
         h.sx = f2(h0.x, h0.y); h.sy = f2(h0.z, h0.w);                                    \
         h.sq = f2(h1.x, h1.y); h.sc = f2(h1.z, h1.w);                                    \
+    }
+#endif
+#define JDS_P2_STEP(r, EMIT)                                                             \
+    {                                                                                    \
+        HSum h;                                                                          \
+        JDS_P2_LOAD(r, h)                                                                \
         ring[r] = h;                                                                     \
         acc.sx = __fadd2_rn(acc.sx, h.sx);                                               \
         acc.sy = __fadd2_rn(acc.sy, h.sy);                                               \
@@ -253,81 +391,38 @@ k_ssim_strip(int H, int W, int seg_rows, const uint8_t* __restrict__ a_img, size
     }
 
     for (int c = 0; c < n_chunks; ++c) {
-        // raw[c & 1] (chunk c) was consumed by prep(c) before the last barrier: refill it
-        if (tid < 32 && c + 2 < n_chunks) issue(c + 2);
+        const int buf = c & 1;
         const int y0 = py0 + c * S_R;
         const int nr = min(S_R, in_end - y0);
 
         // ---- pass 1: horizontal 7-tap sums of x, y, x^2+y^2, xy (sliding window) ---------
-        if (p1_active && p1_row < nr) {
-            // pixel-pair index of the segment's first pixel is 4 * seg (even): pairs alternate
-            // between the even and the odd half of the row
-            const float4* qa = &sm.fpl[0][p1_pair][p1_row][2 * p1_seg];
-            const float4* qb = &sm.fpl[1][p1_pair][p1_row][2 * p1_seg];
-            // sliding 7-tap window over 14 pixels, two pixels per 16-byte load; pixels are
-            // loaded just before they enter the window and dropped 7 steps later, so only a
-            // short history is live (register pressure decides the occupancy of this kernel)
-            const bool own_row = (y0 + p1_row) < py1;
-            const bool own_all = p1_c0 + S_SEG <= own_px;
-            float2 xs[S_SEG + 6], ys[S_SEG + 6];
-            float2 wx = f2(0.f), wy = f2(0.f), wq = f2(0.f), wc = f2(0.f), sse = f2(0.f);
-#if JDS_SSIM_SPLIT_Q
-            float2 wq2 = f2(0.f);
-#endif
-#pragma unroll
-            for (int i2 = 0; i2 < (S_SEG + 6) / 2; ++i2) {
-                const int off = (i2 & 1) * S_FHALF + (i2 >> 1);
-                const float4 a = qa[off], b = qb[off];
-                xs[2 * i2] = f2(a.x, a.y); xs[2 * i2 + 1] = f2(a.z, a.w);
-                ys[2 * i2] = f2(b.x, b.y); ys[2 * i2 + 1] = f2(b.z, b.w);
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const int i = 2 * i2 + k;
-                    if (i < S_SEG) {
-                        // squared error of the 8 pixels this task owns (exact: integer channels)
-                        const float2 d = sub2(xs[i], ys[i]);
-                        if (own_all || p1_c0 + i < own_px) sse = __ffma2_rn(d, d, sse);
-                    }
-                    wx = __fadd2_rn(wx, xs[i]);
-                    wy = __fadd2_rn(wy, ys[i]);
-#if JDS_SSIM_SPLIT_Q
-                    wq = __ffma2_rn(xs[i], xs[i], wq);
-                    wq2 = __ffma2_rn(ys[i], ys[i], wq2);
-#else
-                    wq = __ffma2_rn(xs[i], xs[i], __ffma2_rn(ys[i], ys[i], wq));
-#endif
-                    wc = __ffma2_rn(xs[i], ys[i], wc);
-                    if (i >= 6) {
-                        const int j = i - 6;
-                        sm.hxy[p1_row][p1_pair * S_OW + p1_c0 + j] = make_float4(wx.x, wx.y, wy.x, wy.y);
-#if JDS_SSIM_SPLIT_Q
-                        const float2 wqs = __fadd2_rn(wq, wq2);
-                        sm.hqc[p1_row][p1_pair * S_OW + p1_c0 + j] = make_float4(wqs.x, wqs.y, wc.x, wc.y);
-#else
-                        sm.hqc[p1_row][p1_pair * S_OW + p1_c0 + j] = make_float4(wq.x, wq.y, wc.x, wc.y);
-#endif
-                        if (j < S_SEG - 1) {
-                            const float2 ox = xs[j], oy = ys[j];
-                            const float2 nox = sub2(f2(0.f), ox), noy = sub2(f2(0.f), oy);
-                            wx = __fadd2_rn(wx, nox);
-                            wy = __fadd2_rn(wy, noy);
-#if JDS_SSIM_SPLIT_Q
-                            wq = __ffma2_rn(nox, ox, wq);
-                            wq2 = __ffma2_rn(noy, oy, wq2);
-#else
-                            wq = __ffma2_rn(nox, ox, __ffma2_rn(noy, oy, wq));
-#endif
-                            wc = __ffma2_rn(nox, oy, wc);
-                        }
-                    }
-                }
-            }
-            if (own_row) {
+        if (p1_active) {
+            const float2 sse = pair == 0 ? pass1_task<0>(sm, buf, p1_row, p1_seg)
+                                         : pass1_task<1>(sm, buf, p1_row, p1_seg);
+            if ((y0 + p1_row) < py1 && own_seg) {
                 sse_a += (double)sse.x;
                 sse_b += (double)sse.y;
             }
         }
+#if JDS_SSIM_PREP_SPLIT
+        if (pair == 1 && c + 1 < n_chunks) {
+            // first part of the next chunk's (B,Y) planes (the other buffer): evens out the byte
+            // conversion the (R,G) warps did above
+            mbar_wait(&sm.bar[buf ^ 1], (uint32_t)(((c + 1) >> 1) & 1));
+            prep_tasks(c + 1, tid - S_OW, PREP_A, S_OW);
+        }
+#endif
+#if JDS_SSIM_PAIRBAR && !JDS_SSIM_PREP_SPLIT
+        // hxy / hqc are private to a channel pair: only its own 64 threads (two warps) meet here,
+        // so the (B,Y) warps never wait for the byte conversion of the (R,G) warps
+        if (pair == 0) asm volatile("bar.sync 1, 64;" ::: "memory");
+        else asm volatile("bar.sync 2, 64;" ::: "memory");
+#else
         __syncthreads();
+#endif
+        // raw[buf] (chunk c) has been consumed - by prep(c) before the last full barrier and by
+        // the (R,G) threads just now (thread 0 is one of them): refill it with chunk c+2
+        if (tid == 0 && c + 2 < n_chunks) issue(c + 2);
 
         // ---- pass 2: vertical sliding sum + SSIM; then prep of the next chunk -------------
         {
@@ -361,19 +456,37 @@ k_ssim_strip(int H, int W, int seg_rows, const uint8_t* __restrict__ a_img, size
                 ssim_b += (double)ssum.y;
             }
         }
-        if (c + 1 < n_chunks) prep(c + 1);
+        if (c + 1 < n_chunks) {
+#if JDS_SSIM_PREP_SPLIT
+            if (pair == 0) {
+                mbar_wait(&sm.bar[buf ^ 1], (uint32_t)(((c + 1) >> 1) & 1));
+                prep_tasks(c + 1, PREP_A + tid, PREP_B0, S_OW);
+            } else {
+                prep_tasks(c + 1, PREP_B0 + tid - S_OW, N_PREP, S_OW);
+            }
+#elif JDS_SSIM_PAIRBAR
+            // the (B,Y) warps take the larger share: the (R,G) warps converted bytes in pass 1
+            mbar_wait(&sm.bar[buf ^ 1], (uint32_t)(((c + 1) >> 1) & 1));
+            if (pair == 1) prep_tasks(c + 1, tid - S_OW, JDS_SSIM_PREP_BY1, S_OW);
+            else prep_tasks(c + 1, JDS_SSIM_PREP_BY1 + tid, N_PREP, S_OW);
+#else
+            mbar_wait(&sm.bar[buf ^ 1], (uint32_t)(((c + 1) >> 1) & 1));
+            prep_tasks(c + 1, tid, N_PREP, S_NT);
+#endif
+        }
         __syncthreads();
     }
 #undef JDS_P2_STEP
+#undef JDS_P2_LOAD
 
     // ---- reductions ---------------------------------------------------------------
     const int lane = tid & 31, warp = tid >> 5;
-    // pass-1 pair varies inside a warp (56 tasks per pair): reduce per pair
+    // the pass-1 pair is warp uniform (warps 0,1: pair 0; warps 2,3: pair 1)
     double e[4];
-    e[0] = (p1_active && p1_pair == 0) ? sse_a : 0.0;
-    e[1] = (p1_active && p1_pair == 0) ? sse_b : 0.0;
-    e[2] = (p1_active && p1_pair == 1) ? sse_a : 0.0;
-    e[3] = (p1_active && p1_pair == 1) ? sse_b : 0.0;
+    e[0] = (p1_active && pair == 0) ? sse_a : 0.0;
+    e[1] = (p1_active && pair == 0) ? sse_b : 0.0;
+    e[2] = (p1_active && pair == 1) ? sse_a : 0.0;
+    e[3] = (p1_active && pair == 1) ? sse_b : 0.0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         ssim_a += __shfl_down_sync(0xffffffffu, ssim_a, o);
@@ -406,8 +519,38 @@ k_ssim_strip(int H, int W, int seg_rows, const uint8_t* __restrict__ a_img, size
 
 size_t ssim_strip_smem_bytes() { return sizeof(SsimSmem); }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    // resolved per call: the lookup is a table probe inside the runtime and keeps this file free
+    // of mutable statics (contexts on several threads / devices share nothing)
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(fn);
+}
+
+// bytes x rows x units view of `units` packed uint8 RGB frames; unit stride 0 = one shared frame
+static cudaError_t make_map(EncodeTiledFn enc, CUtensorMap* map, const uint8_t* base, int H, int W,
+                            size_t unit_stride, int units) {
+    const cuuint64_t dims[3] = {(cuuint64_t)W * 3, (cuuint64_t)H, (cuuint64_t)(unit_stride ? units : 1)};
+    const cuuint64_t strides[2] = {(cuuint64_t)W * 3, (cuuint64_t)(unit_stride ? unit_stride : (size_t)H * W * 3)};
+    const cuuint32_t box[3] = {(cuuint32_t)S_ROWB, (cuuint32_t)S_R, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), dims, strides,
+                           box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
 // once per context (jds_ctx_create): dynamic shared memory opt-in and the largest carve-out so
-// that four 54 KB CTAs fit an SM; idempotent, no state shared between contexts
+// that four CTAs fit an SM; idempotent, no state shared between contexts
 cudaError_t ssim_configure_device() {
     cudaError_t e = cudaFuncSetAttribute(k_ssim_strip, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(SsimSmem));
@@ -427,6 +570,12 @@ cudaError_t launch_ssim_strip(int H, int W, const uint8_t* a, size_t a_stride, c
                               size_t b_stride, DevMetrics* metrics, int units, bool want_ssim,
                               bool want_sse, int sm_count, cudaStream_t s) {
     const size_t smem = sizeof(SsimSmem);
+    const EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return cudaErrorNotSupported;
+    CUtensorMap map_a, map_b;
+    cudaError_t e = make_map(enc, &map_a, a, H, W, a_stride, units);
+    if (e == cudaSuccess) e = make_map(enc, &map_b, b, H, W, b_stride, units);
+    if (e != cudaSuccess) return e;
     const int strips = (W + S_OW - 1) / S_OW;
     // Vertical segments per strip.  More segments = more CTAs to balance over the 4 x sm_count
     // resident slots, but every segment re-reads 6 rows and pays a fixed prologue; fewer = a
@@ -459,8 +608,8 @@ cudaError_t launch_ssim_strip(int H, int W, const uint8_t* a, size_t a_stride, c
 #endif
     segs = (H + seg_rows - 1) / seg_rows;
     dim3 grid(strips, segs, units);
-    k_ssim_strip<<<grid, S_NT, smem, s>>>(H, W, seg_rows, a, a_stride, b, b_stride, metrics,
-                                          want_ssim ? 1 : 0, want_sse ? 1 : 0);
+    k_ssim_strip<<<grid, S_NT, smem, s>>>(map_a, map_b, H, W, seg_rows, a_stride ? 1 : 0, b_stride ? 1 : 0,
+                                          metrics, want_ssim ? 1 : 0, want_sse ? 1 : 0);
     return cudaGetLastError();
 }
 

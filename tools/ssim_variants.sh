@@ -1,7 +1,8 @@
 #!/bin/bash
-# Build libjds variants that differ only in jds_ssim.cu's tuning knobs (A/B runs on the GPU box):
+# Build libjds variants that differ only in jds_ssim.cu (A/B runs on the GPU box):
 #   tools/ssim_variants.sh            -> build/variants/libjds_<name>.so
 # then on the box:  for f in build/variants/*.so; do JDS_LIB=$f python tools/ssim_time.py; done
+# `v1` is the round-1 kernel (kept under build/ssim_v1 when present).
 set -e
 cd "$(dirname "$0")/.."
 CS=jpeg_dsp_studio_b200/csrc
@@ -12,15 +13,16 @@ for f in jds_api jds_kernels jds_fused jds_preview jds_ops jds_alias jds_entropy
   [ $OUT/obj/$f.o -nt $CS/$f.cu ] || nvcc $FLAGS -c $CS/$f.cu -o $OUT/obj/$f.o &
 done
 wait
-build() { # name, defines...
-  name=$1; shift
-  nvcc $FLAGS "$@" -c $CS/jds_ssim.cu -o $OUT/obj/ssim_$name.o
+build() { # name, source, defines...
+  name=$1; src=$2; shift; shift
+  nvcc $FLAGS -I$CS "$@" -c $src -o $OUT/obj/ssim_$name.o
   nvcc -shared -o $OUT/libjds_$name.so $OUT/obj/jds_*.o $OUT/obj/ssim_$name.o
 }
-build base &
-build ctas24 -DJDS_SSIM_CTAS_PER_SM=24 &
-build ctas32 -DJDS_SSIM_CTAS_PER_SM=32 &
-build ctas40 -DJDS_SSIM_CTAS_PER_SM=40 &
-build naive24 -DJDS_SSIM_COMPENSATED=0 -DJDS_SSIM_CTAS_PER_SM=24 &
+rm -f $OUT/libjds_*.so
+build base $CS/jds_ssim.cu &
+for v in "$@"; do   # extra variants: name:-DFLAG=1,-DOTHER=2
+  name=${v%%:*}; defs=${v#*:}
+  build $name $CS/jds_ssim.cu ${defs//,/ } &
+done
 wait
 ls -la $OUT/*.so
