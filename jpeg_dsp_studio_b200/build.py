@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libjds.so")
-SOURCES = ["jds_api.cu", "jds_kernels.cu", "jds_ssim.cu", "jds_fused.cu", "jds_preview.cu", "jds_ops.cu", "jds_alias.cu", "jds_entropy.cu"]
+SOURCES = ["jds_api.cu", "jds_kernels.cu", "jds_ssim.cu", "jds_fused.cu", "jds_fused_exact.cu", "jds_preview.cu", "jds_ops.cu", "jds_alias.cu", "jds_entropy.cu"]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-shared", "-Xcompiler", "-fPIC"]
 

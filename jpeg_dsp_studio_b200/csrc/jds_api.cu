@@ -163,6 +163,7 @@ extern "C" int jds_ctx_create(int device, jds_ctx** out) {
     e = fused_configure_device();
     if (e == cudaSuccess) e = ssim_configure_device();
     if (e == cudaSuccess) e = entropy_configure_device();
+    if (e == cudaSuccess) e = exact_fused_configure_device();
     if (e != cudaSuccess) {
         jds_ctx_destroy(c);
         return fail(JDS_ERR_CUDA, "kernel setup failed: %s", cudaGetErrorString(e));
@@ -441,6 +442,34 @@ static int launch_chunk(jds_ctx* c, const UnitJob& J, const ChunkPtrs& P, int n,
         ran[1] = true;
         ran[2] = false;
         ran[3] = true;      // squared errors always come from the strip kernel here
+        JDS_CUDA(launch_ssim_strip(g.H, g.W, P.d_rgb, P.rgb_stride, P.d_recon, frame_bytes,
+                                   P.d_metrics, n, want_ssim, true, c->sm_count, s));
+        c->launches++;
+    } else if (exact && !c->no_fused && !P.d_ey && !P.d_ergb && !g.general &&
+               fused_supported(g, p->prefilter, P.d_rgb, P.rgb_stride, P.d_recon, frame_bytes) &&
+               ssim_strip_supported(g.H, g.W, P.d_rgb, P.rgb_stride, P.d_recon, frame_bytes)) {
+        // exact mode on block-aligned frames: chroma through the staged forward / codec kernels
+        // (decimated planes only), luma + compose fused (jds_fused_exact.cu) - no fp64 luma planes
+        // in HBM; squared errors come from the strip kernel (integer SSE: psnr_rgb stays exact)
+        ran[0] = !J.shared_input || P.first_chunk;
+        if (ran[0]) {
+            launch_forward(true, g, p->prefilter, P.d_rgb, P.rgb_stride, fwd, fwd_stride,
+                           J.shared_input ? 1 : n, s, true);
+            c->launches++;
+        }
+        if (timed) JDS_CUDA(cudaEventRecord(evs[1], s));
+        launch_codec(true, g, fwd, fwd_stride, rec, rec_stride, P.d_tables, tstride, P.d_coeffs, ncoef,
+                     false, P.d_metrics, n, s, true);
+        JDS_CUDA(launch_exact_luma(g, P.d_rgb, P.rgb_stride, (const double*)rec, rec_stride, P.d_tables,
+                                   tstride, P.d_coeffs, ncoef, P.d_recon, frame_bytes, P.d_metrics, n, s));
+        c->launches += 2;
+        if (timed) {
+            JDS_CUDA(cudaEventRecord(evs[2], s));
+            JDS_CUDA(cudaEventRecord(evs[3], s));
+        }
+        ran[1] = true;
+        ran[2] = false;
+        ran[3] = true;
         JDS_CUDA(launch_ssim_strip(g.H, g.W, P.d_rgb, P.rgb_stride, P.d_recon, frame_bytes,
                                    P.d_metrics, n, want_ssim, true, c->sm_count, s));
         c->launches++;

@@ -46,6 +46,7 @@ inline void fill_tables(int quality, QTables* t) {
     for (int i = 0; i < 64; ++i) {
         volatile double r = 1.0 / t->q[i];        // correctly rounded reciprocal
         t->rq[i] = r;
+        t->dqx[i] = ldexp(t->q[i], -exact_coeff_shift(i) - 4);   // Q * 2^-shift / 16, exact
     }
     static double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};      // AAN scale factors, computed once
     if (s[0] == 0.0) {

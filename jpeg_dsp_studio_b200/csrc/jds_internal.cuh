@@ -30,12 +30,22 @@ struct DevMetrics {
     unsigned long long hist[50];
 };
 
+// Power-of-two scale the exact block codec keeps OUT of forward coefficient i = r * 8 + c (r:
+// vertical frequency, first axis, f = 1/16; c: horizontal frequency, second axis, f = 1):
+// true coefficient = 2^-exact_coeff_shift(i) * unscaled coefficient (jds_math.cuh, dct8_ref_unscaled)
+JDS_HD constexpr int exact_coeff_shift(int i) {
+    return 4 - dct8_pow2_shift(i >> 3) - dct8_pow2_shift(i & 7);
+}
+
 // Quantiser tables of one unit, in the arithmetic the policy needs.
-//   exact: q[i] = Q (fp64, integer valued), rq[i] = RN(1/Q);   fq, dq unused
+//   exact: q[i] = Q (fp64, integer valued), rq[i] = RN(1/Q), dqx[i] = Q * 2^-shift(i) / 16 (the
+//          dequantiser with the deferred power-of-two scales of the transforms folded in,
+//          BlockCodec<Exact>);   fq, dq unused
 //   fast : fq[i] = 1 / (Q * AAN_FWD[u] * AAN_FWD[v]);  dq[i] = Q * AAN_INV[u] * AAN_INV[v]
 struct QTables {
     double q[64];
     double rq[64];   // RN(1/Q): exact mode divides by Markstein's 3-operation sequence
+    double dqx[64];  // Q * exact_coeff_scale(i) / 16, exact (powers of two)
     float fq[64];
     float dq[64];
 };

@@ -32,7 +32,7 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
 template <class P, int SUB, bool PF>
 __global__ void __launch_bounds__(256)
 k_forward(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
-          typename P::T* __restrict__ fwd, size_t fwd_stride) {
+          typename P::T* __restrict__ fwd, size_t fwd_stride, int chroma_only) {
     const int cx = blockIdx.x * blockDim.x + threadIdx.x;
     const int cy = blockIdx.y * blockDim.y + threadIdx.y;
     if (cx >= g.wc || cy >= g.hc) return;
@@ -40,7 +40,7 @@ k_forward(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
     typename P::T* Y = fwd + (size_t)blockIdx.z * fwd_stride;
     typename P::T* Cb = Y + g.plane_y;
     typename P::T* Cr = Cb + g.plane_c;
-    forward_cell<P, SUB, PF>(g, in, cx, cy, Y, Cb, Cr);
+    forward_cell<P, SUB, PF>(g, in, cx, cy, chroma_only ? nullptr : Y, Cb, Cr);
 }
 
 // general geometry (odd width, or odd height under 4:2:0): one thread per luma pixel; the
@@ -69,7 +69,7 @@ k_codec(Geom g, const typename P::T* __restrict__ fwd, size_t fwd_stride,
         typename P::T* __restrict__ rec, size_t rec_stride,
         const QTables* __restrict__ tables, int table_stride,
         int16_t* __restrict__ coeffs, size_t coeff_stride,
-        DevMetrics* __restrict__ metrics) {
+        DevMetrics* __restrict__ metrics, long long first_block) {
     typedef typename P::T T;
     __shared__ QTables tb;
     __shared__ unsigned int s_hist[50];
@@ -79,6 +79,7 @@ k_codec(Geom g, const typename P::T* __restrict__ fwd, size_t fwd_stride,
         for (int i = threadIdx.x; i < 64; i += blockDim.x) {
             tb.q[i] = src->q[i];
             tb.rq[i] = src->rq[i];
+            tb.dqx[i] = src->dqx[i];
             tb.fq[i] = src->fq[i];
             tb.dq[i] = src->dq[i];
         }
@@ -88,7 +89,7 @@ k_codec(Geom g, const typename P::T* __restrict__ fwd, size_t fwd_stride,
     __syncthreads();
 
     const long long total = g.nblk_y + 2 * g.nblk_c;
-    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long b = first_block + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long bits = 0, nnz = 0;
     if (b < total) {
         // block -> (plane, bx, by); coefficient order is Y | Cb | Cr, block raster
@@ -576,7 +577,8 @@ void launch_block_ops(int op, long long n_blocks, const double* in, const int16_
 // ------------------------------------------------------------------------------
 template <class P>
 static void launch_forward_t(const Geom& g, int prefilter, const uint8_t* rgb, size_t rgb_stride,
-                             typename P::T* fwd, size_t fwd_stride, int units, cudaStream_t s) {
+                             typename P::T* fwd, size_t fwd_stride, int units, cudaStream_t s,
+                             int chroma_only) {
     if (g.general) {
         dim3 blk(32, 8), grid((g.W + 31) / 32, (g.H + 7) / 8, units);
         if (prefilter)
@@ -587,50 +589,55 @@ static void launch_forward_t(const Geom& g, int prefilter, const uint8_t* rgb, s
     }
     dim3 blk(32, 8), grid((g.wc + 31) / 32, (g.hc + 7) / 8, units);
     if (g.sub == 0)
-        k_forward<P, 0, false><<<grid, blk, 0, s>>>(g, rgb, rgb_stride, fwd, fwd_stride);
+        k_forward<P, 0, false><<<grid, blk, 0, s>>>(g, rgb, rgb_stride, fwd, fwd_stride, chroma_only);
     else if (g.sub == 1 && !prefilter)
-        k_forward<P, 1, false><<<grid, blk, 0, s>>>(g, rgb, rgb_stride, fwd, fwd_stride);
+        k_forward<P, 1, false><<<grid, blk, 0, s>>>(g, rgb, rgb_stride, fwd, fwd_stride, chroma_only);
     else if (g.sub == 1)
-        k_forward<P, 1, true><<<grid, blk, 0, s>>>(g, rgb, rgb_stride, fwd, fwd_stride);
+        k_forward<P, 1, true><<<grid, blk, 0, s>>>(g, rgb, rgb_stride, fwd, fwd_stride, chroma_only);
     else if (!prefilter)
-        k_forward<P, 2, false><<<grid, blk, 0, s>>>(g, rgb, rgb_stride, fwd, fwd_stride);
+        k_forward<P, 2, false><<<grid, blk, 0, s>>>(g, rgb, rgb_stride, fwd, fwd_stride, chroma_only);
     else
-        k_forward<P, 2, true><<<grid, blk, 0, s>>>(g, rgb, rgb_stride, fwd, fwd_stride);
+        k_forward<P, 2, true><<<grid, blk, 0, s>>>(g, rgb, rgb_stride, fwd, fwd_stride, chroma_only);
 }
 
 void launch_forward(bool exact, const Geom& g, int prefilter, const uint8_t* rgb,
-                    size_t rgb_stride, void* fwd, size_t fwd_stride, int units, cudaStream_t s) {
+                    size_t rgb_stride, void* fwd, size_t fwd_stride, int units, cudaStream_t s,
+                    bool chroma_only) {
+    // chroma_only (regular geometry only): the Y plane is neither computed nor written
+    const int co = (chroma_only && !g.general) ? 1 : 0;
     if (exact)
-        launch_forward_t<Exact>(g, prefilter, rgb, rgb_stride, (double*)fwd, fwd_stride, units, s);
+        launch_forward_t<Exact>(g, prefilter, rgb, rgb_stride, (double*)fwd, fwd_stride, units, s, co);
     else
-        launch_forward_t<Fast>(g, prefilter, rgb, rgb_stride, (float*)fwd, fwd_stride, units, s);
+        launch_forward_t<Fast>(g, prefilter, rgb, rgb_stride, (float*)fwd, fwd_stride, units, s, co);
 }
 
 template <class P>
 static void launch_codec_t(const Geom& g, const typename P::T* fwd, size_t fwd_stride,
                            typename P::T* rec, size_t rec_stride, const QTables* tables,
                            int table_stride, int16_t* coeffs, size_t coeff_stride, bool hist,
-                           DevMetrics* metrics, int units, cudaStream_t s) {
-    const long long total = g.nblk_y + 2 * g.nblk_c;
+                           DevMetrics* metrics, int units, cudaStream_t s, bool chroma_only) {
+    // chroma_only: the blocks of the Cb / Cr planes only (the fused exact luma kernel owns Y)
+    const long long first = chroma_only ? g.nblk_y : 0;
+    const long long total = g.nblk_y + 2 * g.nblk_c - first;
     dim3 blk(128), grid((unsigned)((total + 127) / 128), 1, units);
     if (hist)
         k_codec<P, true><<<grid, blk, 0, s>>>(g, fwd, fwd_stride, rec, rec_stride, tables,
-                                              table_stride, coeffs, coeff_stride, metrics);
+                                              table_stride, coeffs, coeff_stride, metrics, first);
     else
         k_codec<P, false><<<grid, blk, 0, s>>>(g, fwd, fwd_stride, rec, rec_stride, tables,
-                                               table_stride, coeffs, coeff_stride, metrics);
+                                               table_stride, coeffs, coeff_stride, metrics, first);
 }
 
 void launch_codec(bool exact, const Geom& g, const void* fwd, size_t fwd_stride, void* rec,
                   size_t rec_stride, const QTables* tables, int table_stride, int16_t* coeffs,
                   size_t coeff_stride, bool hist, DevMetrics* metrics, int units,
-                  cudaStream_t s) {
+                  cudaStream_t s, bool chroma_only) {
     if (exact)
         launch_codec_t<Exact>(g, (const double*)fwd, fwd_stride, (double*)rec, rec_stride, tables,
-                              table_stride, coeffs, coeff_stride, hist, metrics, units, s);
+                              table_stride, coeffs, coeff_stride, hist, metrics, units, s, chroma_only);
     else
         launch_codec_t<Fast>(g, (const float*)fwd, fwd_stride, (float*)rec, rec_stride, tables,
-                             table_stride, coeffs, coeff_stride, hist, metrics, units, s);
+                             table_stride, coeffs, coeff_stride, hist, metrics, units, s, chroma_only);
 }
 
 void launch_inverse(bool exact, const Geom& g, const uint8_t* rgb, size_t rgb_stride,

@@ -11,13 +11,16 @@ namespace jds {
 cudaError_t fused_configure_device();      // jds_fused.cu
 cudaError_t ssim_configure_device();       // jds_ssim.cu
 cudaError_t entropy_configure_device();    // jds_entropy.cu
+cudaError_t exact_fused_configure_device();   // jds_fused_exact.cu
 
 // strides are in elements of the buffer's type, per unit (0 = shared by all units)
 void launch_forward(bool exact, const Geom& g, int prefilter, const uint8_t* rgb,
-                    size_t rgb_stride, void* fwd, size_t fwd_stride, int units, cudaStream_t s);
+                    size_t rgb_stride, void* fwd, size_t fwd_stride, int units, cudaStream_t s,
+                    bool chroma_only = false);
 void launch_codec(bool exact, const Geom& g, const void* fwd, size_t fwd_stride, void* rec,
                   size_t rec_stride, const QTables* tables, int table_stride, int16_t* coeffs,
-                  size_t coeff_stride, bool hist, DevMetrics* metrics, int units, cudaStream_t s);
+                  size_t coeff_stride, bool hist, DevMetrics* metrics, int units, cudaStream_t s,
+                  bool chroma_only = false);
 void launch_inverse(bool exact, const Geom& g, const uint8_t* rgb, size_t rgb_stride,
                     const void* fwd, size_t fwd_stride, const void* rec, size_t rec_stride,
                     uint8_t* recon, size_t recon_stride, double* err_y, double* err_rgb,
@@ -44,6 +47,12 @@ cudaError_t launch_fused_luma(const Geom& g, const uint8_t* rgb, size_t rgb_stri
                               int table_stride, int16_t* coeffs, size_t coeff_stride,
                               uint8_t* recon, size_t recon_stride, DevMetrics* metrics, int units,
                               cudaStream_t s);
+// fused exact-mode luma + compose kernel (jds_fused_exact.cu): Y never touches HBM; `rec` holds
+// the reconstructed chroma planes the chroma-only k_codec wrote (plane layout of the staged path)
+cudaError_t launch_exact_luma(const Geom& g, const uint8_t* rgb, size_t rgb_stride, const double* rec,
+                              size_t rec_stride, const QTables* tables, int table_stride,
+                              int16_t* coeffs, size_t coeff_stride, uint8_t* recon,
+                              size_t recon_stride, DevMetrics* metrics, int units, cudaStream_t s);
 void launch_hist50(const int16_t* coeffs, size_t coeff_stride, size_t n_coeffs, DevMetrics* metrics,
                    int units, int sm_count, cudaStream_t s);
 constexpr int VALUE_HIST_BINS = 2048;          // int16 coefficient value v -> bin v + 1024

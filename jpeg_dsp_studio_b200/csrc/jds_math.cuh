@@ -16,6 +16,7 @@
 #pragma once
 #include <stdint.h>
 #include <math.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define JDS_HD __host__ __device__ __forceinline__
@@ -47,8 +48,43 @@ struct Exact {
 #endif
     static JDS_HD T rint_(T a) { return ::rint(a); }
     static JDS_HD T abs_(T a) { return ::fabs(a); }
-    static JDS_HD T clamp255(T a) { return ::fmin(::fmax(a, 0.0), 255.0); }
+    // np.clip(a, 0, 255) for finite a as two compares and selects (fmin / fmax in fp64 expand
+    // to ~14 instructions each for their NaN rules: a quarter of the exact luma kernel's
+    // instructions before this); -0.0 and negative values give +0.0
+    static JDS_HD T clamp255(T a) { return a > 0.0 ? (a > 255.0 ? 255.0 : a) : 0.0; }
 };
+
+// np.round(x).astype(int16) of a quotient |x| < 2^31 (engines/quantizer.py:24): adding
+// 1.5 * 2^52 rounds to the nearest integer, ties to even (one IEEE addition), and leaves that
+// integer in the low word of the sum; subtracting the constant again gives it as a double -
+// +0.0, never -0.0, like the reference's int16 -> float64 cast (quantizer.py:29).
+struct RoundedQuotient {
+    double value;   // the rounded quotient as fp64 (times 2^SHIFT)
+    int ivalue;     // the rounded quotient as an integer
+    int expo;       // biased exponent field of `value` (0 for zero): bit_length(|v|) = expo - 1022 - SHIFT
+};
+// `x` holds the quotient TIMES 2^SHIFT (the block codec keeps a power-of-two scale in its
+// coefficients).  Adding 1.5 * 2^(52+SHIFT) rounds x to a multiple of 2^SHIFT, i.e. the true
+// quotient to an integer (ties to even; the scaling is exact), and that integer again sits in
+// the low word of the sum.  SHIFT = 0 is plain np.round.
+template <int SHIFT>
+JDS_HD RoundedQuotient round_half_even(double x) {
+    RoundedQuotient r;
+    constexpr double MAGIC = 6755399441055744.0 * (double)(1ull << SHIFT);
+    const double t = Exact::add(x, MAGIC);
+    r.value = Exact::sub(t, MAGIC);
+#if defined(__CUDA_ARCH__)
+    r.ivalue = __double2loint(t);
+    r.expo = (__double2hiint(r.value) >> 20) & 0x7FF;
+#else
+    unsigned long long tb, vb;
+    memcpy(&tb, &t, 8);
+    memcpy(&vb, &r.value, 8);
+    r.ivalue = (int)(unsigned int)(tb & 0xFFFFFFFFull);
+    r.expo = (int)((vb >> 52) & 0x7FF);
+#endif
+    return r;
+}
 
 struct Fast {
     typedef float T;
@@ -250,6 +286,110 @@ JDS_HD void idct8_ref(typename P::T* c, typename P::T f) {
     r[6] = P::sub(ti, g[2]);
 #pragma unroll
     for (int i = 0; i < 8; ++i) r[i] = P::mul(r[i], f);
+#pragma unroll
+    for (int k = 1; k <= 5; k += 2) {
+        T a = r[k], b = r[k + 1];
+        r[k] = P::sub(a, b);
+        r[k + 1] = P::add(a, b);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i] = r[i];
+}
+
+// ------------------------------------------------------------------------------
+// The same transforms with every power-of-two multiplication DEFERRED (A5: "multiplications
+// by 2, 0.5, 1/16 are exact and may be moved / merged").  A multiplication by 2^k is exact and
+// commutes with every individually rounded operation - RN(2a + 2b) = 2 RN(a + b),
+// RN(T (2a)) = 2 RN(T a) - so the doublings of dct8_ref (c0, c7, h3, h7, p, q), its f scale
+// and the final halvings can be pulled out of the butterfly:
+//   dct8_ref(c, f)[k]  ==  dct8_pow2_scale(k) * f * dct8_ref_unscaled(c)[k]     bit for bit,
+// with dct8_pow2_scale(0) = dct8_pow2_scale(4) = 2 and 1 otherwise.  56 operations instead
+// of 78 (the block codec folds the scales into its quantiser tables, BlockCodec<Exact>).
+// ------------------------------------------------------------------------------
+JDS_HD constexpr int dct8_pow2_shift(int k) { return (k == 0 || k == 4) ? 1 : 0; }   // log2 of the scale
+
+template <class P>
+JDS_HD void dct8_ref_unscaled(typename P::T* c) {
+    typedef typename P::T T;
+    const T TW[7] = {T(JDS_T0), T(JDS_T1), T(JDS_T2), T(JDS_T3), T(JDS_T4), T(JDS_T5), T(JDS_T6)};
+    const T s07 = P::add(c[0], c[7]), d07 = P::sub(c[0], c[7]);       // h0 / 2, h4 / 2
+#pragma unroll
+    for (int k = 1; k <= 5; k += 2) {
+        T a = c[k + 1], b = c[k];
+        c[k + 1] = P::sub(a, b);
+        c[k] = P::add(a, b);
+    }
+    const T h1 = P::add(c[1], c[5]);
+    const T tr = P::sub(c[1], c[5]);
+    const T ti = P::add(c[2], c[6]);
+    const T h2 = P::sub(c[2], c[6]);
+    const T h6 = P::add(P::mul(T(JDS_WR), ti), P::mul(T(JDS_WI), tr));
+    const T h5 = P::sub(P::mul(T(JDS_WR), tr), P::mul(T(JDS_WI), ti));
+    T r[8];                                                           // r / 2 of dct8_ref
+    {
+        const T u = P::add(s07, c[3]), v = P::sub(s07, c[3]);         // h3 = 2 c3
+        r[0] = P::add(u, h1);
+        r[4] = P::sub(u, h1);
+        r[6] = P::add(v, h2);
+        r[2] = P::sub(v, h2);
+    }
+    {
+        const T u = P::sub(d07, c[4]), v = P::add(d07, c[4]);         // h7 = -2 c4
+        r[1] = P::add(u, h5);
+        r[5] = P::sub(u, h5);
+        r[7] = P::add(v, h6);
+        r[3] = P::sub(v, h6);
+    }
+    c[0] = P::mul(r[0], T(JDS_HALF_S2));
+#pragma unroll
+    for (int k = 1; k <= 3; ++k) {
+        const int kc = 8 - k;
+        T t1 = P::add(P::mul(TW[k - 1], r[kc]), P::mul(TW[kc - 1], r[k]));
+        T t2 = P::sub(P::mul(TW[k - 1], r[k]), P::mul(TW[kc - 1], r[kc]));
+        c[k] = P::add(t1, t2);
+        c[kc] = P::sub(t1, t2);
+    }
+    c[4] = P::mul(r[4], TW[3]);
+}
+
+// idct8_ref without its f scale: idct8_ref(c, f) == idct8_ref_unscaled(f * c) bit for bit (f a
+// power of two), so the caller scales the INPUT once (the block codec: in its dequantiser table)
+template <class P>
+JDS_HD void idct8_ref_unscaled(typename P::T* c) {
+    typedef typename P::T T;
+    const T TW[7] = {T(JDS_T0), T(JDS_T1), T(JDS_T2), T(JDS_T3), T(JDS_T4), T(JDS_T5), T(JDS_T6)};
+    c[0] = P::mul(c[0], T(JDS_S2));
+#pragma unroll
+    for (int k = 1; k <= 3; ++k) {
+        const int kc = 8 - k;
+        T t1 = P::add(c[k], c[kc]);
+        T t2 = P::sub(c[k], c[kc]);
+        c[k] = P::add(P::mul(TW[k - 1], t2), P::mul(TW[kc - 1], t1));
+        c[kc] = P::sub(P::mul(TW[k - 1], t1), P::mul(TW[kc - 1], t2));
+    }
+    c[4] = P::mul(c[4], T(2.0 * JDS_T3));
+    T g[8];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        T x0 = c[k], x1 = c[k + 2], x2 = c[k + 4], x3 = c[k + 6];
+        T tr1 = P::add(x3, x1);
+        g[4 * k + 2] = P::sub(x3, x1);
+        T tr2 = P::add(x0, x2);
+        g[4 * k + 1] = P::sub(x0, x2);
+        g[4 * k] = P::add(tr2, tr1);
+        g[4 * k + 3] = P::sub(tr2, tr1);
+    }
+    T r[8];
+    r[0] = P::add(g[0], g[4]);
+    r[7] = P::sub(g[0], g[4]);
+    r[4] = -g[7];
+    r[3] = g[3];
+    T tr = P::add(P::mul(T(JDS_WR), g[5]), P::mul(T(JDS_WI), g[6]));
+    T ti = P::sub(P::mul(T(JDS_WR), g[6]), P::mul(T(JDS_WI), g[5]));
+    r[1] = P::add(g[1], tr);
+    r[5] = P::sub(g[1], tr);
+    r[2] = P::add(ti, g[2]);
+    r[6] = P::sub(ti, g[2]);
 #pragma unroll
     for (int k = 1; k <= 5; k += 2) {
         T a = r[k], b = r[k + 1];

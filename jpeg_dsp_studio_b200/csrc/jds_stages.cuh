@@ -39,8 +39,12 @@ JDS_HD void forward_cell(const Geom& g, const uint8_t* __restrict__ rgb, int cx,
         for (int dx = 0; dx < CW; ++dx) {
             T r, gg, b, yy;
             load_rgb<P>(rgb, g.W, y0 + dy, x0 + dx, r, gg, b);
-            rgb_to_ycbcr<P>(r, gg, b, yy, cb[dy][dx], cr[dy][dx]);
-            Yp[(size_t)(y0 + dy) * g.Wp + (x0 + dx)] = yy;
+            if (Yp) {
+                rgb_to_ycbcr<P>(r, gg, b, yy, cb[dy][dx], cr[dy][dx]);
+                Yp[(size_t)(y0 + dy) * g.Wp + (x0 + dx)] = yy;
+            } else {                                  // chroma only (fused exact path: Y never
+                rgb_to_cbcr<P>(r, gg, b, cb[dy][dx], cr[dy][dx]);      // leaves the luma kernel)
+            }
         }
     if (SUB != 0 && PF) {
         // cv2.GaussianBlur(3x3, sigma 0.75) of the full-resolution chroma at the
@@ -213,6 +217,45 @@ struct BlockCodec;
 template <>
 struct BlockCodec<Exact> {
     // v: 64 samples (row-major) in, reconstructed samples out; q: quantised out.
+    //
+    // The arithmetic is SURVEY Appendix A5-A7 bit for bit, with the transforms' power-of-two
+    // multiplications deferred (dct8_ref_unscaled / idct8_ref_unscaled, jds_math.cuh): the
+    // forward coefficients stay multiplied by 2^shift(i) (exact_coeff_shift), which the
+    // quantiser absorbs - the correctly rounded quotient of a scaled value is the scaled
+    // quotient, the rounding constant is scaled with it, and the dequantiser table dqx carries
+    // 2^-shift together with the 1/16 of the inverse's first axis.
+    template <int I>
+    static JDS_HD void quant_one(double* v, int16_t* q, const QTables& tb, unsigned int* esum,
+                                 unsigned int* nnz, double* dct_out, double* deq_out) {
+        typedef Exact P;
+        constexpr int SH = exact_coeff_shift(I);
+        if (dct_out) dct_out[I] = P::mul(v[I], 1.0 / (double)(1 << SH));
+        // X / Q correctly rounded without the division subroutine (Markstein): with
+        // y = RN(1/Q), q0 = RN(X y), r = X - q0 Q (exact in one FMA), RN(q0 + r y) is the
+        // IEEE quotient for every integer Q in 1..255 (102 M cases incl. near-ties checked
+        // against x/Q in tests/emul; tests/test_device_math_on_cpu.py)
+        const double q0 = P::mul(v[I], tb.rq[I]);
+        const double rem = P::fma(-q0, tb.q[I], v[I]);
+        const RoundedQuotient rq = round_half_even<SH>(P::fma(rem, tb.rq[I], q0));
+        q[I] = (int16_t)rq.ivalue;
+        esum[SH] += (unsigned int)rq.expo;
+        nnz[SH] += ((unsigned int)rq.expo + 2047u) >> 11;       // 1 for every non-zero value
+        v[I] = P::mul(rq.value, tb.dqx[I]);     // = int16 * Q / 16: never -0.0 (quantizer.py:29)
+        if (deq_out) deq_out[I] = P::mul(v[I], 16.0);
+    }
+    template <int I0>
+    static JDS_HD void quant_row(double* v, int16_t* q, const QTables& tb, unsigned int* esum,
+                                 unsigned int* nnz, double* dct_out, double* deq_out) {
+        quant_one<I0 + 0>(v, q, tb, esum, nnz, dct_out, deq_out);
+        quant_one<I0 + 1>(v, q, tb, esum, nnz, dct_out, deq_out);
+        quant_one<I0 + 2>(v, q, tb, esum, nnz, dct_out, deq_out);
+        quant_one<I0 + 3>(v, q, tb, esum, nnz, dct_out, deq_out);
+        quant_one<I0 + 4>(v, q, tb, esum, nnz, dct_out, deq_out);
+        quant_one<I0 + 5>(v, q, tb, esum, nnz, dct_out, deq_out);
+        quant_one<I0 + 6>(v, q, tb, esum, nnz, dct_out, deq_out);
+        quant_one<I0 + 7>(v, q, tb, esum, nnz, dct_out, deq_out);
+    }
+
     static JDS_HD void run(double* v, int16_t* q, const QTables& tb, BlockStats& st,
                            double* dct_out, double* deq_out) {
         typedef Exact P;
@@ -224,43 +267,43 @@ struct BlockCodec<Exact> {
             double t[8];
 #pragma unroll
             for (int r = 0; r < 8; ++r) t[r] = v[r * 8 + c];
-            dct8_ref<P>(t, 0.0625);
+            dct8_ref_unscaled<P>(t);
 #pragma unroll
             for (int r = 0; r < 8; ++r) v[r * 8 + c] = t[r];
         }
 #pragma unroll
-        for (int r = 0; r < 8; ++r) dct8_ref<P>(v + r * 8, 1.0);
-        unsigned int bits = 0, nnz = 0;
+        for (int r = 0; r < 8; ++r) dct8_ref_unscaled<P>(v + r * 8);
+        // bit model (utils/metrics.py:75-79): 6 + ceil(log2(|v|+1)) + 1 = 7 + bit_length(|v|)
+        // per non-zero value; bit_length comes from the exponent field of the rounded (still
+        // scaled) quotient: biased exponent - 1022 - shift, summed per shift class
+        unsigned int esum[5] = {0, 0, 0, 0, 0}, nnz[5] = {0, 0, 0, 0, 0};
+        quant_row<0>(v, q, tb, esum, nnz, dct_out, deq_out);
+        quant_row<8>(v, q, tb, esum, nnz, dct_out, deq_out);
+        quant_row<16>(v, q, tb, esum, nnz, dct_out, deq_out);
+        quant_row<24>(v, q, tb, esum, nnz, dct_out, deq_out);
+        quant_row<32>(v, q, tb, esum, nnz, dct_out, deq_out);
+        quant_row<40>(v, q, tb, esum, nnz, dct_out, deq_out);
+        quant_row<48>(v, q, tb, esum, nnz, dct_out, deq_out);
+        quant_row<56>(v, q, tb, esum, nnz, dct_out, deq_out);
+        unsigned int bits = 0, n = 0;
 #pragma unroll
-        for (int i = 0; i < 64; ++i) {
-            if (dct_out) dct_out[i] = v[i];
-            // X / Q correctly rounded without the division subroutine (Markstein): with
-            // y = RN(1/Q), q0 = RN(X y), r = X - q0 Q (exact in one FMA), RN(q0 + r y) is the
-            // IEEE quotient for every integer Q in 1..255 (102 M cases incl. near-ties checked
-            // against x/Q in tests/emul; tests/test_device_math_on_cpu.py)
-            const double q0 = P::mul(v[i], tb.rq[i]);
-            const double rem = P::fma(-q0, tb.q[i], v[i]);
-            const double qv = P::rint_(P::fma(rem, tb.rq[i], q0));
-            const int qi = (int)qv;
-            q[i] = (int16_t)qi;
-            bits += coeff_bits(qi);
-            nnz += (qi != 0);
-            v[i] = P::mul((double)qi, tb.q[i]);     // int16 -> fp64: never -0.0 (quantizer.py:29)
-            if (deq_out) deq_out[i] = v[i];
+        for (int sh = 2; sh <= 4; ++sh) {       // the shifts that occur: 2, 3, 4
+            bits += esum[sh] - (1015u + (unsigned)sh) * nnz[sh];
+            n += nnz[sh];
         }
         st.bits = bits;
-        st.nnz = nnz;
+        st.nnz = n;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             double t[8];
 #pragma unroll
             for (int r = 0; r < 8; ++r) t[r] = v[r * 8 + c];
-            idct8_ref<P>(t, 0.0625);
+            idct8_ref_unscaled<P>(t);
 #pragma unroll
             for (int r = 0; r < 8; ++r) v[r * 8 + c] = t[r];
         }
 #pragma unroll
-        for (int r = 0; r < 8; ++r) idct8_ref<P>(v + r * 8, 1.0);
+        for (int r = 0; r < 8; ++r) idct8_ref_unscaled<P>(v + r * 8);
 #pragma unroll
         for (int i = 0; i < 64; ++i) v[i] = P::clamp255(P::add(v[i], 128.0));
     }

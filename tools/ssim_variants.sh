@@ -9,7 +9,7 @@ CS=jpeg_dsp_studio_b200/csrc
 OUT=build/variants
 mkdir -p $OUT/obj
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC"
-for f in jds_api jds_kernels jds_fused jds_preview jds_ops jds_alias jds_entropy; do
+for f in jds_api jds_kernels jds_fused jds_fused_exact jds_preview jds_ops jds_alias jds_entropy; do
   [ $OUT/obj/$f.o -nt $CS/$f.cu ] || nvcc $FLAGS -c $CS/$f.cu -o $OUT/obj/$f.o &
 done
 wait
