@@ -64,7 +64,7 @@ struct jds_ctx {
     int plan_chunk = 1;
     double stage_ms[4] = {0, 0, 0, 0};   // forward, codec, inverse, ssim (accumulated)
     uint64_t stage_launches[4] = {0, 0, 0, 0};
-    DevBuf planes, in, recon, coeffs, errs, metrics, tables, selected, payload, alias;
+    DevBuf planes, in, recon, coeffs, errs, metrics, tables, selected, payload, alias, fcoef;
     void* h_metrics = nullptr;   // pinned
     size_t h_metrics_bytes = 0;
     void* h_tables = nullptr;    // pinned
@@ -75,6 +75,7 @@ struct jds_ctx {
     size_t l2_bytes = (size_t)96 << 20;
     bool legacy_ssim = false;     // JDS_LEGACY_SSIM=1: use the tile kernel (debug / A-B runs)
     bool no_fused = false;        // JDS_NO_FUSED=1: fast mode through the staged kernels
+    bool no_hoist = false;        // JDS_NO_HOIST=1: sweeps redo the forward half per point (A/B runs)
     bool l2_chunking = false;     // JDS_L2_CHUNK=1: size launches so a frame sequence stays in L2
     bool stage_timing = false;    // per-kernel CUDA events (jds_ctx_stage_timing)
     // jds_sweep_records returns without synchronising: its table uploads are staged in a ring
@@ -178,6 +179,8 @@ extern "C" int jds_ctx_create(int device, jds_ctx** out) {
     c->legacy_ssim = ls && atoi(ls) != 0;
     const char* nf = getenv("JDS_NO_FUSED");
     c->no_fused = nf && atoi(nf) != 0;
+    const char* nh = getenv("JDS_NO_HOIST");
+    c->no_hoist = nh && atoi(nh) != 0;
     const char* l2c = getenv("JDS_L2_CHUNK");
     c->l2_chunking = l2c && atoi(l2c) != 0;
     const char* mb = getenv("JDS_SCRATCH_MB");
@@ -191,7 +194,7 @@ extern "C" int jds_ctx_destroy(jds_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->planes, &c->in, &c->recon, &c->coeffs, &c->errs,
-                      &c->metrics, &c->tables, &c->selected, &c->payload, &c->alias};
+                      &c->metrics, &c->tables, &c->selected, &c->payload, &c->alias, &c->fcoef};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->h_metrics) cudaFreeHost(c->h_metrics);
@@ -393,6 +396,7 @@ struct ChunkPtrs {
     const QTables* d_tables;
     DevMetrics* d_metrics;
     bool first_chunk;
+    bool hoist;                 // sweep: forward half once per frame (c->fcoef), see launch_chunk
 };
 
 static int launch_chunk(jds_ctx* c, const UnitJob& J, const ChunkPtrs& P, int n, cudaStream_t s,
@@ -425,15 +429,28 @@ static int launch_chunk(jds_ctx* c, const UnitJob& J, const ChunkPtrs& P, int n,
         const size_t cpl_stride = fused_chroma_plane_floats(g);
         // each compute stream has its own chroma-plane scratch
         float* cpl = (float*)c->planes.p + (size_t)scratch_slot * cpl_stride * (size_t)c->plan_chunk;
+        // sweeps (one shared frame, metrics only): the quality-independent forward half - colour,
+        // decimation / prefilter, forward DCT - runs once per frame into c->fcoef (first chunk),
+        // every quality point then starts at quantisation (gui/worker.py:55-74 redoes it all)
+        const bool hoist = P.hoist;
+        float* fcoef = hoist ? (float*)c->fcoef.p : nullptr;
+        const int stage = hoist ? 2 : 0;
+        if (hoist && P.first_chunk) {
+            JDS_CUDA(launch_fused_chroma(g, p->prefilter, P.d_rgb, 0, nullptr, 0, nullptr, 0, nullptr, 0,
+                                         nullptr, 1, s, 1, fcoef));
+            JDS_CUDA(launch_fused_luma(g, P.d_rgb, 0, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0, nullptr,
+                                       1, s, 1, fcoef));
+            c->launches += 2;
+        }
         ran[0] = g.sub != 0;
         if (ran[0]) {
             JDS_CUDA(launch_fused_chroma(g, p->prefilter, P.d_rgb, P.rgb_stride, cpl, cpl_stride, P.d_tables,
-                                         tstride, P.d_coeffs, ncoef, P.d_metrics, n, s));
+                                         tstride, P.d_coeffs, ncoef, P.d_metrics, n, s, stage, fcoef));
             c->launches++;
         }
         if (timed) JDS_CUDA(cudaEventRecord(evs[1], s));
         JDS_CUDA(launch_fused_luma(g, P.d_rgb, P.rgb_stride, cpl, cpl_stride, P.d_tables, tstride,
-                                   P.d_coeffs, ncoef, P.d_recon, frame_bytes, P.d_metrics, n, s));
+                                   P.d_coeffs, ncoef, P.d_recon, frame_bytes, P.d_metrics, n, s, stage, fcoef));
         c->launches++;
         if (timed) {
             JDS_CUDA(cudaEventRecord(evs[2], s));
@@ -451,18 +468,28 @@ static int launch_chunk(jds_ctx* c, const UnitJob& J, const ChunkPtrs& P, int n,
         // exact mode on block-aligned frames: chroma through the staged forward / codec kernels
         // (decimated planes only), luma + compose fused (jds_fused_exact.cu) - no fp64 luma planes
         // in HBM; squared errors come from the strip kernel (integer SSE: psnr_rgb stays exact)
-        ran[0] = !J.shared_input || P.first_chunk;
-        if (ran[0]) {
-            launch_forward(true, g, p->prefilter, P.d_rgb, P.rgb_stride, fwd, fwd_stride,
-                           J.shared_input ? 1 : n, s, true);
+        if (exact_chroma_supported(g, p->prefilter)) {
+            // decimation + chroma codec in one kernel (stage "forward_colour" in the timings)
+            ran[0] = true;
+            JDS_CUDA(launch_exact_chroma(g, P.d_rgb, P.rgb_stride, (double*)rec, rec_stride, P.d_tables,
+                                         tstride, P.d_coeffs, ncoef, P.d_metrics, n, s));
+            c->launches++;
+            if (timed) JDS_CUDA(cudaEventRecord(evs[1], s));
+        } else {
+            ran[0] = !J.shared_input || P.first_chunk;
+            if (ran[0]) {
+                launch_forward(true, g, p->prefilter, P.d_rgb, P.rgb_stride, fwd, fwd_stride,
+                               J.shared_input ? 1 : n, s, true);
+                c->launches++;
+            }
+            if (timed) JDS_CUDA(cudaEventRecord(evs[1], s));
+            launch_codec(true, g, fwd, fwd_stride, rec, rec_stride, P.d_tables, tstride, P.d_coeffs, ncoef,
+                         false, P.d_metrics, n, s, true);
             c->launches++;
         }
-        if (timed) JDS_CUDA(cudaEventRecord(evs[1], s));
-        launch_codec(true, g, fwd, fwd_stride, rec, rec_stride, P.d_tables, tstride, P.d_coeffs, ncoef,
-                     false, P.d_metrics, n, s, true);
         JDS_CUDA(launch_exact_luma(g, P.d_rgb, P.rgb_stride, (const double*)rec, rec_stride, P.d_tables,
                                    tstride, P.d_coeffs, ncoef, P.d_recon, frame_bytes, P.d_metrics, n, s));
-        c->launches += 2;
+        c->launches++;
         if (timed) {
             JDS_CUDA(cudaEventRecord(evs[2], s));
             JDS_CUDA(cudaEventRecord(evs[3], s));
@@ -580,7 +607,11 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
     const bool will_fuse = !exact && !c->no_fused && !want_ey && !want_ergb &&
                            fused_supported(g, p->prefilter, probe_in, frame_bytes, probe_out, frame_bytes) &&
                            ssim_strip_supported(g.H, g.W, probe_in, frame_bytes, probe_out, frame_bytes);
-    const bool dual = c->l2_chunking && will_fuse && !c->stage_timing && J.units > chunk;
+    // hoisted sweep: one shared frame, fused kernels, metrics (and optionally recon) only
+    const bool hoist = J.shared_input && will_fuse && J.units > 1 && !want_coeffs && !want_hist &&
+                       fused_fcoef_floats(g) > 0 && !c->no_hoist;
+    // (a hoisted sweep's pre-pass runs on the first stream only: no second compute stream)
+    const bool dual = c->l2_chunking && will_fuse && !c->stage_timing && J.units > chunk && !hoist;
     const int nscr = (pipelined || dual) ? 2 : 1;        // recon / coefficient scratch slots
 
     int rc;
@@ -591,6 +622,7 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
         if (dual && need2 > need) need = need2;
         if ((rc = ensure(c, c->planes, need))) return rc;
     }
+    if (hoist && (rc = ensure(c, c->fcoef, fused_fcoef_floats(g) * sizeof(float)))) return rc;
     if ((rc = ensure(c, c->metrics, sizeof(DevMetrics) * (size_t)J.units))) return rc;
     const int n_tables_total = J.qualities ? J.units : 1;
     if ((rc = ensure(c, c->tables, sizeof(QTables) * (size_t)n_tables_total))) return rc;
@@ -656,6 +688,7 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
         cudaStream_t cs = slot ? c->stream2 : s;           // compute stream of this chunk
         ChunkPtrs P;
         P.first_chunk = (u0 == 0);
+        P.hoist = hoist;
         P.d_tables = d_tables + (J.qualities ? u0 : 0);
         P.d_metrics = d_metrics + u0;
         // --- inputs ---

@@ -108,10 +108,9 @@ __device__ __forceinline__ void idct8_aan_sat(float* d) {
 // clamped to [0,1].  s_fq / s_dq: shared-memory tables (dq already divided by 255).
 // esum accumulates the fp32 exponent fields of the non-zero quantised values
 // (bits = esum - 119 * nnz, utils/metrics.py:75-79), nnz their count.
-template <bool COEFFS>
-__device__ __forceinline__ void codec_fast(float* v, const float* __restrict__ s_fq,
-                                           const float* __restrict__ s_dq, unsigned& esum,
-                                           unsigned& nnz, int16_t* __restrict__ coef_out) {
+// Forward half of the block codec: level-shifted samples in v (row-major) -> scaled AAN DCT
+// coefficients (quality independent: a sweep computes them once per frame).
+__device__ __forceinline__ void codec_fast_fwd(float* v) {
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
         float t[8];
@@ -123,7 +122,16 @@ __device__ __forceinline__ void codec_fast(float* v, const float* __restrict__ s
     }
 #pragma unroll
     for (int r = 0; r < 8; ++r) dct8_aan(v + r * 8);
+}
 
+// Back half: coefficients -> quantise, bit model, dequantise, IDCT -> reconstructed samples
+// / 255 clamped to [0,1].  s_fq / s_dq: shared-memory tables (dq already divided by 255).
+// esum accumulates the fp32 exponent fields of the non-zero quantised values
+// (bits = esum - 119 * nnz, utils/metrics.py:75-79), nnz their count.
+template <bool COEFFS>
+__device__ __forceinline__ void codec_fast_back(float* v, const float* __restrict__ s_fq,
+                                                const float* __restrict__ s_dq, unsigned& esum,
+                                                unsigned& nnz, int16_t* __restrict__ coef_out) {
     unsigned e_acc = 0, n_acc = 0;
     uint32_t packed[32];
 #pragma unroll
@@ -167,6 +175,42 @@ __device__ __forceinline__ void codec_fast(float* v, const float* __restrict__ s
     }
 #pragma unroll
     for (int r = 0; r < 8; ++r) idct8_aan_sat(v + r * 8);
+}
+
+// One 8x8 block, level-shifted samples in v (row-major) -> reconstructed samples / 255
+template <bool COEFFS>
+__device__ __forceinline__ void codec_fast(float* v, const float* __restrict__ s_fq,
+                                           const float* __restrict__ s_dq, unsigned& esum,
+                                           unsigned& nnz, int16_t* __restrict__ coef_out) {
+    codec_fast_fwd(v);
+    codec_fast_back<COEFFS>(v, s_fq, s_dq, esum, nnz, coef_out);
+}
+
+// Hoisted sweeps (gui/worker.py:55-74 recomputes everything per quality; only quantisation
+// onwards depends on it): the forward coefficients of a frame live in a scratch buffer, one
+// 8 KB region per warp of the producing grid - float4 number i4 of the warp's lane L at
+// (i4 * 32 + L) * 16 bytes, so every 16-byte access of a warp is one contiguous 512-byte piece.
+// STAGE 0: the full kernel; 1: forward half only (writes the scratch, nothing else);
+// 2: back half only (reads the scratch instead of the frame).
+enum { STAGE_FULL = 0, STAGE_FWD = 1, STAGE_BACK = 2 };
+constexpr size_t FCOEF_WARP_FLOATS = 32 * 64;
+
+__device__ __forceinline__ float4* fcoef_warp_base(float* fcoef, int warps_per_cta) {
+    const size_t cta = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+    return reinterpret_cast<float4*>(fcoef + (cta * warps_per_cta + (threadIdx.x >> 5)) * FCOEF_WARP_FLOATS) +
+           (threadIdx.x & 31);
+}
+__device__ __forceinline__ void fcoef_store(float4* base, const float* v) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+        base[i * 32] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+__device__ __forceinline__ void fcoef_load(const float4* base, float* v) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const float4 a = base[i * 32];
+        v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = a.z; v[4 * i + 3] = a.w;
+    }
 }
 
 __device__ __forceinline__ void load_tables(const QTables* __restrict__ src, float* s_fq,
@@ -213,28 +257,38 @@ struct ChromaSmem {
 };
 
 // codec of the chroma tile: thread t -> channel t/64, block t%64 of plane[2][64][68]
-template <bool COEFFS>
+template <bool COEFFS, int STAGE>
 __device__ __forceinline__ void chroma_codec_tail(
     const Geom& g, float (*plane)[CA_BX * CA_BY][BLK_STRIDE], const float* s_fq, const float* s_dq,
     int bx0, int by0, int unit, float* __restrict__ cplanes, size_t cplane_stride,
-    int16_t* __restrict__ coeffs, size_t coeff_stride, DevMetrics* __restrict__ metrics) {
+    int16_t* __restrict__ coeffs, size_t coeff_stride, DevMetrics* __restrict__ metrics,
+    float* __restrict__ fcoef) {
     const int tid = threadIdx.x;
     const int ch = tid >> 6, blk = tid & 63;
     const int bx = bx0 + (blk & (CA_BX - 1)), by = by0 + (blk >> 4);
     unsigned esum = 0, nnz = 0;
     if (bx < g.nbx_c && by < g.nby_c) {
         float v[64];
-        const float4* src = reinterpret_cast<const float4*>(&plane[ch][blk][0]);
+        if (STAGE == STAGE_BACK) {
+            fcoef_load(fcoef_warp_base(fcoef, CA_NT / 32), v);
+        } else {
+            const float4* src = reinterpret_cast<const float4*>(&plane[ch][blk][0]);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const float4 a = src[i];
-            v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = a.z; v[4 * i + 3] = a.w;
+            for (int i = 0; i < 16; ++i) {
+                const float4 a = src[i];
+                v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = a.z; v[4 * i + 3] = a.w;
+            }
+            codec_fast_fwd(v);
+        }
+        if (STAGE == STAGE_FWD) {
+            fcoef_store(fcoef_warp_base(fcoef, CA_NT / 32), v);
+            return;
         }
         int16_t* cout = nullptr;
         if (COEFFS)
             cout = coeffs + (size_t)unit * coeff_stride +
                    ((size_t)g.nblk_y + (size_t)ch * g.nblk_c + (size_t)by * g.nbx_c + bx) * 64;
-        codec_fast<COEFFS>(v, s_fq, s_dq, esum, nnz, cout);
+        codec_fast_back<COEFFS>(v, s_fq, s_dq, esum, nnz, cout);
         float* dst = cplanes + (size_t)unit * cplane_stride + (size_t)ch * g.plane_c +
                      (size_t)(by * 8) * g.wcp + bx * 8;
 #pragma unroll
@@ -244,15 +298,16 @@ __device__ __forceinline__ void chroma_codec_tail(
             d4[1] = make_float4(v[r * 8 + 4], v[r * 8 + 5], v[r * 8 + 6], v[r * 8 + 7]);
         }
     }
-    flush_stats(esum, nnz, metrics + unit);
+    if (STAGE != STAGE_FWD) flush_stats(esum, nnz, metrics + unit);
 }
 
-template <int SUB, bool COEFFS>
+template <int SUB, bool COEFFS, int STAGE>
 __global__ void __launch_bounds__(CA_NT)
 k_fast_chroma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
               float* __restrict__ cplanes, size_t cplane_stride,
               const QTables* __restrict__ tables, int table_stride,
-              int16_t* __restrict__ coeffs, size_t coeff_stride, DevMetrics* __restrict__ metrics) {
+              int16_t* __restrict__ coeffs, size_t coeff_stride, DevMetrics* __restrict__ metrics,
+              float* __restrict__ fcoef) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ChromaSmem<SUB>& sm = *reinterpret_cast<ChromaSmem<SUB>*>(smem_raw);
     constexpr int VS = (SUB == 2) ? 2 : 1;            // luma rows per chroma row
@@ -265,7 +320,14 @@ k_fast_chroma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
     const int n_rows = min(ROWS, g.H - y0);
     const int n_px = min(CA_BX * 16, g.W - x0);
 
-    load_tables(tables + (size_t)unit * table_stride, sm.fq, sm.dq, tid, CA_NT);
+    if (STAGE != STAGE_FWD) load_tables(tables + (size_t)unit * table_stride, sm.fq, sm.dq, tid, CA_NT);
+    if (STAGE == STAGE_BACK) {
+        // hoisted sweep: the forward coefficients of this tile come from the scratch
+        __syncthreads();
+        chroma_codec_tail<COEFFS, STAGE>(g, sm.plane, sm.fq, sm.dq, bx0, by0, unit, cplanes, cplane_stride,
+                                         coeffs, coeff_stride, metrics, fcoef);
+        return;
+    }
 
     // ---- decimation: a task = one chroma row x 8 chroma samples (16 luma pixels) ----
     // channel sums over the 2x1 / 2x2 footprint with IDP4A on the interleaved bytes,
@@ -344,8 +406,8 @@ k_fast_chroma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
     }
     __syncthreads();
 
-    chroma_codec_tail<COEFFS>(g, sm.plane, sm.fq, sm.dq, bx0, by0, unit, cplanes, cplane_stride,
-                              coeffs, coeff_stride, metrics);
+    chroma_codec_tail<COEFFS, STAGE>(g, sm.plane, sm.fq, sm.dq, bx0, by0, unit, cplanes, cplane_stride,
+                                     coeffs, coeff_stride, metrics, fcoef);
 }
 
 // ------------------------------------------------------------------------------
@@ -366,13 +428,13 @@ struct ChromaPfSmem {
     alignas(16) float dq[64];
 };
 
-template <int SUB, bool COEFFS>
+template <int SUB, bool COEFFS, int STAGE>
 __global__ void __launch_bounds__(CA_NT)
 k_fast_chroma_pf(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
                  float* __restrict__ cplanes, size_t cplane_stride,
                  const QTables* __restrict__ tables, int table_stride,
                  int16_t* __restrict__ coeffs, size_t coeff_stride,
-                 DevMetrics* __restrict__ metrics) {
+                 DevMetrics* __restrict__ metrics, float* __restrict__ fcoef) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ChromaPfSmem<SUB>& sm = *reinterpret_cast<ChromaPfSmem<SUB>*>(smem_raw);
     constexpr int VS = (SUB == 2) ? 2 : 1;
@@ -386,7 +448,7 @@ k_fast_chroma_pf(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
     const int x0 = bx0 * 16, y0 = by0 * 8 * VS;
     const int n_rows = min(LROWS - 2, g.H - y0);                          // tile's own luma rows
     const int n_px = min(CA_BX * 16, g.W - x0);
-    load_tables(tables + (size_t)unit * table_stride, sm.fq, sm.dq, tid, CA_NT);
+    if (STAGE != STAGE_FWD) load_tables(tables + (size_t)unit * table_stride, sm.fq, sm.dq, tid, CA_NT);
 
     // ---- phase A: a task = one luma row (halo rows included) x 16 pixels -> 8 samples ----
     for (int task = tid; task < LROWS * CA_BX; task += CA_NT) {
@@ -480,8 +542,8 @@ k_fast_chroma_pf(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
         pr[1] = make_float4(orr[4], orr[5], orr[6], orr[7]);
     }
     __syncthreads();
-    chroma_codec_tail<COEFFS>(g, sm.plane, sm.fq, sm.dq, bx0, by0, unit, cplanes, cplane_stride,
-                              coeffs, coeff_stride, metrics);
+    chroma_codec_tail<COEFFS, STAGE>(g, sm.plane, sm.fq, sm.dq, bx0, by0, unit, cplanes, cplane_stride,
+                                     coeffs, coeff_stride, metrics, fcoef);
 }
 
 // ------------------------------------------------------------------------------
@@ -528,13 +590,14 @@ __device__ __forceinline__ void stage_up16(const float* src, bool left_edge, boo
     upsample_row16(c, o);
 }
 
-template <int SUB, bool COEFFS>
+template <int SUB, bool COEFFS, int STAGE>
 __global__ void __launch_bounds__(LU_NT)
 k_fast_luma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
             const float* __restrict__ cplanes, size_t cplane_stride,
             const QTables* __restrict__ tables, int table_stride,
             int16_t* __restrict__ coeffs, size_t coeff_stride,
-            uint8_t* __restrict__ recon, size_t recon_stride, DevMetrics* __restrict__ metrics) {
+            uint8_t* __restrict__ recon, size_t recon_stride, DevMetrics* __restrict__ metrics,
+            float* __restrict__ fcoef) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     LumaSmem<SUB>& sm = *reinterpret_cast<LumaSmem<SUB>*>(smem_raw);
     const int tid = threadIdx.x;
@@ -559,7 +622,7 @@ k_fast_luma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (tid < 32) {
+    if (STAGE != STAGE_FWD && tid < 32) {
         // reconstructed chroma (written by k_fast_chroma earlier in this stream): TMA bulk
         // copies, one row per lane, overlapped with the luma work below
         if (tid == 0)
@@ -574,12 +637,12 @@ k_fast_luma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
                        (uint32_t)(ccol1 - ccol0) * 4u, &sm.bar);
         }
     }
-    load_tables(tables + (size_t)unit * table_stride, sm.fq, sm.dq, tid, LU_NT);
+    if (STAGE != STAGE_FWD) load_tables(tables + (size_t)unit * table_stride, sm.fq, sm.dq, tid, LU_NT);
 
     // ---- RGB -> level-shifted Y, block layout: a task = one row x 16 pixels ----------
     // thread t owns segment t%16 of rows t/16 + 8k, k = 0..3; all twelve 16-byte loads are
     // issued before the first use so the DRAM / L2 latency is paid once
-    {
+    if (STAGE != STAGE_BACK) {
         constexpr int NTASK = LU_TH * (LU_TW / 16) / LU_NT;        // 4
         const int seg = tid & 15, rbase = tid >> 4;
         const bool seg_ok = seg * 16 < n_px;
@@ -630,19 +693,29 @@ k_fast_luma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
         if (bx < g.nbx_y && by < g.nby_y) {
             float v[64];
             float4* slot = reinterpret_cast<float4*>(&sm.plane[tid][0]);
+            if (STAGE == STAGE_BACK) {
+                fcoef_load(fcoef_warp_base(fcoef, LU_NT / 32), v);
+            } else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const float4 a = slot[i];
-                v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = a.z; v[4 * i + 3] = a.w;
+                for (int i = 0; i < 16; ++i) {
+                    const float4 a = slot[i];
+                    v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = a.z; v[4 * i + 3] = a.w;
+                }
+                codec_fast_fwd(v);
+            }
+            if (STAGE == STAGE_FWD) {
+                fcoef_store(fcoef_warp_base(fcoef, LU_NT / 32), v);
+                return;
             }
             int16_t* cout = nullptr;
             if (COEFFS)
                 cout = coeffs + (size_t)unit * coeff_stride + ((size_t)by * g.nbx_y + bx) * 64;
-            codec_fast<COEFFS>(v, sm.fq, sm.dq, esum, nnz, cout);
+            codec_fast_back<COEFFS>(v, sm.fq, sm.dq, esum, nnz, cout);
 #pragma unroll
             for (int i = 0; i < 16; ++i)
                 slot[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         }
+        if (STAGE == STAGE_FWD) return;
         flush_stats(esum, nnz, metrics + unit);
     }
     __syncthreads();
@@ -891,50 +964,84 @@ cudaError_t fused_configure_device() {
     cudaError_t e;
 #define JDS_SET(K, BYTES)                                                                       \
     if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES))) != cudaSuccess) return e
-    JDS_SET((k_fast_chroma<1, false>), sizeof(ChromaSmem<1>));
-    JDS_SET((k_fast_chroma<1, true>), sizeof(ChromaSmem<1>));
-    JDS_SET((k_fast_chroma<2, false>), sizeof(ChromaSmem<2>));
-    JDS_SET((k_fast_chroma<2, true>), sizeof(ChromaSmem<2>));
-    JDS_SET((k_fast_chroma_pf<1, false>), sizeof(ChromaPfSmem<1>));
-    JDS_SET((k_fast_chroma_pf<1, true>), sizeof(ChromaPfSmem<1>));
-    JDS_SET((k_fast_chroma_pf<2, false>), sizeof(ChromaPfSmem<2>));
-    JDS_SET((k_fast_chroma_pf<2, true>), sizeof(ChromaPfSmem<2>));
-    JDS_SET((k_fast_luma<1, false>), sizeof(LumaSmem<1>));
-    JDS_SET((k_fast_luma<1, true>), sizeof(LumaSmem<1>));
-    JDS_SET((k_fast_luma<2, false>), sizeof(LumaSmem<2>));
-    JDS_SET((k_fast_luma<2, true>), sizeof(LumaSmem<2>));
+    JDS_SET((k_fast_chroma<1, false, STAGE_FULL>), sizeof(ChromaSmem<1>));
+    JDS_SET((k_fast_chroma<1, false, STAGE_FWD>), sizeof(ChromaSmem<1>));
+    JDS_SET((k_fast_chroma<1, false, STAGE_BACK>), sizeof(ChromaSmem<1>));
+    JDS_SET((k_fast_chroma<1, true, STAGE_FULL>), sizeof(ChromaSmem<1>));
+    JDS_SET((k_fast_chroma<2, false, STAGE_FULL>), sizeof(ChromaSmem<2>));
+    JDS_SET((k_fast_chroma<2, false, STAGE_FWD>), sizeof(ChromaSmem<2>));
+    JDS_SET((k_fast_chroma<2, false, STAGE_BACK>), sizeof(ChromaSmem<2>));
+    JDS_SET((k_fast_chroma<2, true, STAGE_FULL>), sizeof(ChromaSmem<2>));
+    JDS_SET((k_fast_chroma_pf<1, false, STAGE_FULL>), sizeof(ChromaPfSmem<1>));
+    JDS_SET((k_fast_chroma_pf<1, false, STAGE_FWD>), sizeof(ChromaPfSmem<1>));
+    JDS_SET((k_fast_chroma_pf<1, true, STAGE_FULL>), sizeof(ChromaPfSmem<1>));
+    JDS_SET((k_fast_chroma_pf<2, false, STAGE_FULL>), sizeof(ChromaPfSmem<2>));
+    JDS_SET((k_fast_chroma_pf<2, false, STAGE_FWD>), sizeof(ChromaPfSmem<2>));
+    JDS_SET((k_fast_chroma_pf<2, true, STAGE_FULL>), sizeof(ChromaPfSmem<2>));
+    JDS_SET((k_fast_luma<1, false, STAGE_FULL>), sizeof(LumaSmem<1>));
+    JDS_SET((k_fast_luma<1, false, STAGE_FWD>), sizeof(LumaSmem<1>));
+    JDS_SET((k_fast_luma<1, false, STAGE_BACK>), sizeof(LumaSmem<1>));
+    JDS_SET((k_fast_luma<1, true, STAGE_FULL>), sizeof(LumaSmem<1>));
+    JDS_SET((k_fast_luma<2, false, STAGE_FULL>), sizeof(LumaSmem<2>));
+    JDS_SET((k_fast_luma<2, false, STAGE_FWD>), sizeof(LumaSmem<2>));
+    JDS_SET((k_fast_luma<2, false, STAGE_BACK>), sizeof(LumaSmem<2>));
+    JDS_SET((k_fast_luma<2, true, STAGE_FULL>), sizeof(LumaSmem<2>));
     JDS_SET((k_fast_444<false>), sizeof(F444Smem));
     JDS_SET((k_fast_444<true>), sizeof(F444Smem));
 #undef JDS_SET
     return cudaSuccess;
 }
 
+// forward-coefficient scratch of a hoisted sweep: [chroma grid][luma grid], one 8 KB region per
+// warp of the producing kernels
+static size_t fcoef_chroma_floats(const Geom& g) {
+    return g.sub == 0 ? 0 : (size_t)((g.nbx_c + CA_BX - 1) / CA_BX) * ((g.nby_c + CA_BY - 1) / CA_BY) *
+                                (CA_NT / 32) * FCOEF_WARP_FLOATS;
+}
+size_t fused_fcoef_floats(const Geom& g) {
+    if (g.sub == 0) return 0;                      // 4:4:4 sweeps are not hoisted
+    return fcoef_chroma_floats(g) + (size_t)((g.nbx_y + LU_BX - 1) / LU_BX) * ((g.nby_y + LU_BY - 1) / LU_BY) *
+                                        (LU_NT / 32) * FCOEF_WARP_FLOATS;
+}
+
+// stage: 0 full kernel; 1 forward half of ONE frame into `fcoef` (tables / planes / metrics
+// unused); 2 back half of `units` quality points from `fcoef`
 cudaError_t launch_fused_chroma(const Geom& g, int prefilter, const uint8_t* rgb, size_t rgb_stride,
                                 float* cplanes, size_t cplane_stride, const QTables* tables,
                                 int table_stride, int16_t* coeffs, size_t coeff_stride,
-                                DevMetrics* metrics, int units, cudaStream_t s) {
+                                DevMetrics* metrics, int units, cudaStream_t s, int stage, float* fcoef) {
     dim3 grid((g.nbx_c + CA_BX - 1) / CA_BX, (g.nby_c + CA_BY - 1) / CA_BY, units);
+#define JDS_ARGS g, rgb, rgb_stride, cplanes, cplane_stride, tables, table_stride, coeffs, coeff_stride, metrics, fcoef
+    if (stage == STAGE_BACK) {
+        // the coefficients already contain the prefilter: one kernel for both cases
+        if (g.sub == 2) k_fast_chroma<2, false, STAGE_BACK><<<grid, CA_NT, sizeof(ChromaSmem<2>), s>>>(JDS_ARGS);
+        else k_fast_chroma<1, false, STAGE_BACK><<<grid, CA_NT, sizeof(ChromaSmem<1>), s>>>(JDS_ARGS);
+        return cudaGetLastError();
+    }
+    if (stage == STAGE_FWD) {
+        if (prefilter) {
+            if (g.sub == 2) k_fast_chroma_pf<2, false, STAGE_FWD><<<grid, CA_NT, sizeof(ChromaPfSmem<2>), s>>>(JDS_ARGS);
+            else k_fast_chroma_pf<1, false, STAGE_FWD><<<grid, CA_NT, sizeof(ChromaPfSmem<1>), s>>>(JDS_ARGS);
+        } else {
+            if (g.sub == 2) k_fast_chroma<2, false, STAGE_FWD><<<grid, CA_NT, sizeof(ChromaSmem<2>), s>>>(JDS_ARGS);
+            else k_fast_chroma<1, false, STAGE_FWD><<<grid, CA_NT, sizeof(ChromaSmem<1>), s>>>(JDS_ARGS);
+        }
+        return cudaGetLastError();
+    }
     if (prefilter) {
-#define JDS_LAUNCH_PF(SUBV, CO)                                                                 \
-    do {                                                                                        \
-        k_fast_chroma_pf<SUBV, CO><<<grid, CA_NT, sizeof(ChromaPfSmem<SUBV>), s>>>(              \
-            g, rgb, rgb_stride, cplanes, cplane_stride, tables, table_stride, coeffs,            \
-            coeff_stride, metrics);                                                              \
-    } while (0)
+#define JDS_LAUNCH_PF(SUBV, CO) \
+    k_fast_chroma_pf<SUBV, CO, STAGE_FULL><<<grid, CA_NT, sizeof(ChromaPfSmem<SUBV>), s>>>(JDS_ARGS)
         if (g.sub == 2) { if (coeffs) JDS_LAUNCH_PF(2, true); else JDS_LAUNCH_PF(2, false); }
         else { if (coeffs) JDS_LAUNCH_PF(1, true); else JDS_LAUNCH_PF(1, false); }
 #undef JDS_LAUNCH_PF
         return cudaGetLastError();
     }
-#define JDS_LAUNCH_CA(SUBV, CO)                                                                 \
-    do {                                                                                        \
-        k_fast_chroma<SUBV, CO><<<grid, CA_NT, sizeof(ChromaSmem<SUBV>), s>>>(                   \
-            g, rgb, rgb_stride, cplanes, cplane_stride, tables, table_stride, coeffs,            \
-            coeff_stride, metrics);                                                              \
-    } while (0)
+#define JDS_LAUNCH_CA(SUBV, CO) \
+    k_fast_chroma<SUBV, CO, STAGE_FULL><<<grid, CA_NT, sizeof(ChromaSmem<SUBV>), s>>>(JDS_ARGS)
     if (g.sub == 2) { if (coeffs) JDS_LAUNCH_CA(2, true); else JDS_LAUNCH_CA(2, false); }
     else { if (coeffs) JDS_LAUNCH_CA(1, true); else JDS_LAUNCH_CA(1, false); }
 #undef JDS_LAUNCH_CA
+#undef JDS_ARGS
     return cudaGetLastError();
 }
 
@@ -942,7 +1049,7 @@ cudaError_t launch_fused_luma(const Geom& g, const uint8_t* rgb, size_t rgb_stri
                               const float* cplanes, size_t cplane_stride, const QTables* tables,
                               int table_stride, int16_t* coeffs, size_t coeff_stride,
                               uint8_t* recon, size_t recon_stride, DevMetrics* metrics, int units,
-                              cudaStream_t s) {
+                              cudaStream_t s, int stage, float* fcoef) {
     if (g.sub == 0) {
         dim3 grid((g.nbx_y + F4_BX - 1) / F4_BX, (g.nby_y + F4_BY - 1) / F4_BY, units);
         if (coeffs) {
@@ -955,14 +1062,20 @@ cudaError_t launch_fused_luma(const Geom& g, const uint8_t* rgb, size_t rgb_stri
         return cudaGetLastError();
     }
     dim3 grid((g.nbx_y + LU_BX - 1) / LU_BX, (g.nby_y + LU_BY - 1) / LU_BY, units);
-#define JDS_LAUNCH_LU(SUBV, CO)                                                                 \
-    do {                                                                                        \
-        k_fast_luma<SUBV, CO><<<grid, LU_NT, sizeof(LumaSmem<SUBV>), s>>>(                       \
-            g, rgb, rgb_stride, cplanes, cplane_stride, tables, table_stride, coeffs,            \
-            coeff_stride, recon, recon_stride, metrics);                                         \
-    } while (0)
-    if (g.sub == 2) { if (coeffs) JDS_LAUNCH_LU(2, true); else JDS_LAUNCH_LU(2, false); }
-    else { if (coeffs) JDS_LAUNCH_LU(1, true); else JDS_LAUNCH_LU(1, false); }
+    float* lcoef = fcoef ? fcoef + fcoef_chroma_floats(g) : nullptr;
+#define JDS_LAUNCH_LU(SUBV, CO, ST)                                                             \
+    k_fast_luma<SUBV, CO, ST><<<grid, LU_NT, sizeof(LumaSmem<SUBV>), s>>>(                       \
+        g, rgb, rgb_stride, cplanes, cplane_stride, tables, table_stride, coeffs,                \
+        coeff_stride, recon, recon_stride, metrics, lcoef)
+    if (stage == STAGE_FWD) {
+        if (g.sub == 2) JDS_LAUNCH_LU(2, false, STAGE_FWD); else JDS_LAUNCH_LU(1, false, STAGE_FWD);
+    } else if (stage == STAGE_BACK) {
+        if (g.sub == 2) JDS_LAUNCH_LU(2, false, STAGE_BACK); else JDS_LAUNCH_LU(1, false, STAGE_BACK);
+    } else if (g.sub == 2) {
+        if (coeffs) JDS_LAUNCH_LU(2, true, STAGE_FULL); else JDS_LAUNCH_LU(2, false, STAGE_FULL);
+    } else {
+        if (coeffs) JDS_LAUNCH_LU(1, true, STAGE_FULL); else JDS_LAUNCH_LU(1, false, STAGE_FULL);
+    }
 #undef JDS_LAUNCH_LU
     return cudaGetLastError();
 }

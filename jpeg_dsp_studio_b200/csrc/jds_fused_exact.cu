@@ -43,22 +43,6 @@ __device__ __forceinline__ uint32_t trunc_u8(double x) {
     return (uint32_t)__double2loint(__dadd_rd(x, 4503599627370496.0));
 }
 
-// cv2.resize(INTER_LINEAR) source taps at the exact factor 2 (A8): destination index i reads
-// samples i0, i1 with weight f on (S[i1] - S[i0]); f = fma(i + .5, .5, -.5) - floor(.) is
-// exactly .75 for even and .25 for odd i, the indices clamp at the plane border
-__device__ __forceinline__ void taps2(int i, int n, int& i0, int& i1, double& f) {
-    const int k = i >> 1;
-    if (i & 1) {
-        i0 = k;
-        i1 = min(k + 1, n - 1);
-        f = 0.25;
-    } else {
-        i0 = max(k - 1, 0);
-        i1 = k;
-        f = 0.75;
-    }
-}
-
 template <int SUB, bool COEFFS>
 __global__ void __launch_bounds__(XL_NT)
 k_exact_luma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
@@ -198,11 +182,13 @@ k_exact_luma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
                 cr[0][i] = __ldg(pr + i);
             }
         } else {
-            // horizontal taps of the four pixels (x is a multiple of 4)
-            int i0[4], i1[4];
-            double fx[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) taps2(x + i, g.wc, i0[i], i1[i], fx[i]);
+            // horizontal taps of the four pixels x .. x+3 (x a multiple of 4, k = x / 2 even):
+            //   x    : (S[k-1], S[k])   f = .75      x+1 : (S[k],   S[k+1]) f = .25
+            //   x+2  : (S[k],   S[k+1]) f = .75      x+3 : (S[k+1], S[k+2]) f = .25
+            // k-1 / k+2 clamp at the plane border (taps2) - four distinct samples per row, of which
+            // S[k], S[k+1] are one aligned 16-byte load
+            const int k = x >> 1;
+            const int km1 = max(k - 1, 0), kp2 = min(k + 2, g.wc - 1);
             // chroma rows: 4:2:0 - the three rows around the pair (y0r, y1r per luma row);
             // 4:2:2 - the luma row itself
             constexpr int NCR = (SUB == 2) ? 3 : 1;
@@ -220,13 +206,19 @@ k_exact_luma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
             for (int rr = 0; rr < NCR; ++rr) {
                 const double* pb = Cbr + (size_t)crow[rr] * g.wcp;
                 const double* pr = Crr + (size_t)crow[rr] * g.wcp;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const double b0 = __ldg(pb + i0[i]), b1 = __ldg(pb + i1[i]);
-                    const double c0 = __ldg(pr + i0[i]), c1 = __ldg(pr + i1[i]);
-                    hb[rr][i] = P::fma(P::sub(b1, b0), fx[i], b0);
-                    hr[rr][i] = P::fma(P::sub(c1, c0), fx[i], c0);
-                }
+                const double2 bm = __ldg(reinterpret_cast<const double2*>(pb + k));
+                const double2 rm = __ldg(reinterpret_cast<const double2*>(pr + k));
+                const double bl = __ldg(pb + km1), br = __ldg(pb + kp2);
+                const double rl = __ldg(pr + km1), rr2 = __ldg(pr + kp2);
+                const double db = P::sub(bm.y, bm.x), dr = P::sub(rm.y, rm.x);
+                hb[rr][0] = P::fma(P::sub(bm.x, bl), 0.75, bl);
+                hb[rr][1] = P::fma(db, 0.25, bm.x);
+                hb[rr][2] = P::fma(db, 0.75, bm.x);
+                hb[rr][3] = P::fma(P::sub(br, bm.y), 0.25, bm.y);
+                hr[rr][0] = P::fma(P::sub(rm.x, rl), 0.75, rl);
+                hr[rr][1] = P::fma(dr, 0.25, rm.x);
+                hr[rr][2] = P::fma(dr, 0.75, rm.x);
+                hr[rr][3] = P::fma(P::sub(rr2, rm.y), 0.25, rm.y);
             }
             if (SUB == 2) {
 #pragma unroll
@@ -270,6 +262,163 @@ k_exact_luma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
     }
 }
 
+// ------------------------------------------------------------------------------
+// exact chroma kernel (no prefilter): RGB tile -> Cb / Cr (A1) -> 2x1 / 2x2 INTER_AREA
+// average (A3) -> 8x8 codec -> reconstructed chroma planes, all in one pass; replaces the
+// chroma-only k_forward + k_codec pair (two trips of the decimated planes through HBM and a
+// codec whose threads each walk eight strided rows).  tile = 16 x 4 chroma blocks per channel;
+// thread t: channel t / 64, block t % 64.
+// ------------------------------------------------------------------------------
+constexpr int XC_BX = 16, XC_BY = 4, XC_NT = 128;
+
+struct ExactChromaSmem {
+    alignas(16) double plane[2][XC_BX * XC_BY][XL_STRIDE];
+    QTables tb;
+};
+
+template <int SUB, bool COEFFS>
+__global__ void __launch_bounds__(XC_NT)
+k_exact_chroma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
+               double* __restrict__ rec, size_t rec_stride,
+               const QTables* __restrict__ tables, int table_stride,
+               int16_t* __restrict__ coeffs, size_t coeff_stride, DevMetrics* __restrict__ metrics) {
+    typedef Exact P;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ExactChromaSmem& sm = *reinterpret_cast<ExactChromaSmem*>(smem_raw);
+    constexpr int VS = (SUB == 2) ? 2 : 1;            // luma rows per chroma row
+    const int tid = threadIdx.x;
+    const int unit = blockIdx.z;
+    const uint8_t* in = rgb + (size_t)unit * rgb_stride;
+    const int bx0 = blockIdx.x * XC_BX, by0 = blockIdx.y * XC_BY;   // chroma block origin
+    const int x0 = bx0 * 16, y0 = by0 * 8 * VS;                      // luma pixel origin
+    const int n_rows = min(XC_BY * 8 * VS, g.H - y0);
+    const int n_px = min(XC_BX * 16, g.W - x0);
+    {
+        const QTables* src = tables + (size_t)unit * table_stride;
+        for (int i = tid; i < 64; i += XC_NT) {
+            sm.tb.q[i] = src->q[i];
+            sm.tb.rq[i] = src->rq[i];
+            sm.tb.dqx[i] = src->dqx[i];
+        }
+    }
+    // ---- decimation: a task = one chroma row x 8 chroma samples (16 luma pixels) ---------
+    {
+        constexpr int NTASK = XC_BY * 8 * XC_BX / XC_NT;            // 4
+        const int seg = tid & 15, crbase = tid >> 4;
+        const bool seg_ok = seg * 16 < n_px;
+#pragma unroll 1
+        for (int k = 0; k < NTASK; ++k) {
+            const int cr = crbase + 8 * k;
+            if (!(seg_ok && cr * VS < n_rows)) continue;
+            uint32_t w[VS][12];
+#pragma unroll
+            for (int v = 0; v < VS; ++v) {
+                const uint4* q = reinterpret_cast<const uint4*>(
+                    in + ((size_t)(y0 + cr * VS + v) * g.W + x0 + seg * 16) * 3);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const uint4 a = __ldg(q + i);
+                    w[v][4 * i] = a.x; w[v][4 * i + 1] = a.y; w[v][4 * i + 2] = a.z; w[v][4 * i + 3] = a.w;
+                }
+            }
+            const int blk = (cr >> 3) * XC_BX + seg, ry = cr & 7;
+            double2* pb = reinterpret_cast<double2*>(&sm.plane[0][blk][ry * 8]);
+            double2* pr = reinterpret_cast<double2*>(&sm.plane[1][blk][ry * 8]);
+#pragma unroll
+            for (int s2 = 0; s2 < 4; ++s2) {            // two chroma samples per 16-byte store
+                double ob[2], orr[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int px = 2 * (2 * s2 + e);    // first luma pixel of the sample
+                    double cb[VS][2], cr_[VS][2];
+#pragma unroll
+                    for (int v = 0; v < VS; ++v)
+#pragma unroll
+                        for (int d = 0; d < 2; ++d) {
+                            const int b = 3 * (px + d);
+                            const double rr = byte_to_double(w[v][b >> 2], b & 3);
+                            const double gg = byte_to_double(w[v][(b + 1) >> 2], (b + 1) & 3);
+                            const double bb = byte_to_double(w[v][(b + 2) >> 2], (b + 2) & 3);
+                            rgb_to_cbcr<P>(rr, gg, bb, cb[v][d], cr_[v][d]);
+                        }
+                    if (SUB == 1) {                     // A3, 4:2:2: (a+b)*0.5
+                        ob[e] = P::mul(P::add(cb[0][0], cb[0][1]), 0.5);
+                        orr[e] = P::mul(P::add(cr_[0][0], cr_[0][1]), 0.5);
+                    } else {                            // A3, 4:2:0: (((a+b)+c)+d)*0.25
+                        ob[e] = P::mul(P::add(P::add(P::add(cb[0][0], cb[0][1]), cb[VS - 1][0]), cb[VS - 1][1]), 0.25);
+                        orr[e] = P::mul(P::add(P::add(P::add(cr_[0][0], cr_[0][1]), cr_[VS - 1][0]), cr_[VS - 1][1]), 0.25);
+                    }
+                }
+                pb[s2] = make_double2(ob[0], ob[1]);
+                pr[s2] = make_double2(orr[0], orr[1]);
+            }
+        }
+    }
+    __syncthreads();
+    // ---- codec: thread t -> channel t / 64, block t % 64, in place ------------------------
+    {
+        const int ch = tid >> 6, blk = tid & 63;
+        const int bx = bx0 + (blk & (XC_BX - 1)), by = by0 + (blk >> 4);
+        unsigned long long bits = 0, nnz = 0;
+        if (bx < g.nbx_c && by < g.nby_c) {
+            double v[64];
+            double2* slot = reinterpret_cast<double2*>(&sm.plane[ch][blk][0]);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const double2 a = slot[i];
+                v[2 * i] = a.x;
+                v[2 * i + 1] = a.y;
+            }
+            int16_t q[64];
+            BlockStats st;
+            BlockCodec<P>::run(v, q, sm.tb, st, nullptr, nullptr);
+            bits = st.bits;
+            nnz = st.nnz;
+            if (COEFFS) {
+                uint4* out = reinterpret_cast<uint4*>(
+                    coeffs + (size_t)unit * coeff_stride +
+                    ((size_t)g.nblk_y + (size_t)ch * g.nblk_c + (size_t)by * g.nbx_c + bx) * 64);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    uint4 pk;
+                    pk.x = (uint16_t)q[i * 8 + 0] | ((uint32_t)(uint16_t)q[i * 8 + 1] << 16);
+                    pk.y = (uint16_t)q[i * 8 + 2] | ((uint32_t)(uint16_t)q[i * 8 + 3] << 16);
+                    pk.z = (uint16_t)q[i * 8 + 4] | ((uint32_t)(uint16_t)q[i * 8 + 5] << 16);
+                    pk.w = (uint16_t)q[i * 8 + 6] | ((uint32_t)(uint16_t)q[i * 8 + 7] << 16);
+                    out[i] = pk;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) slot[i] = make_double2(v[2 * i], v[2 * i + 1]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            bits += __shfl_down_sync(0xffffffffu, bits, o);
+            nnz += __shfl_down_sync(0xffffffffu, nnz, o);
+        }
+        if ((tid & 31) == 0 && nnz) {
+            atomicAdd(&metrics[unit].coeff_bits, bits);
+            atomicAdd(&metrics[unit].nnz, nnz);
+        }
+    }
+    __syncthreads();
+    // ---- reconstructed planes out: a task = (channel, chroma row, 8 samples): consecutive
+    // threads write consecutive 64-byte pieces of a plane row --------------------------------
+    for (int task = tid; task < 2 * XC_BY * 8 * XC_BX; task += XC_NT) {
+        const int ch = task / (XC_BY * 8 * XC_BX);
+        const int rem = task % (XC_BY * 8 * XC_BX);
+        const int cr = rem / XC_BX, seg = rem % XC_BX;
+        const int bx = bx0 + seg, cy = by0 * 8 + cr;
+        if (bx >= g.nbx_c || cy >= g.hcp) continue;
+        const int blk = (cr >> 3) * XC_BX + seg, ry = cr & 7;
+        const double2* src = reinterpret_cast<const double2*>(&sm.plane[ch][blk][ry * 8]);
+        double2* dst = reinterpret_cast<double2*>(rec + (size_t)unit * rec_stride + g.plane_y +
+                                                  (size_t)ch * g.plane_c + (size_t)cy * g.wcp + bx * 8);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dst[i] = src[i];
+    }
+}
+
 cudaError_t exact_fused_configure_device() {
     cudaError_t e;
 #define JDS_SET(K)                                                                              \
@@ -279,7 +428,31 @@ cudaError_t exact_fused_configure_device() {
     JDS_SET((k_exact_luma<1, false>)); JDS_SET((k_exact_luma<1, true>));
     JDS_SET((k_exact_luma<2, false>)); JDS_SET((k_exact_luma<2, true>));
 #undef JDS_SET
+#define JDS_SET(K)                                                                              \
+    if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize,                \
+                                  (int)sizeof(ExactChromaSmem))) != cudaSuccess) return e
+    JDS_SET((k_exact_chroma<1, false>)); JDS_SET((k_exact_chroma<1, true>));
+    JDS_SET((k_exact_chroma<2, false>)); JDS_SET((k_exact_chroma<2, true>));
+#undef JDS_SET
     return cudaSuccess;
+}
+
+// chroma of a subsampled, block-aligned frame WITHOUT prefilter in one kernel
+bool exact_chroma_supported(const Geom& g, int prefilter) { return g.sub != 0 && !prefilter && !g.general; }
+
+cudaError_t launch_exact_chroma(const Geom& g, const uint8_t* rgb, size_t rgb_stride, double* rec,
+                                size_t rec_stride, const QTables* tables, int table_stride,
+                                int16_t* coeffs, size_t coeff_stride, DevMetrics* metrics, int units,
+                                cudaStream_t s) {
+    dim3 grid((g.nbx_c + XC_BX - 1) / XC_BX, (g.nby_c + XC_BY - 1) / XC_BY, units);
+    const size_t smem = sizeof(ExactChromaSmem);
+#define JDS_LAUNCH_XC(SUBV, CO)                                                                 \
+    k_exact_chroma<SUBV, CO><<<grid, XC_NT, smem, s>>>(g, rgb, rgb_stride, rec, rec_stride, tables, \
+                                                       table_stride, coeffs, coeff_stride, metrics)
+    if (g.sub == 1) { if (coeffs) JDS_LAUNCH_XC(1, true); else JDS_LAUNCH_XC(1, false); }
+    else { if (coeffs) JDS_LAUNCH_XC(2, true); else JDS_LAUNCH_XC(2, false); }
+#undef JDS_LAUNCH_XC
+    return cudaGetLastError();
 }
 
 cudaError_t launch_exact_luma(const Geom& g, const uint8_t* rgb, size_t rgb_stride, const double* rec,

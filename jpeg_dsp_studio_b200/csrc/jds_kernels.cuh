@@ -41,18 +41,28 @@ size_t fused_chroma_plane_floats(const Geom& g);
 cudaError_t launch_fused_chroma(const Geom& g, int prefilter, const uint8_t* rgb, size_t rgb_stride,
                                 float* cplanes, size_t cplane_stride, const QTables* tables,
                                 int table_stride, int16_t* coeffs, size_t coeff_stride,
-                                DevMetrics* metrics, int units, cudaStream_t s);
+                                DevMetrics* metrics, int units, cudaStream_t s, int stage = 0,
+                                float* fcoef = nullptr);
+// hoisted sweeps: `stage` 1 writes the quality-independent forward DCT coefficients of one
+// frame into `fcoef` (fused_fcoef_floats(g) floats; 0 = this geometry is not hoisted), `stage` 2
+// runs quantisation .. reconstruction of `units` quality points from it; 0 = the full kernels
+size_t fused_fcoef_floats(const Geom& g);
 cudaError_t launch_fused_luma(const Geom& g, const uint8_t* rgb, size_t rgb_stride,
                               const float* cplanes, size_t cplane_stride, const QTables* tables,
                               int table_stride, int16_t* coeffs, size_t coeff_stride,
                               uint8_t* recon, size_t recon_stride, DevMetrics* metrics, int units,
-                              cudaStream_t s);
+                              cudaStream_t s, int stage = 0, float* fcoef = nullptr);
 // fused exact-mode luma + compose kernel (jds_fused_exact.cu): Y never touches HBM; `rec` holds
 // the reconstructed chroma planes the chroma-only k_codec wrote (plane layout of the staged path)
 cudaError_t launch_exact_luma(const Geom& g, const uint8_t* rgb, size_t rgb_stride, const double* rec,
                               size_t rec_stride, const QTables* tables, int table_stride,
                               int16_t* coeffs, size_t coeff_stride, uint8_t* recon,
                               size_t recon_stride, DevMetrics* metrics, int units, cudaStream_t s);
+bool exact_chroma_supported(const Geom& g, int prefilter);
+cudaError_t launch_exact_chroma(const Geom& g, const uint8_t* rgb, size_t rgb_stride, double* rec,
+                                size_t rec_stride, const QTables* tables, int table_stride,
+                                int16_t* coeffs, size_t coeff_stride, DevMetrics* metrics, int units,
+                                cudaStream_t s);
 void launch_hist50(const int16_t* coeffs, size_t coeff_stride, size_t n_coeffs, DevMetrics* metrics,
                    int units, int sm_count, cudaStream_t s);
 constexpr int VALUE_HIST_BINS = 2048;          // int16 coefficient value v -> bin v + 1024

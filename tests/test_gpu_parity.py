@@ -325,6 +325,19 @@ def test_fused_batch_and_sweep_consistency(J):
         assert np.array_equal(o.recon, single.recon)
         assert o.scalars["estimated_bits"] == single.scalars["estimated_bits"]
         assert o.metrics.sse_rgb == single.metrics.sse_rgb
+    # hoisted sweep: colour, prefilter / decimation and the forward DCT run once
+    # per frame (two pre-pass kernels), every point starts at quantisation - same bits as
+    # single calls, and 2 + 3 n launches instead of the staged path's or 3 n full kernels
+    img = CS.rand_rgb(77, 272, 400)
+    l0 = eng.launch_count()
+    sw = eng.sweep(img, qs, "4:2:0", True, precision="fast", want_recon=True)
+    assert eng.launch_count() - l0 == 2 + 3 * len(qs)
+    for q, o in zip(qs, sw):
+        single = eng.roundtrip(img, q, "4:2:0", True, precision="fast")
+        assert np.array_equal(o.recon, single.recon)
+        assert o.scalars["estimated_bits"] == single.scalars["estimated_bits"]
+        assert o.metrics.sse_rgb == single.metrics.sse_rgb and o.metrics.nnz == single.metrics.nnz
+        assert abs(o.scalars["ssim_y"] - single.scalars["ssim_y"]) <= 1e-9
 
 
 def test_sweep_sharded_single_rank_equals_engine_sweep(J):
