@@ -5,6 +5,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
+os.environ.setdefault("JDS_SCRATCH_MB", "8192")      # like bench.py: the whole batch in one launch sequence
 import jpeg_dsp_studio_b200 as J
 
 precision = sys.argv[1] if len(sys.argv) > 1 else "fast"
