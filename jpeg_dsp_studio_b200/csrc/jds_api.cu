@@ -76,7 +76,7 @@ struct jds_ctx {
     bool legacy_ssim = false;     // JDS_LEGACY_SSIM=1: use the tile kernel (debug / A-B runs)
     bool no_fused = false;        // JDS_NO_FUSED=1: fast mode through the staged kernels
     bool no_hoist = false;        // JDS_NO_HOIST=1: sweeps redo the forward half per point (A/B runs)
-    bool l2_chunking = false;     // JDS_L2_CHUNK=1: size launches so a frame sequence stays in L2
+    int l2_chunking = 0;          // JDS_L2_CHUNK=k: launch sequences of k x the frames whose working set fits L2 (0 = off)
     bool stage_timing = false;    // per-kernel CUDA events (jds_ctx_stage_timing)
     // jds_sweep_records returns without synchronising: its table uploads are staged in a ring
     // of pinned slots, each guarded by an event, so back-to-back calls never wait on the stream
@@ -182,7 +182,8 @@ extern "C" int jds_ctx_create(int device, jds_ctx** out) {
     const char* nh = getenv("JDS_NO_HOIST");
     c->no_hoist = nh && atoi(nh) != 0;
     const char* l2c = getenv("JDS_L2_CHUNK");
-    c->l2_chunking = l2c && atoi(l2c) != 0;
+    c->l2_chunking = l2c ? atoi(l2c) : 0;
+    if (c->l2_chunking < 0) c->l2_chunking = 0;
     const char* mb = getenv("JDS_SCRATCH_MB");
     if (mb && atol(mb) > 0) c->scratch_budget = (size_t)atol(mb) << 20;
     *out = c;
@@ -581,6 +582,7 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
                           (want_coeffs ? ncoef * 2 : 0);
         int lc = (int)((c->l2_bytes * 6 / 10) / (ws ? ws : 1));
         if (lc < 1) lc = 1;
+        lc *= c->l2_chunking;          // k > 1: trade some L2 residency for larger grids
         if (chunk > lc) chunk = lc;
     }
     const bool pipelined = (in_host || (out_host && (want_recon || want_coeffs))) && J.units > 1;
@@ -611,7 +613,7 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
     const bool hoist = J.shared_input && will_fuse && J.units > 1 && !want_coeffs && !want_hist &&
                        fused_fcoef_floats(g) > 0 && !c->no_hoist;
     // (a hoisted sweep's pre-pass runs on the first stream only: no second compute stream)
-    const bool dual = c->l2_chunking && will_fuse && !c->stage_timing && J.units > chunk && !hoist;
+    const bool dual = c->l2_chunking > 0 && will_fuse && !c->stage_timing && J.units > chunk && !hoist;
     const int nscr = (pipelined || dual) ? 2 : 1;        // recon / coefficient scratch slots
 
     int rc;

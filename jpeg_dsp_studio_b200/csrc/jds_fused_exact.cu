@@ -23,6 +23,10 @@
 
 namespace jds {
 
+#ifndef JDS_XL_MIN_CTAS
+#define JDS_XL_MIN_CTAS 3      // CTAs per SM the exact kernels are compiled for: 168 registers, 4-8 bytes of spills,
+                               // 12 warps per SM (2: 255 registers, luma 0.96 ms; 3: 0.85 ms; 4: 1.01 ms per 16 x 4K)
+#endif
 constexpr int XL_BX = 32, XL_BY = 4, XL_NT = 128;     // 32 x 4 luma blocks = 256 x 32 pixels per CTA
 constexpr int XL_TW = XL_BX * 8, XL_TH = XL_BY * 8;
 constexpr int XL_STRIDE = 66;                         // doubles per block slot: 528 B = 4 * 128 + 16,
@@ -44,7 +48,7 @@ __device__ __forceinline__ uint32_t trunc_u8(double x) {
 }
 
 template <int SUB, bool COEFFS>
-__global__ void __launch_bounds__(XL_NT)
+__global__ void __launch_bounds__(XL_NT, JDS_XL_MIN_CTAS)
 k_exact_luma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
              const double* __restrict__ rec, size_t rec_stride,
              const QTables* __restrict__ tables, int table_stride,
@@ -277,7 +281,7 @@ struct ExactChromaSmem {
 };
 
 template <int SUB, bool COEFFS>
-__global__ void __launch_bounds__(XC_NT)
+__global__ void __launch_bounds__(XC_NT, JDS_XL_MIN_CTAS)
 k_exact_chroma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
                double* __restrict__ rec, size_t rec_stride,
                const QTables* __restrict__ tables, int table_stride,

@@ -51,7 +51,17 @@ struct Exact {
     // np.clip(a, 0, 255) for finite a as two compares and selects (fmin / fmax in fp64 expand
     // to ~14 instructions each for their NaN rules: a quarter of the exact luma kernel's
     // instructions before this); -0.0 and negative values give +0.0
+#if defined(__CUDA_ARCH__)
+    // on the device the two comparisons read the high word as an integer (sign bit: negative
+    // or -0.0; >= 0x406FE000: 255.0 and above), which keeps them off the fp64 pipe - the pipe
+    // that bounds the exact kernels; same results as the floating-point form below
+    static JDS_HD T clamp255(T a) {
+        const int hi = __double2hiint(a);
+        return hi < 0 ? 0.0 : (hi >= 0x406FE000 ? 255.0 : a);
+    }
+#else
     static JDS_HD T clamp255(T a) { return a > 0.0 ? (a > 255.0 ? 255.0 : a) : 0.0; }
+#endif
 };
 
 // np.round(x).astype(int16) of a quotient |x| < 2^31 (engines/quantizer.py:24): adding
