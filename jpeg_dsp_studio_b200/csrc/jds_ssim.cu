@@ -79,6 +79,8 @@ constexpr int S_TILEB = 1792;        // bytes reserved per TMA tile (7 x 240 = 1
 constexpr int S_BHALF = S_PG;              // float4 per half row of `by` (even / odd pixel pairs)
 constexpr int S_BPITCH = 2 * S_BHALF + 1;  // 37 float4 = 592 B = 4 * 128 + 80
 constexpr int S_HPITCH = 2 * S_OW + 1;     // float4 row pitch of hxy / hqc: 129 * 16 B = 16 * 128 + 16
+// (B,Y) planes: double buffered only when prep(c+1) overlaps pass 1 of chunk c (PREP_SPLIT)
+constexpr int S_NBY = JDS_SSIM_PREP_SPLIT ? 2 : 1;
 
 struct HSum {                        // window sums of one (row, pair, column)
     float2 sx, sy, sq, sc;           // .x = first channel of the pair, .y = second
@@ -88,7 +90,7 @@ struct SsimSmem {
     alignas(128) uint8_t raw[2][2][S_TILEB];        // [buffer][image]: 7 rows x 240 B, as the TMA writes them
     // centred fp32 (B, Y) pairs [buffer][image][row]: each float4 holds two pixels
     // (B p, Y p, B p+1, Y p+1); even pixel-pairs in [0, 18), odd pixel-pairs in [18, 36)
-    alignas(16) float4 by[2][2][S_R][S_BPITCH];
+    alignas(16) float4 by[S_NBY][2][S_R][S_BPITCH];
     alignas(16) float4 hxy[S_R][S_HPITCH];          // horizontal sums (sx, sy) [row][pair*64+col]
     alignas(16) float4 hqc[S_R][S_HPITCH];          // horizontal sums (sq, sc)
     alignas(8) unsigned long long bar[2];
@@ -194,8 +196,8 @@ __device__ __forceinline__ float2 pass1_task(SsimSmem& sm, int buf, int p1_row, 
     } else {
         // pixel-pair index of the segment's first pixel is 4 * seg (even): pairs alternate
         // between the even and the odd half of the row
-        qa = &sm.by[buf][0][p1_row][2 * p1_seg];
-        qb = &sm.by[buf][1][p1_row][2 * p1_seg];
+        qa = &sm.by[buf & (S_NBY - 1)][0][p1_row][2 * p1_seg];
+        qb = &sm.by[buf & (S_NBY - 1)][1][p1_row][2 * p1_seg];
     }
     float2 wx = f2(0.f), wy = f2(0.f), wq = f2(0.f), wc = f2(0.f), sse = f2(0.f);
     const uint32_t hx_dst = smem_u32(&sm.hxy[p1_row][PAIR * S_OW + S_SEG * p1_seg]);
@@ -264,7 +266,10 @@ __device__ __forceinline__ float2 pass1_task(SsimSmem& sm, int buf, int p1_row, 
     return sse;
 }
 
-__global__ void __launch_bounds__(S_NT, 4)
+#ifndef JDS_SSIM_MIN_CTAS
+#define JDS_SSIM_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(S_NT, JDS_SSIM_MIN_CTAS)
 k_ssim_strip(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
              int H, int W, int seg_rows, int a_unit_step, int b_unit_step,
              DevMetrics* __restrict__ metrics, int want_ssim, int want_sse) {
@@ -348,8 +353,8 @@ k_ssim_strip(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
             const float Y3 = fmaf(0.299f, R3, fmaf(0.587f, G3, 0.114f * B3));
             // pixels 4*g4 .. 4*g4+3 = pixel-pairs 2*g4 (even half) and 2*g4+1 (odd half):
             // consecutive threads store consecutive float4 -> no bank conflicts
-            sm.by[buf][img][r][g4] = make_float4(B0, Y0, B1, Y1);
-            sm.by[buf][img][r][S_BHALF + g4] = make_float4(B2, Y2, B3, Y3);
+            sm.by[buf & (S_NBY - 1)][img][r][g4] = make_float4(B0, Y0, B1, Y1);
+            sm.by[buf & (S_NBY - 1)][img][r][S_BHALF + g4] = make_float4(B2, Y2, B3, Y3);
         }
     };
     constexpr int N_PREP = 2 * S_R * S_PG;          // 252 tasks per chunk
@@ -605,7 +610,7 @@ cudaError_t launch_ssim_strip(int H, int W, const uint8_t* a, size_t a_stride, c
         // overlap + prologue per CTA, last term = average ragged tail) is flat around
         // r* = sqrt(2 c x work / slots); take the segment count just below it (measured on
         // 16 x 4K: 4 segments 1.40 ms, 2 segments 1.44 ms, 3 segments 1.43 ms)
-        const double slots = 4.0 * sm_count;
+        const double slots = (double)JDS_SSIM_MIN_CTAS * sm_count;
         const double work = (double)strips * units * H;
         double r_opt = sqrt(2.0 * 28.0 * work / slots);
         if (r_opt < 126.0) r_opt = 126.0;
