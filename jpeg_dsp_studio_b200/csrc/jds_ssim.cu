@@ -33,6 +33,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "jds_kernels.cuh"
 #include "jds_ssim_formula.cuh"
 
@@ -620,6 +621,13 @@ cudaError_t launch_ssim_strip(int H, int W, const uint8_t* a, size_t a_stride, c
         if (seg_rows < 126) seg_rows = 126;
     }
 #endif
+    if (const char* ov = getenv("JDS_SSIM_SEGS")) {      // A/B runs: force the vertical segment count
+        const int n = atoi(ov);
+        if (n >= 1) {
+            seg_rows = rows_for(n);
+            if (seg_rows < S_R) seg_rows = S_R;
+        }
+    }
     segs = (H + seg_rows - 1) / seg_rows;
     dim3 grid(strips, segs, units);
     k_ssim_strip<<<grid, S_NT, smem, s>>>(map_a, map_b, H, W, seg_rows, a_stride ? 1 : 0, b_stride ? 1 : 0,
