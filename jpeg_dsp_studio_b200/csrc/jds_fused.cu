@@ -419,10 +419,21 @@ k_fast_chroma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
 // vertically).  Phase A filters every luma row of the tile (+1 halo row each side)
 // horizontally into shared memory, phase B combines rows.
 // ------------------------------------------------------------------------------
+// the tile's luma rows go through the row filter in this many passes (measured per 16 x 4K:
+// 4:2:0 - 1 pass 0.442, 2 passes 0.370, 4 passes 0.346 ms; 4:2:2 - 0.509 / 0.464 / 0.495 ms)
 template <int SUB>
 struct ChromaPfSmem {
+    static constexpr int PARTS = (SUB == 2) ? 4 : 2;
     static constexpr int LROWS = CA_BY * 8 * (SUB == 2 ? 2 : 1) + 2;     // luma rows incl. halo
-    alignas(16) float2 hrow[LROWS][CA_BX * 8];                            // (cb, cr), level shifted
+    // rows of one pass (+ one halo row each side): the tile is filtered in PARTS passes so
+    // that the row buffer stays small (4 passes: 18 KB instead of 68 KB -> four CTAs per SM
+    // instead of two; the halo rows between passes are filtered twice: +12 %)
+    static constexpr int PROWS = (LROWS - 2) / PARTS;
+    // row-filtered (cb, cr) samples, level shifted: float4 number k2 (two samples) of segment `seg`
+    // sits at [row][k2 * 16 + seg], so the 16 segments a half-warp works on are contiguous 16-byte
+    // pieces (a [seg * 4 + k2] order puts them 64 B apart: 4-way bank conflicts, 67 % of all
+    // shared-memory wavefronts of this kernel before the change)
+    alignas(16) float4 hrow[PROWS + 2][4 * CA_BX];
     alignas(16) float plane[2][CA_BX * CA_BY][BLK_STRIDE];
     alignas(16) float fq[64];
     alignas(16) float dq[64];
@@ -450,9 +461,15 @@ k_fast_chroma_pf(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
     const int n_px = min(CA_BX * 16, g.W - x0);
     if (STAGE != STAGE_FWD) load_tables(tables + (size_t)unit * table_stride, sm.fq, sm.dq, tid, CA_NT);
 
+    constexpr int PROWS = ChromaPfSmem<SUB>::PROWS;
+    for (int part = 0; part < ChromaPfSmem<SUB>::PARTS; ++part) {
+    const int lr0 = part * PROWS;                                         // first luma row (tile local, halo = -1)
+    if (lr0 >= n_rows) break;
+    if (part) __syncthreads();                                            // phase B of the last pass is done with hrow
     // ---- phase A: a task = one luma row (halo rows included) x 16 pixels -> 8 samples ----
-    for (int task = tid; task < LROWS * CA_BX; task += CA_NT) {
-        const int lr = task / CA_BX, seg = task % CA_BX;
+    for (int task = tid; task < (PROWS + 2) * CA_BX; task += CA_NT) {
+        const int lrp = task / CA_BX, seg = task % CA_BX;                 // row inside this pass
+        const int lr = lr0 + lrp;                                         // row inside the tile (0 = halo above)
         if (lr >= n_rows + 2 || seg * 16 >= n_px) continue;
         // smem row lr holds image row y0 + lr - 1, REFLECT_101 at the top / bottom edge
         int y = y0 + lr - 1;
@@ -495,7 +512,7 @@ k_fast_chroma_pf(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
             cb[17] = cb[15];
             cr[17] = cr[15];
         }
-        float4* dst = reinterpret_cast<float4*>(&sm.hrow[lr][seg * 8]);
+        float4* dst = &sm.hrow[lrp][seg];
 #pragma unroll
         for (int k2 = 0; k2 < 4; ++k2) {            // two samples per float4 store
             float o[4];
@@ -505,24 +522,25 @@ k_fast_chroma_pf(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
                 o[2 * h] = fmaf(HA, cb[2 * k] + cb[2 * k + 3], HB * (cb[2 * k + 1] + cb[2 * k + 2]));
                 o[2 * h + 1] = fmaf(HA, cr[2 * k] + cr[2 * k + 3], HB * (cr[2 * k + 1] + cr[2 * k + 2]));
             }
-            dst[k2] = make_float4(o[0], o[1], o[2], o[3]);
+            dst[k2 * CA_BX] = make_float4(o[0], o[1], o[2], o[3]);
         }
     }
     __syncthreads();
 
-    // ---- phase B: vertical taps, a task = one chroma row x 8 samples ---------------------
-    for (int task = tid; task < CA_BY * 8 * CA_BX; task += CA_NT) {
-        const int cr_ = task / CA_BX, seg = task % CA_BX;
+    // ---- phase B: vertical taps, a task = one chroma row of this pass x 8 samples --------
+    for (int task = tid; task < (PROWS / VS) * CA_BX; task += CA_NT) {
+        const int crp = task / CA_BX, seg = task % CA_BX;                 // chroma row inside the pass
+        const int cr_ = lr0 / VS + crp;                                   // chroma row inside the tile
         if (cr_ * VS >= n_rows || seg * 16 >= n_px) continue;
         float ob[8], orr[8];
-        // smem rows of this chroma row: luma rows VS*cr_-1 .. VS*cr_+VS  ->  lr = VS*cr_ .. +VS+1
-        const float4* r0 = reinterpret_cast<const float4*>(&sm.hrow[VS * cr_][seg * 8]);
-        const float4* r1 = reinterpret_cast<const float4*>(&sm.hrow[VS * cr_ + 1][seg * 8]);
-        const float4* r2 = reinterpret_cast<const float4*>(&sm.hrow[VS * cr_ + 2][seg * 8]);
-        const float4* r3 = reinterpret_cast<const float4*>(&sm.hrow[VS * cr_ + (SUB == 2 ? 3 : 2)][seg * 8]);
+        // smem rows of this chroma row: luma rows VS*cr_-1 .. VS*cr_+VS  ->  pass rows VS*crp .. +VS+1
+        const float4* r0 = &sm.hrow[VS * crp][seg];
+        const float4* r1 = &sm.hrow[VS * crp + 1][seg];
+        const float4* r2 = &sm.hrow[VS * crp + 2][seg];
+        const float4* r3 = &sm.hrow[VS * crp + (SUB == 2 ? 3 : 2)][seg];
 #pragma unroll
         for (int k2 = 0; k2 < 4; ++k2) {
-            const float4 a = r0[k2], b = r1[k2], c = r2[k2], d = r3[k2];
+            const float4 a = r0[k2 * CA_BX], b = r1[k2 * CA_BX], c = r2[k2 * CA_BX], d = r3[k2 * CA_BX];
             const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
             const float cv[4] = {c.x, c.y, c.z, c.w}, dv[4] = {d.x, d.y, d.z, d.w};
             float o[4];
@@ -541,6 +559,7 @@ k_fast_chroma_pf(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
         pr[0] = make_float4(orr[0], orr[1], orr[2], orr[3]);
         pr[1] = make_float4(orr[4], orr[5], orr[6], orr[7]);
     }
+    }   // passes over the tile's rows
     __syncthreads();
     chroma_codec_tail<COEFFS, STAGE>(g, sm.plane, sm.fq, sm.dq, bx0, by0, unit, cplanes, cplane_stride,
                                      coeffs, coeff_stride, metrics, fcoef);
