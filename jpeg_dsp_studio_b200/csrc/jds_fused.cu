@@ -71,6 +71,8 @@ constexpr int kMagicRoundBits = 0x4B400000;
 constexpr float kInv255 = 1.0f / 255.0f;
 constexpr float k128_255 = 128.0f / 255.0f;
 constexpr int BLK_STRIDE = 68;                    // floats per 8x8 block slot in shared memory
+// luma tiles: which blocks keep the two halves of their rows swapped (bit 3 of the slot index)
+__device__ __forceinline__ int slot_swz(int blk) { return (blk >> 3) & 1; }
 
 template <int B>
 __device__ __forceinline__ float f_byte_centered(uint32_t w) {
@@ -694,12 +696,16 @@ k_fast_luma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
                     yv[4 * gq + 3] = fmaf(0.299f, f_byte_centered<1>(w2), fmaf(0.587f, f_byte_centered<2>(w2), 0.114f * f_byte_centered<3>(w2)));
                 }
                 const int blk = (r >> 3) * LU_BX + seg * 2, ry = r & 7;
+                // slot swizzle: the two 16-byte halves of a block row swap places in blocks with
+                // bit 3 set (SLOT_SWZ), so the eight lanes of a quarter-warp - blocks 2s, s = 0..7,
+                // 32 B apart modulo 128 - hit eight different bank groups instead of four twice
+                const int f = slot_swz(blk);
                 float4* p0 = reinterpret_cast<float4*>(&sm.plane[blk][ry * 8]);
                 float4* p1 = reinterpret_cast<float4*>(&sm.plane[blk + 1][ry * 8]);
-                p0[0] = make_float4(yv[0], yv[1], yv[2], yv[3]);
-                p0[1] = make_float4(yv[4], yv[5], yv[6], yv[7]);
-                p1[0] = make_float4(yv[8], yv[9], yv[10], yv[11]);
-                p1[1] = make_float4(yv[12], yv[13], yv[14], yv[15]);
+                p0[f] = make_float4(yv[0], yv[1], yv[2], yv[3]);
+                p0[1 - f] = make_float4(yv[4], yv[5], yv[6], yv[7]);
+                p1[f] = make_float4(yv[8], yv[9], yv[10], yv[11]);
+                p1[1 - f] = make_float4(yv[12], yv[13], yv[14], yv[15]);
             }
         }
     }
@@ -712,12 +718,16 @@ k_fast_luma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
         if (bx < g.nbx_y && by < g.nby_y) {
             float v[64];
             float4* slot = reinterpret_cast<float4*>(&sm.plane[tid][0]);
+            // swizzled halves (see above): float4 i lives at i ^ f - two bases, constant offsets
+            const int f = slot_swz(tid);
+            float4* slot_e = slot + f;
+            float4* slot_o = slot - f;
             if (STAGE == STAGE_BACK) {
                 fcoef_load(fcoef_warp_base(fcoef, LU_NT / 32), v);
             } else {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const float4 a = slot[i];
+                    const float4 a = (i & 1) ? slot_o[i] : slot_e[i];
                     v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = a.z; v[4 * i + 3] = a.w;
                 }
                 codec_fast_fwd(v);
@@ -732,7 +742,7 @@ k_fast_luma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
             codec_fast_back<COEFFS>(v, sm.fq, sm.dq, esum, nnz, cout);
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-                slot[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                ((i & 1) ? slot_o : slot_e)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         }
         if (STAGE == STAGE_FWD) return;
         flush_stats(esum, nnz, metrics + unit);
@@ -779,9 +789,10 @@ k_fast_luma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
             const int blk = (r >> 3) * LU_BX + seg * 2, ry = r & 7;
             float yv[16];
             {
+                const int f = slot_swz(blk);
                 const float4* p0 = reinterpret_cast<const float4*>(&sm.plane[blk][ry * 8]);
                 const float4* p1 = reinterpret_cast<const float4*>(&sm.plane[blk + 1][ry * 8]);
-                float4 a = p0[0], b = p0[1], c = p1[0], d = p1[1];
+                float4 a = p0[f], b = p0[1 - f], c = p1[f], d = p1[1 - f];
                 yv[0] = a.x; yv[1] = a.y; yv[2] = a.z; yv[3] = a.w;
                 yv[4] = b.x; yv[5] = b.y; yv[6] = b.z; yv[7] = b.w;
                 yv[8] = c.x; yv[9] = c.y; yv[10] = c.z; yv[11] = c.w;
