@@ -41,7 +41,9 @@ typedef enum jds_status {
     JDS_ERR_UNSUPPORTED = -2,  /* valid for the reference but not implemented (odd
                                   plane sizes with chroma subsampling)               */
     JDS_ERR_CUDA = -3,         /* CUDA runtime error; text in jds_last_error()       */
-    JDS_ERR_NOMEM = -4
+    JDS_ERR_NOMEM = -4,
+    JDS_ERR_CAPACITY = -5      /* caller's output buffer too small; the needed size is
+                                  in the size outputs of the call                    */
 } jds_status;
 
 /* subsampling_mode of models/compression_params.py:13 */
@@ -164,6 +166,28 @@ int jds_roundtrip_batch(jds_ctx* ctx, const jds_params* params, int n_frames,
                         jds_metrics* metrics);
 
 /*
+ * Tile-band sharding of ONE frame (second row): rows [row0, row1) of the frame as
+ * one rank's share of engines/pipeline.py:17-167, for single-image latency on several GPUs.
+ * params->height / width describe the WHOLE frame and rgb points at its first row (host or
+ * device; only the band and its halo are read / transferred).  row0 and row1 are multiples of
+ * 16 (row1 may also be the frame height).  The library runs the band with the halo of MCU rows
+ * that makes every owned pixel, coefficient and SSIM window identical to the whole-frame run
+ * (16 rows; 32 with the prefilter), then reduces over the band's OWN rows only:
+ *   recon_rows  [out] (row1-row0)*W*3 uint8: rows row0..row1 of reconstructed_image
+ *   coeffs_rows [out] the band's blocks, Y | Cb | Cr, each in block raster order: block rows
+ *               [row0/8, row1/8) of Y and [row0/8v, row1/8v) of Cb, Cr (v = 2 at 4:2:0)
+ *   metrics     [out] partial sums: sse over the band's rows, SSIM over the window centres in
+ *               the band (rows 3..H-4 of the frame), bits / nnz / blocks of the band's blocks.
+ * Adding the partials of all bands field by field gives the jds_metrics of jds_roundtrip on the
+ * whole frame (integers exactly; the fp64 sums up to summation order).  Error maps and hist50
+ * are whole-frame outputs (JDS_ERR_UNSUPPORTED), as is 4:2:0 with an odd height unless the band
+ * is the whole frame (cv2's area taps then depend on the frame height).
+ */
+int jds_roundtrip_band(jds_ctx* ctx, const jds_params* params, const uint8_t* rgb, int rgb_loc,
+                       int row0, int row1, uint8_t* recon_rows, int16_t* coeffs_rows, int out_loc,
+                       jds_metrics* metrics);
+
+/*
  * Quality sweep on one frame (gui/worker.py:55-74 BatchSweepWorker.run): the same
  * frame at each quality in qualities[0..n_q); params->quality is ignored.
  * recon is n_q frames or NULL (the sweep's consumers read only the metrics,
@@ -280,6 +304,32 @@ int jds_aliasing_metrics(jds_ctx* ctx, const uint8_t* a, const uint8_t* b, int l
  */
 int jds_entropy_bits(jds_ctx* ctx, const int16_t* coeffs, int loc, int height, int width,
                      int subsampling, uint64_t scan_bits[3]);
+
+/*
+ * The entropy-coded BYTES of those three scans, coded on the device: zig-zag order
+ * (utils/constants.py:18-27 ZIGZAG_ORDER, which the reference defines and never uses), DC
+ * differences, run/size Huffman codes of the Annex K tables, the final byte of each scan padded
+ * with 1-bits, 0x00 stuffed after every 0xFF (T.81 F.1.2, B.1.1.5).
+ *   out [out] the three scans back to back (scan k starts at scan_bytes[0] + .. + scan_bytes[k-1]),
+ *             host or device (out_loc); NULL = sizes only.  out_capacity < total returns
+ *             JDS_ERR_CAPACITY with scan_bytes / scan_bits filled.
+ * Values without a baseline code (DC difference beyond 11 bits, AC beyond 10 bits - the round
+ * trip never produces them: |q| <= 1016, engines/quantizer.py:22-24) return JDS_ERR_INVALID.
+ */
+int jds_entropy_encode(jds_ctx* ctx, const int16_t* coeffs, int loc, int height, int width,
+                       int subsampling, uint8_t* out, int out_loc, uint64_t out_capacity,
+                       uint64_t scan_bytes[3], uint64_t scan_bits[3]);
+/*
+ * A complete baseline JFIF file (SOI, APP0, DQT, SOF0, 4 x DHT, three non-interleaved
+ * SOS + scan, EOI) of a round trip's coefficients - the file the reference's "compression"
+ * stands for but never writes (utils/metrics.py:57-61).  qtable: the 64 raster-order values of
+ * jds_quant_table (one table for all components, engines/pipeline.py:43).  out: HOST buffer or
+ * NULL (size only); *out_bytes = file size.  Subsampled modes need even sizes (JPEG rounds
+ * component sizes up, engines/color_space.py:44-49 rounds down).
+ */
+int jds_jfif_encode(jds_ctx* ctx, const int16_t* coeffs, int loc, int height, int width,
+                    int subsampling, const double qtable[64], uint8_t* out, uint64_t out_capacity,
+                    uint64_t* out_bytes, uint64_t scan_bits[3]);
 
 /*
  * Stand-alone 8x8 block operators, exact (reference) arithmetic, host buffers:

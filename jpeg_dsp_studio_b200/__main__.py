@@ -49,6 +49,8 @@ def main(argv=None):
     ap.add_argument("--sweep", default=None, metavar="START:END:STEP",
                     help="rate-distortion sweep instead of a single run (BatchSweepWorker)")
     ap.add_argument("--output", default="reconstructed.png")
+    ap.add_argument("--jpeg", default=None, metavar="FILE",
+                    help="also write the coefficients as a baseline JPEG file (entropy-coded on the GPU)")
     args = ap.parse_args(argv)
 
     print("JPEG-DSP Studio - CLI Mode (B200 path)")
@@ -70,13 +72,20 @@ def main(argv=None):
             print(f"{q:3d} {r.bpp:7.3f} {r.psnr_y:8.2f} {r.ssim_y:8.4f} {r.psnr_rgb:9.2f} "
                   f"{r.ssim_rgb:9.4f} {r.compression_ratio:6.2f}x")
         return 0
-    result, _ = compress_reconstruct(image, params, precision=precision)
+    result, inter = compress_reconstruct(image, params, precision=precision)
     print(f"PSNR (Y): {result.psnr_y:.2f} dB")
     print(f"SSIM (Y): {result.ssim_y:.4f}")
     print(f"BPP: {result.bpp:.3f}")
     print(f"Compression Ratio: {result.compression_ratio:.2f}x")
     print(f"Runtime: {result.encode_time_ms + result.decode_time_ms:.1f} ms")
     print(f"Saved: {_save(args.output, result.reconstructed_image)}")
+    if args.jpeg:
+        from .utils.metrics import encode_jfif
+        data = encode_jfif(inter.all_quantized_coeffs, image.shape[:2], args.mode, args.quality)
+        with open(args.jpeg, "wb") as f:
+            f.write(data)
+        print(f"JPEG: {args.jpeg} ({len(data)} bytes, {8 * len(data) / (image.shape[0] * image.shape[1]):.3f} bpp "
+              "with entropy coding)")
     return 0
 
 

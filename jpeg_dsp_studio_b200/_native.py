@@ -13,6 +13,7 @@ LIB_PATH = os.environ.get("JDS_LIB", os.path.join(HERE, "libjds.so"))
 
 JDS_ABI_VERSION = 1
 JDS_OK, JDS_ERR_INVALID, JDS_ERR_UNSUPPORTED, JDS_ERR_CUDA, JDS_ERR_NOMEM = 0, -1, -2, -3, -4
+JDS_ERR_CAPACITY = -5
 JDS_SUB_444, JDS_SUB_422, JDS_SUB_420 = 0, 1, 2
 JDS_EXACT, JDS_FAST = 0, 1
 JDS_HOST, JDS_DEVICE = 0, 1
@@ -79,6 +80,14 @@ PROTOTYPES = {
                                        C.POINTER(JdsMetrics), C.POINTER(JdsMetrics)]),
     "jds_entropy_bits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.POINTER(C.c_uint64)]),
+    "jds_roundtrip_band": (C.c_int, [C.c_void_p, C.POINTER(JdsParams), C.c_void_p, C.c_int, C.c_int,
+                                     C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(JdsMetrics)]),
+    "jds_entropy_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_int, C.c_uint64, C.POINTER(C.c_uint64),
+                                     C.POINTER(C.c_uint64)]),
+    "jds_jfif_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  C.POINTER(C.c_double), C.c_void_p, C.c_uint64,
+                                  C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "jds_roundtrip_batch_records": (C.c_int, [C.c_void_p, C.POINTER(JdsParams), C.c_int, C.c_void_p,
                                               C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "jds_plot_payload": (C.c_int, [C.c_void_p, C.POINTER(JdsParams), C.c_void_p, C.c_int,

@@ -65,6 +65,7 @@ struct jds_ctx {
     double stage_ms[4] = {0, 0, 0, 0};   // forward, codec, inverse, ssim (accumulated)
     uint64_t stage_launches[4] = {0, 0, 0, 0};
     DevBuf planes, in, recon, coeffs, errs, metrics, tables, selected, payload, alias, fcoef;
+    DevBuf ent_sizes, ent_bits, ent_out, band;   // entropy bitstream: size passes, unstuffed bits, stuffed bytes
     void* h_metrics = nullptr;   // pinned
     size_t h_metrics_bytes = 0;
     void* h_tables = nullptr;    // pinned
@@ -195,7 +196,8 @@ extern "C" int jds_ctx_destroy(jds_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->planes, &c->in, &c->recon, &c->coeffs, &c->errs,
-                      &c->metrics, &c->tables, &c->selected, &c->payload, &c->alias, &c->fcoef};
+                      &c->metrics, &c->tables, &c->selected, &c->payload, &c->alias, &c->fcoef,
+                      &c->ent_sizes, &c->ent_bits, &c->ent_out, &c->band};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->h_metrics) cudaFreeHost(c->h_metrics);
@@ -1013,6 +1015,135 @@ static int compare_device(jds_ctx* c, const uint8_t* d_a, const uint8_t* d_b, in
     return JDS_OK;
 }
 
+// Tile-band sharding of ONE frame: the rows [row0, row1) of a frame as one
+// rank's share of engines/pipeline.py:17-167.  The band is run with a halo of whole MCU rows on
+// each interior edge - everything a pixel of the band depends on lies inside it:
+//   * 8x8 blocks / 16-row MCUs are independent (block_processor.py:19-48);
+//   * the bilinear chroma upsample reads one chroma sample beyond the band (color_space.py:64-65)
+//     and SSIM's 7x7 windows three reconstructed rows (utils/metrics.py:12-14): 16 rows cover both;
+//   * the 3x3 prefilter (color_space.py:39-40) reads one row beyond each chroma block, so the
+//     outermost halo MCU row of a prefiltered band is itself inexact - a second one is added.
+// The partial metrics are sums over the band's own rows / window centres / blocks, so adding the
+// partials of all bands (an all-reduce of a few dozen numbers) gives the frame's jds_metrics.
+extern "C" int jds_roundtrip_band(jds_ctx* c, const jds_params* p, const uint8_t* rgb, int rgb_loc,
+                                  int row0, int row1, uint8_t* recon_rows, int16_t* coeffs_rows,
+                                  int out_loc, jds_metrics* m) {
+    if (!c || !rgb || !m) return fail(JDS_ERR_INVALID, "NULL argument");
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (p->quality < 1 || p->quality > 100)
+        return fail(JDS_ERR_INVALID, "Quality must be 1-100, got %d", p->quality);
+    const int H = p->height, W = p->width, sub = p->subsampling;
+    if (row0 < 0 || row1 > H || row0 >= row1 || (row0 % 16) != 0 || ((row1 % 16) != 0 && row1 != H))
+        return fail(JDS_ERR_INVALID, "band [%d, %d) of %d rows: bounds must be multiples of 16 (or the last row)",
+                    row0, row1, H);
+    if (p->outputs & (JDS_OUT_ERR_Y | JDS_OUT_ERR_RGB | JDS_OUT_HIST))
+        return fail(JDS_ERR_UNSUPPORTED, "error maps and histogram are whole-frame outputs");
+    const bool whole = row0 == 0 && row1 == H;
+    if (sub == JDS_SUB_420 && (H & 1) && !whole)
+        return fail(JDS_ERR_UNSUPPORTED, "4:2:0 with an odd height: cv2.resize's area taps depend on the "
+                                         "whole height (engines/color_space.py:48-49), bands cannot reproduce them");
+    Geom gf;
+    if ((rc = make_geom(H, W, sub, &gf))) return rc;
+    const int halo = (p->prefilter && sub != JDS_SUB_444) ? 32 : 16;
+    const int e0 = row0 - halo > 0 ? row0 - halo : 0, e1 = row1 + halo < H ? row1 + halo : H;
+    const int he = e1 - e0;
+    jds_params pe = *p;
+    pe.height = he;
+    pe.outputs = JDS_OUT_RECON | JDS_OUT_COEFFS | JDS_OUT_PSNR;
+    UnitJob J;
+    memset(&J, 0, sizeof J);
+    if ((rc = make_geom(he, W, sub, &J.g))) return rc;
+    const Geom& g = J.g;
+    JDS_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const size_t row_bytes = (size_t)W * 3, ext_bytes = row_bytes * he;
+    const size_t ncoef = 64ull * (size_t)(g.nblk_y + 2 * g.nblk_c);
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const bool in_host = rgb_loc == JDS_HOST;
+    const size_t o_recon = in_host ? up(ext_bytes) : 0, o_coef = o_recon + up(ext_bytes);
+    if ((rc = ensure(c, c->band, o_coef + up(ncoef * 2)))) return rc;
+    uint8_t* base = (uint8_t*)c->band.p;
+    const uint8_t* d_in = rgb + row_bytes * e0;
+    if (in_host) {
+        JDS_CUDA(cudaMemcpyAsync(base, rgb + row_bytes * e0, ext_bytes, cudaMemcpyHostToDevice, s));
+        d_in = base;
+    }
+    uint8_t* d_recon = base + o_recon;
+    int16_t* d_coef = (int16_t*)(base + o_coef);
+    jds_metrics ext;
+    J.p = &pe;
+    J.units = 1;
+    J.rgb = d_in;
+    J.rgb_loc = JDS_DEVICE;
+    J.recon = d_recon;
+    J.coeffs = d_coef;
+    J.out_loc = JDS_DEVICE;
+    J.metrics = &ext;
+    if ((rc = run_job(c, J))) return rc;
+
+    // the band's own share of the metrics
+    if ((rc = ensure(c, c->metrics, sizeof(DevMetrics)))) return rc;
+    if ((rc = ensure_pinned(&c->h_metrics, &c->h_metrics_bytes, sizeof(DevMetrics)))) return rc;
+    DevMetrics* dm = (DevMetrics*)c->metrics.p;
+    JDS_CUDA(cudaMemsetAsync(dm, 0, sizeof(DevMetrics), s));
+    const size_t own_off = row_bytes * (size_t)(row0 - e0);
+    launch_sse_u8(d_in + own_off, d_recon + own_off, (long long)(row1 - row0) * W, dm, c->sm_count, s);
+    c->launches++;
+    // window centres of the frame are rows [3, H-3): this band's are [c0, c1)
+    const int c0 = row0 > 3 ? row0 : 3, c1 = row1 < H - 3 ? row1 : H - 3;
+    const bool want_ssim = (p->outputs & JDS_OUT_SSIM) != 0 && c1 > c0 && W >= 7;
+    if (want_ssim) {
+        const int hs = c1 - c0 + 6;
+        const size_t off = row_bytes * (size_t)(c0 - 3 - e0), fb = row_bytes * hs;
+        if (!c->legacy_ssim && ssim_strip_supported(hs, W, d_in + off, fb, d_recon + off, fb))
+            JDS_CUDA(launch_ssim_strip(hs, W, d_in + off, fb, d_recon + off, fb, dm, 1, true, false,
+                                       c->sm_count, s));
+        else
+            launch_ssim(true, hs, W, d_in + off, fb, d_recon + off, fb, dm, 1, s);
+        c->launches++;
+    }
+    // blocks of the band: block rows [row0/8, row1/8) of Y, [row0/8v, row1/8v) of Cb and Cr
+    const int v = sub == JDS_SUB_420 ? 2 : 1;
+    const int by0 = row0 / 8, by1 = row1 == H ? gf.nby_y : row1 / 8;
+    const int cy0 = row0 / (8 * v), cy1 = row1 == H ? gf.nby_c : row1 / (8 * v);
+    const size_t n_y = 64ull * (size_t)(by1 - by0) * gf.nbx_y, n_c = 64ull * (size_t)(cy1 - cy0) * gf.nbx_c;
+    const int16_t* src[3] = {d_coef + 64ull * (size_t)(by0 - e0 / 8) * g.nbx_y,
+                             d_coef + 64ull * ((size_t)g.nblk_y + (size_t)(cy0 - e0 / (8 * v)) * g.nbx_c),
+                             d_coef + 64ull * ((size_t)g.nblk_y + g.nblk_c + (size_t)(cy0 - e0 / (8 * v)) * g.nbx_c)};
+    const size_t cnt[3] = {n_y, n_c, n_c};
+    for (int k = 0; k < 3; ++k)
+        if (cnt[k]) {
+            launch_bitcount(src[k], cnt[k], dm, c->sm_count, s);
+            c->launches++;
+        }
+    JDS_CUDA(cudaGetLastError());
+    JDS_CUDA(cudaMemcpyAsync(c->h_metrics, dm, sizeof(DevMetrics), cudaMemcpyDeviceToHost, s));
+    const cudaMemcpyKind kind = out_loc == JDS_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    if ((p->outputs & JDS_OUT_RECON) && recon_rows)
+        JDS_CUDA(cudaMemcpyAsync(recon_rows, d_recon + own_off, row_bytes * (size_t)(row1 - row0), kind, s));
+    if ((p->outputs & JDS_OUT_COEFFS) && coeffs_rows) {
+        size_t at = 0;
+        for (int k = 0; k < 3; ++k) {
+            if (cnt[k]) JDS_CUDA(cudaMemcpyAsync(coeffs_rows + at, src[k], cnt[k] * 2, kind, s));
+            at += cnt[k];
+        }
+    }
+    JDS_CUDA(cudaStreamSynchronize(s));
+    const DevMetrics& d = *(const DevMetrics*)c->h_metrics;
+    memset(m, 0, sizeof *m);
+    m->sse_rgb = d.sse_rgb;
+    m->sse_y = d.sse_y;
+    for (int k = 0; k < 4; ++k) m->ssim_sum[k] = want_ssim ? d.ssim_sum[k] : 0.0;
+    m->ssim_count = want_ssim ? (uint64_t)(c1 - c0) * (uint64_t)(W - 6) : 0;
+    m->coeff_bits = d.coeff_bits;
+    m->nnz = d.nnz;
+    m->total_coeffs = n_y + 2 * n_c;
+    m->luma_blocks = (uint64_t)(by1 - by0) * gf.nbx_y;
+    m->gpu_ms = ext.gpu_ms;
+    return JDS_OK;
+}
+
 // One arm of AliasingDemoWorker.run (gui/dialogs/aliasing_demo_dialog.py:98-166):
 // _process_with_explicit_subsample(prefilter) - OpenCV float32 YCrCb, optional 5x5 blur,
 // [::2, ::2], bilinear re-enlargement, back to uint8 RGB (jds_alias.cu) - then the hot path at
@@ -1145,6 +1276,145 @@ extern "C" int jds_entropy_bits(jds_ctx* c, const int16_t* coeffs, int loc, int 
     JDS_CUDA(cudaMemcpyAsync(c->h_metrics, d_bits, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     JDS_CUDA(cudaStreamSynchronize(s));
     for (int k = 0; k < 3; ++k) scan_bits[k] = ((const unsigned long long*)c->h_metrics)[k];
+    return JDS_OK;
+}
+
+// The entropy-coded BYTES of the same three scans, produced on the device (jds_entropy.cu).
+// On success *d_scans points at the stuffed scans, back to back, in ctx scratch (valid until the
+// next entropy call on this context) and the stream has been synchronised.
+static int entropy_encode_device(jds_ctx* c, const int16_t* d_c, const Geom& g, const uint8_t** d_scans,
+                                 uint64_t scan_bytes[3], uint64_t scan_bits[3]) {
+    int rc;
+    cudaStream_t s = c->stream;
+    const EntropyGrid eg = make_entropy_grid(g.nblk_y, g.nblk_c);
+    const size_t nblk = (size_t)(g.nblk_y + 2 * g.nblk_c);
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    // [layout][bits per block][sum per CTA][offset per CTA]
+    const size_t o_bits = up(sizeof(EntropyLayout)), o_part = o_bits + up(nblk * 4),
+                 o_off = o_part + up((size_t)eg.ctas * 4), sizes_bytes = o_off + up((size_t)eg.ctas * 8);
+    if ((rc = ensure(c, c->ent_sizes, sizes_bytes))) return rc;
+    if ((rc = ensure_pinned(&c->h_metrics, &c->h_metrics_bytes, sizeof(DevMetrics) + sizeof(EntropyLayout))))
+        return rc;
+    uint8_t* base = (uint8_t*)c->ent_sizes.p;
+    EntropyLayout* d_lay = (EntropyLayout*)base;
+    uint32_t* d_blk = (uint32_t*)(base + o_bits);
+    uint32_t* d_part = (uint32_t*)(base + o_part);
+    unsigned long long* d_off = (unsigned long long*)(base + o_off);
+    EntropyLayout* h_lay = (EntropyLayout*)c->h_metrics;
+    JDS_CUDA(launch_entropy_sizes(d_c, eg, d_blk, d_part, d_off, d_lay, s));
+    c->launches += 2;
+    JDS_CUDA(cudaMemcpyAsync(h_lay, d_lay, sizeof(EntropyLayout), cudaMemcpyDeviceToHost, s));
+    JDS_CUDA(cudaStreamSynchronize(s));
+    for (int k = 0; k < 3; ++k) scan_bits[k] = h_lay->bits[k];
+    if (h_lay->invalid)
+        return fail(JDS_ERR_INVALID, "coefficients outside the baseline JPEG code tables "
+                                     "(DC difference beyond 11 bits or AC value beyond 10 bits)");
+    // unstuffed bits: whole 4096-byte chunks; then [count per chunk][offset per chunk]
+    const size_t ubytes = ((size_t)h_lay->total_ubytes + 4095) & ~(size_t)4095;
+    const size_t chunks = ubytes / 4096;
+    const size_t o_cnt = ubytes, o_coff = o_cnt + up(chunks * 4), bits_bytes = o_coff + up(chunks * 8);
+    if ((rc = ensure(c, c->ent_bits, bits_bytes))) return rc;
+    uint8_t* ub = (uint8_t*)c->ent_bits.p;
+    uint32_t* d_ubuf = (uint32_t*)ub;
+    uint32_t* d_cnt = (uint32_t*)(ub + o_cnt);
+    unsigned long long* d_coff = (unsigned long long*)(ub + o_coff);
+    JDS_CUDA(launch_entropy_pack(d_c, eg, d_blk, d_off, d_lay, d_ubuf, ubytes, s));
+    JDS_CUDA(launch_stuff_sizes(d_ubuf, ubytes, d_lay, d_cnt, d_coff, s));
+    c->launches += chunks ? 3 : 2;
+    JDS_CUDA(cudaMemcpyAsync(h_lay, d_lay, sizeof(EntropyLayout), cudaMemcpyDeviceToHost, s));
+    JDS_CUDA(cudaStreamSynchronize(s));
+    uint64_t total = 0;
+    for (int k = 0; k < 3; ++k) total += (scan_bytes[k] = h_lay->ubytes[k] + h_lay->ff[k]);
+    if (total != h_lay->stuffed_bytes)
+        return fail(JDS_ERR_CUDA, "entropy coder: stuffed size %llu != %llu", (unsigned long long)total,
+                    (unsigned long long)h_lay->stuffed_bytes);
+    if ((rc = ensure(c, c->ent_out, (size_t)total + 16))) return rc;
+    JDS_CUDA(launch_stuff_scatter(d_ubuf, ubytes, d_lay, d_coff, (uint8_t*)c->ent_out.p, s));
+    if (chunks) c->launches++;
+    JDS_CUDA(cudaStreamSynchronize(s));
+    *d_scans = (const uint8_t*)c->ent_out.p;
+    return JDS_OK;
+}
+
+static int entropy_input(jds_ctx* c, const int16_t* coeffs, int loc, const Geom& g, const int16_t** d_c) {
+    *d_c = coeffs;
+    if (loc != JDS_HOST) return JDS_OK;
+    const size_t ncoef = 64ull * (size_t)(g.nblk_y + 2 * g.nblk_c);
+    int rc;
+    if ((rc = ensure(c, c->coeffs, ncoef * 2))) return rc;
+    JDS_CUDA(cudaMemcpyAsync(c->coeffs.p, coeffs, ncoef * 2, cudaMemcpyHostToDevice, c->stream));
+    *d_c = (const int16_t*)c->coeffs.p;
+    return JDS_OK;
+}
+
+extern "C" int jds_entropy_encode(jds_ctx* c, const int16_t* coeffs, int loc, int height, int width,
+                                  int subsampling, uint8_t* out, int out_loc, uint64_t out_capacity,
+                                  uint64_t scan_bytes[3], uint64_t scan_bits[3]) {
+    if (!c || !coeffs || !scan_bytes || !scan_bits) return fail(JDS_ERR_INVALID, "NULL argument");
+    Geom g;
+    int rc = make_geom(height, width, subsampling, &g);
+    if (rc) return rc;
+    JDS_CUDA(cudaSetDevice(c->device));
+    const int16_t* d_c;
+    if ((rc = entropy_input(c, coeffs, loc, g, &d_c))) return rc;
+    const uint8_t* d_scans;
+    if ((rc = entropy_encode_device(c, d_c, g, &d_scans, scan_bytes, scan_bits))) return rc;
+    const uint64_t total = scan_bytes[0] + scan_bytes[1] + scan_bytes[2];
+    if (!out) return JDS_OK;
+    if (out_capacity < total)
+        return fail(JDS_ERR_CAPACITY, "output buffer of %llu bytes, the scans need %llu",
+                    (unsigned long long)out_capacity, (unsigned long long)total);
+    JDS_CUDA(cudaMemcpyAsync(out, d_scans, (size_t)total,
+                             out_loc == JDS_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, c->stream));
+    JDS_CUDA(cudaStreamSynchronize(c->stream));
+    return JDS_OK;
+}
+
+// A complete baseline JFIF file of the round trip's coefficients: what the reference would have
+// to write to put its "compressed" result on disk (it never does; utils/metrics.py:57-61 says
+// so).  Headers on the host, the three scans from the device coder above.
+extern "C" int jds_jfif_encode(jds_ctx* c, const int16_t* coeffs, int loc, int height, int width,
+                               int subsampling, const double qtable[64], uint8_t* out,
+                               uint64_t out_capacity, uint64_t* out_bytes, uint64_t scan_bits[3]) {
+    if (!c || !coeffs || !qtable || !out_bytes || !scan_bits) return fail(JDS_ERR_INVALID, "NULL argument");
+    Geom g;
+    int rc = make_geom(height, width, subsampling, &g);
+    if (rc) return rc;
+    if (height > 65535 || width > 65535) return fail(JDS_ERR_INVALID, "JPEG frames are at most 65535 x 65535");
+    // JPEG sizes a subsampled component with ceil(), the pipeline with floor()
+    // (engines/color_space.py:44-49): the two agree on even sizes only
+    if (subsampling != JDS_SUB_444 && ((width & 1) || (subsampling == JDS_SUB_420 && (height & 1))))
+        return fail(JDS_ERR_INVALID, "odd frame sizes: JPEG's component geometry differs from the pipeline's");
+    uint8_t q8[64];
+    for (int k = 0; k < 64; ++k) {
+        if (!(qtable[k] >= 1.0 && qtable[k] <= 255.0) || qtable[k] != (double)(int)qtable[k])
+            return fail(JDS_ERR_INVALID, "quantisation table entries must be integers in 1..255");
+        q8[k] = (uint8_t)qtable[k];
+    }
+    JDS_CUDA(cudaSetDevice(c->device));
+    const int16_t* d_c;
+    if ((rc = entropy_input(c, coeffs, loc, g, &d_c))) return rc;
+    const uint8_t* d_scans;
+    uint64_t scan_bytes[3];
+    if ((rc = entropy_encode_device(c, d_c, g, &d_scans, scan_bytes, scan_bits))) return rc;
+    const size_t head = jfif_write_headers(nullptr, height, width, subsampling, q8);
+    const uint64_t total = head + 3 * 10 + scan_bytes[0] + scan_bytes[1] + scan_bytes[2] + 2;
+    *out_bytes = total;
+    if (!out) return JDS_OK;
+    if (out_capacity < total)
+        return fail(JDS_ERR_CAPACITY, "output buffer of %llu bytes, the file needs %llu",
+                    (unsigned long long)out_capacity, (unsigned long long)total);
+    size_t at = jfif_write_headers(out, height, width, subsampling, q8);
+    size_t from = 0;
+    for (int k = 0; k < 3; ++k) {
+        at += jfif_write_sos(out + at, k);
+        JDS_CUDA(cudaMemcpyAsync(out + at, d_scans + from, (size_t)scan_bytes[k], cudaMemcpyDeviceToHost, c->stream));
+        at += (size_t)scan_bytes[k];
+        from += (size_t)scan_bytes[k];
+    }
+    JDS_CUDA(cudaStreamSynchronize(c->stream));
+    out[at++] = 0xFF;
+    out[at++] = 0xD9;
     return JDS_OK;
 }
 

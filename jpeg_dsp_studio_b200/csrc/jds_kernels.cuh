@@ -89,6 +89,38 @@ size_t selected_out_bytes();
 // non-interleaved scans; blocks [0,ny) Y, then nc Cb, then nc Cr
 cudaError_t launch_entropy_bits(const int16_t* coeffs, long long ny, long long nc,
                                 unsigned long long* scan_bits, cudaStream_t s);
+// the bitstream of those scans (jds_entropy.cu).  Every scan owns a run of CTAs of
+// ENTROPY_CTA_BLOCKS blocks each.
+constexpr int ENTROPY_CTA_BLOCKS = 64;
+struct EntropyGrid {
+    long long n[3];       // blocks of the scan
+    long long first[3];   // index of its first block in the coefficient array
+    int cta0[3];          // its first CTA
+    int ctas;
+};
+struct EntropyLayout {                    // device-resident result of the size passes
+    unsigned long long bits[3];           // entropy-coded bits of each scan
+    unsigned long long ubytes[3];         // ceil(bits / 8)
+    unsigned long long ubase[3];          // byte offset of the scan in the unstuffed buffer
+    unsigned long long ff[3];             // 0xFF bytes of the scan (each gets a stuffed 0x00)
+    unsigned long long total_ubytes;      // end of the last scan, rounded up to 4
+    unsigned long long stuffed_bytes;     // sum of ubytes + ff
+    unsigned int invalid;                 // a value outside the baseline code tables was seen
+    unsigned int pad;
+};
+EntropyGrid make_entropy_grid(long long ny, long long nc);
+cudaError_t launch_entropy_sizes(const int16_t* coeffs, const EntropyGrid& g, uint32_t* blk_bits,
+                                 uint32_t* part, unsigned long long* cta_off, EntropyLayout* lay,
+                                 cudaStream_t s);
+cudaError_t launch_entropy_pack(const int16_t* coeffs, const EntropyGrid& g, const uint32_t* blk_bits,
+                                const unsigned long long* cta_off, const EntropyLayout* lay,
+                                uint32_t* ubuf, size_t ubuf_bytes, cudaStream_t s);
+cudaError_t launch_stuff_sizes(const uint32_t* ubuf, size_t ubuf_bytes, EntropyLayout* lay, uint32_t* cnt,
+                               unsigned long long* chunk_off, cudaStream_t s);
+cudaError_t launch_stuff_scatter(const uint32_t* ubuf, size_t ubuf_bytes, const EntropyLayout* lay,
+                                 const unsigned long long* chunk_off, uint8_t* out, cudaStream_t s);
+size_t jfif_write_headers(uint8_t* out, int height, int width, int sub, const uint8_t q_raster[64]);
+size_t jfif_write_sos(uint8_t* out, int comp);
 // chroma-aliasing demo front end (jds_alias.cu)
 size_t alias_scratch_floats(int H, int W);
 int launch_alias_subsample(int H, int W, int prefilter, const uint8_t* rgb, float* scratch,

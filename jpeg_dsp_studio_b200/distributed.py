@@ -302,3 +302,87 @@ def batch_sharded(engine, frames_of_rank, n_total: int, quality=50, mode="4:2:0"
         "ssim_y": float(tot[6] / tot[7]) if tot[7] else float("nan"),
         "estimated_bits": bits, "bpp": float(bits / n_px), "nonzero_count": int(round(tot[9])),
     }
+
+
+# ---------------------------------------------------------------------------------------
+# tile-band sharding of ONE frame (second row): single-image latency
+# ---------------------------------------------------------------------------------------
+BAND_ALIGN = 16       # rows of one 4:2:0 MCU; band edges of jds_roundtrip_band
+
+
+def band_bounds(height: int, world: int) -> List[Optional[tuple]]:
+    """Rows ``(row0, row1)`` of every rank: the frame's 16-row MCU rows split as evenly as
+    possible, in order; ranks beyond the number of MCU rows get ``None``."""
+    if height < 1 or world < 1:
+        raise ValueError(f"bad height/world {height}/{world}")
+    mcu = (height + BAND_ALIGN - 1) // BAND_ALIGN
+    out, at = [], 0
+    for r in range(world):
+        n = mcu // world + (1 if r < mcu % world else 0)
+        if n == 0:
+            out.append(None)
+            continue
+        out.append((at * BAND_ALIGN, min((at + n) * BAND_ALIGN, height)))
+        at += n
+    return out
+
+
+def merge_band_records(records) -> np.ndarray:
+    """Sum of the bands' partial records (``record_from_metrics`` rows) = the frame's record:
+    every field after ``unit`` and ``quality`` is a sum over rows, windows or blocks."""
+    recs = np.asarray(records, dtype=np.float64).reshape(-1, len(RECORD_FIELDS))
+    out = recs.sum(axis=0)
+    out[0], out[1] = recs[0, 0], recs[0, 1]
+    return out
+
+
+def frame_banded(engine, image, quality=50, mode="4:2:0", prefilter=False, *, precision="exact",
+                 device=None, gather_recon=True) -> dict:
+    """One frame with its rows sharded over the ranks: this rank runs its band (plus the halo
+    ``jds_roundtrip_band`` adds), the partial metrics are summed with one ``all_reduce`` and -
+    if ``gather_recon`` - the reconstructed rows are exchanged with one ``all_gather``, so every
+    rank returns the whole frame's scalars (and image).  ``image``: the whole frame on every
+    rank (only the band and its halo are read).  Without an initialised process group the
+    single rank owns the whole frame."""
+    dist = _dist()
+    world = dist.get_world_size() if dist else 1
+    rank = dist.get_rank() if dist else 0
+    h, w = int(image.shape[0]), int(image.shape[1])
+    bounds = band_bounds(h, world)
+    mine = bounds[rank]
+    rec = np.zeros(len(RECORD_FIELDS), dtype=np.float64)
+    rows = None
+    if mine is not None:
+        out = engine.roundtrip_band(image, mine[0], mine[1], quality, mode, prefilter, precision=precision)
+        rec = record_from_metrics(0, quality, out.metrics)
+        rows = out.recon
+    rec[0], rec[1] = 0.0, 0.0                       # summed below; restored after the reduce
+    total = reduce_partials(rec, device=device)
+    total[0], total[1] = 0.0, float(quality)
+    result = {"band": mine, "bounds": bounds, "record": total,
+              "scalars": scalars_from_record(total, h, w), "recon_rows": rows, "recon": None}
+    if gather_recon:
+        result["recon"] = _gather_rows(rows, bounds, h, w, dist, device)
+    return result
+
+
+def _gather_rows(rows, bounds, h, w, dist, device):
+    """All-gather of the bands' reconstructed rows (padded to the tallest band)."""
+    import torch
+    if dist is None or dist.get_world_size() == 1:
+        return rows
+    cap = max((b[1] - b[0]) for b in bounds if b is not None)
+    on_gpu = device is not None and torch.device(device).type == "cuda"
+    dev = device if on_gpu else "cpu"
+    send = torch.zeros((cap, w, 3), dtype=torch.uint8, device=dev)
+    if rows is not None:
+        t = rows if isinstance(rows, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(rows))
+        send[:t.shape[0]].copy_(t)
+    recv = torch.empty((len(bounds) * cap, w, 3), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(recv, send)
+    parts = [recv[r * cap:r * cap + (b[1] - b[0])] for r, b in enumerate(bounds) if b is not None]
+    full = torch.cat(parts, dim=0)
+    assert full.shape[0] == h
+    if isinstance(rows, torch.Tensor) and rows.is_cuda:
+        return full
+    return full.cpu().numpy()

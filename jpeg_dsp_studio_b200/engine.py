@@ -279,6 +279,48 @@ class Engine:
                                             gp(ey), gp(ergb), loc, C.byref(m)))
         return RoundTripOutputs(recon, coeffs, ey, ergb, m, (h, w))
 
+    # -- tile-band sharding of one frame -----------------------------------
+    def roundtrip_band(self, image, row0: int, row1: int, quality=50, mode="4:2:0", prefilter=False, *,
+                       precision="exact", want_coeffs=False, want_ssim=True) -> RoundTripOutputs:
+        """Rows ``[row0, row1)`` of ``image`` as one rank's share of the round trip
+        (``jds_roundtrip_band``): ``recon`` holds only those rows, ``coeffs`` only the band's
+        blocks (Y | Cb | Cr), ``metrics`` the band's PARTIAL sums - add the partials of all
+        bands (``distributed.merge_band_records``) before turning them into PSNR / SSIM / bpp.
+        ``row0`` / ``row1``: multiples of 16, or the frame height."""
+        h, w, _ = self._frame_geometry(image)
+        ptr, loc, keep = self._in_ptr(image)
+        flags = N.JDS_OUT_RECON | N.JDS_OUT_PSNR
+        flags |= N.JDS_OUT_COEFFS if want_coeffs else 0
+        flags |= N.JDS_OUT_SSIM if want_ssim else 0
+        p = self._params(h, w, quality, mode, prefilter, precision, flags)
+        rows = int(row1) - int(row0)
+        if rows <= 0 or row0 < 0 or row1 > h:
+            raise ValueError(f"band [{row0}, {row1}) outside the {h}-row frame")
+        ncoef = 0
+        if want_coeffs:
+            v = 2 if mode == "4:2:0" else 1
+            hdiv = 1 if mode == "4:4:4" else 2
+            nb = lambda n: (n + 7) // 8
+            by = (nb(h) if row1 == h else row1 // 8) - row0 // 8
+            cy = (nb(h // v) if row1 == h else row1 // (8 * v)) - row0 // (8 * v)
+            ncoef = 64 * (by * nb(w) + 2 * cy * nb(w // hdiv))
+        m = N.JdsMetrics()
+        if loc == N.JDS_DEVICE:
+            import torch
+            recon = torch.empty((rows, w, 3), dtype=torch.uint8, device=keep.device)
+            coeffs = torch.empty(ncoef, dtype=torch.int16, device=keep.device) if want_coeffs else None
+            gp = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        else:
+            recon = host_array((rows, w, 3), np.uint8)
+            coeffs = host_array((ncoef,), np.int16) if want_coeffs else None
+            gp = lambda t: C.c_void_p(t.ctypes.data) if t is not None else None
+        with self._lock:
+            N.check(self._lib.jds_roundtrip_band(self._ctx, C.byref(p), ptr, loc, int(row0), int(row1),
+                                                 gp(recon), gp(coeffs), loc, C.byref(m)))
+        if loc == N.JDS_DEVICE:
+            self._order_torch_after(recon)
+        return RoundTripOutputs(recon, coeffs, None, None, m, (h, w))
+
     # -- GUI plot payload (SURVEY 8f #2) -------------------------------------------------
     def plot_payload(self, image, quality=50, mode="4:2:0", prefilter=False, *,
                      precision="exact", want_heat_rgb=False, want_ssim=True,
@@ -395,6 +437,13 @@ class Engine:
         """Exact bits of the three baseline-JPEG scans (Y, Cb, Cr; Annex K Huffman tables) of
         an ``all_quantized_coeffs`` array (int16 NumPy array or torch tensor, host or CUDA)."""
         sub = _mode_code(mode)
+        ptr, loc, keep, _ = self._coeff_ptr(coeffs, height, width, sub, mode)
+        out = (C.c_uint64 * 3)()
+        with self._lock:
+            N.check(self._lib.jds_entropy_bits(self._ctx, ptr, loc, int(height), int(width), sub, out))
+        return [int(out[0]), int(out[1]), int(out[2])]
+
+    def _coeff_ptr(self, coeffs, height, width, sub, mode):
         n = C.c_uint64()
         N.check(self._lib.jds_coeff_count(int(height), int(width), sub, C.byref(n)))
         if _is_torch(coeffs):
@@ -412,10 +461,56 @@ class Engine:
             ptr, loc, keep, size = C.c_void_p(a.ctypes.data), N.JDS_HOST, a, a.size
         if size != n.value:
             raise ValueError(f"expected {n.value} coefficients for {height}x{width} {mode}, got {size}")
-        out = (C.c_uint64 * 3)()
+        return ptr, loc, keep, int(n.value)
+
+    # -- entropy-coded bytes (the bitstream itself, coded on the device) --------
+    def entropy_encode(self, coeffs, height: int, width: int, mode="4:2:0"):
+        """The three baseline-JPEG scans (Y, Cb, Cr) of an ``all_quantized_coeffs`` array as
+        entropy-coded bytes (zig-zag of utils/constants.py:18-27, Annex K Huffman tables, byte
+        stuffing and padding included): ``([bytes_Y, bytes_Cb, bytes_Cr], [bits_Y, bits_Cb, bits_Cr])``."""
+        sub = _mode_code(mode)
+        ptr, loc, keep, ncoef = self._coeff_ptr(coeffs, height, width, sub, mode)
+        nbytes, nbits = (C.c_uint64 * 3)(), (C.c_uint64 * 3)()
+        cap = 2 * ncoef           # the raw int16 array; real scans are far smaller
         with self._lock:
-            N.check(self._lib.jds_entropy_bits(self._ctx, ptr, loc, int(height), int(width), sub, out))
-        return [int(out[0]), int(out[1]), int(out[2])]
+            while True:
+                out = np.empty(cap, dtype=np.uint8)
+                rc = self._lib.jds_entropy_encode(self._ctx, ptr, loc, int(height), int(width), sub,
+                                                  C.c_void_p(out.ctypes.data), N.JDS_HOST, cap, nbytes, nbits)
+                if rc != N.JDS_ERR_CAPACITY:
+                    N.check(rc)
+                    break
+                cap = int(sum(nbytes))
+        ends = np.cumsum([int(b) for b in nbytes])
+        scans = [out[e - int(b):e].tobytes() for e, b in zip(ends, nbytes)]
+        return scans, [int(b) for b in nbits]
+
+    def jfif_encode(self, coeffs, height: int, width: int, mode="4:2:0", quality: int = 50, qtable=None):
+        """A complete baseline JFIF file (bytes) of a round trip's coefficients, entropy-coded on
+        the device; ``qtable`` (8x8, integers 1..255) defaults to the round trip's own table for
+        ``quality`` (engines/quantizer.py:7-19).  Returns ``(file_bytes, scan_bits)``."""
+        sub = _mode_code(mode)
+        ptr, loc, keep, ncoef = self._coeff_ptr(coeffs, height, width, sub, mode)
+        q = (C.c_double * 64)()
+        if qtable is None:
+            N.check(self._lib.jds_quant_table(int(quality), q))
+        else:
+            flat = np.asarray(qtable, dtype=np.float64).reshape(-1)
+            if flat.size != 64:
+                raise ValueError("qtable must have 64 entries")
+            q[:] = flat.tolist()
+        nbytes, nbits = C.c_uint64(), (C.c_uint64 * 3)()
+        cap = 2 * ncoef + 1024
+        with self._lock:
+            while True:
+                out = np.empty(cap, dtype=np.uint8)
+                rc = self._lib.jds_jfif_encode(self._ctx, ptr, loc, int(height), int(width), sub, q,
+                                               C.c_void_p(out.ctypes.data), cap, C.byref(nbytes), nbits)
+                if rc != N.JDS_ERR_CAPACITY:
+                    N.check(rc)
+                    break
+                cap = int(nbytes.value)
+        return out[:int(nbytes.value)].tobytes(), [int(b) for b in nbits]
 
     def selected_block(self, image, quality, block_row, block_col):
         """IntermediateData.selected_block_* (engines/pipeline.py:126-151) or None."""

@@ -225,3 +225,22 @@ def estimate_bitrate_huffman(quantized_coeffs, original_shape, subsampling_mode:
         'total_coeffs': int(q.size),
         'label': HUFFMAN_LABEL,
     }
+
+
+def encode_jfif(quantized_coeffs, original_shape, subsampling_mode: str = '4:2:0', quality: int = 50,
+                qtable=None) -> bytes:
+    """The baseline JPEG file the round trip's ``all_quantized_coeffs`` stand for - the
+    reference stops at an estimate (utils/metrics.py:57-61) and never uses its
+    ``ZIGZAG_ORDER`` (utils/constants.py:18-27).  Zig-zag scan, DC prediction, Annex K Huffman
+    coding, padding and 0xFF stuffing run on the GPU (``jds_jfif_encode``); any JPEG decoder
+    reads the result.  ``qtable`` defaults to the table of ``quality``
+    (engines/quantizer.py:7-19), the one the round trip quantised with."""
+    from ..engine import get_engine
+    h, w = original_shape
+    q = np.asarray(quantized_coeffs)
+    if q.dtype != np.int16:
+        if q.size and (q.max() > 32767 or q.min() < -32767):
+            raise ValueError("coefficients outside the int16 range")
+        q = q.astype(np.int16)
+    data, _ = get_engine().jfif_encode(q.reshape(-1), h, w, subsampling_mode, quality, qtable)
+    return data

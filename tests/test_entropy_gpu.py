@@ -83,3 +83,104 @@ def test_4k_frame_consistency(J):
     band = img[:64]
     o = eng.roundtrip(band, 50, "4:2:0", False, precision="exact", want_coeffs=True)
     assert eng.entropy_bits(o.coeffs, 64, 3840, "4:2:0") == E.huffman_scan_bits(o.coeffs, (64, 3840), "4:2:0")
+
+
+# ---------------------------------------------------------------------------------------
+# the bitstream itself (jds_entropy_encode / jds_jfif_encode), coded on the device
+# ---------------------------------------------------------------------------------------
+def _oracle_scans(coeffs, shape, mode):
+    comps = E.split_components(coeffs, shape, mode)
+    out = [E._encode_scan(comps[k], 0 if k == 0 else 1) for k in range(3)]
+    return [d for d, _ in out], [b for _, b in out]
+
+
+@pytest.mark.parametrize("shape,q,mode,pf", [
+    ((64, 96), 50, "4:2:0", False), ((64, 96), 5, "4:4:4", False), ((64, 96), 100, "4:2:2", True),
+    ((57, 75), 35, "4:2:0", True), ((8, 8), 50, "4:4:4", False), ((33, 47), 90, "4:2:2", False),
+    ((256, 256), 75, "4:2:0", False), ((120, 520), 98, "4:4:4", False),
+])
+def test_scan_bytes_match_oracle(J, shape, q, mode, pf):
+    """bytes of the three scans, stuffing and padding included, host and device input"""
+    import torch
+    from jpeg_dsp_studio_b200.utils import test_images as TI
+    eng = J.get_engine()
+    for img in (CS.rand_rgb(sum(shape) + q, *shape), np.ascontiguousarray(TI.generate_photo(520)[:shape[0], :shape[1]])):
+        _, inter = J.compress_reconstruct(img, J.CompressionParams(quality=q, subsampling_mode=mode, use_prefilter=pf))
+        want, want_bits = _oracle_scans(inter.all_quantized_coeffs, shape, mode)
+        got, bits = eng.entropy_encode(inter.all_quantized_coeffs, shape[0], shape[1], mode)
+        assert bits == want_bits
+        assert got == want
+        d = torch.from_numpy(np.ascontiguousarray(inter.all_quantized_coeffs)).cuda()
+        got_d, bits_d = eng.entropy_encode(d, shape[0], shape[1], mode)
+        assert got_d == want and bits_d == want_bits
+
+
+def test_scan_bytes_extremes(J):
+    """hand-built coefficients: stuffed 0xFF runs, ZRL chains, category-11 DC differences,
+    all-zero scans, a scan whose size is a whole number of bytes"""
+    eng = J.get_engine()
+    h, w = 24, 40
+    n = 15
+    rng = np.random.default_rng(11)
+    c = np.zeros((3 * n, 64), dtype=np.int16)
+    c[:, 0] = rng.choice([-1024, 1016, 0, 5], size=3 * n)
+    c[1, 63] = -1
+    c[2, 1] = 1023
+    c[20, 62] = 77
+    c[40] = rng.integers(-1023, 1024, 64)
+    c[7] = 1023                                           # long codes + all-ones amplitudes: many 0xFF
+    c[8] = -1023
+    for arr in (c, np.zeros_like(c), np.full_like(c, 1023), np.full_like(c, -1)):
+        want, want_bits = _oracle_scans(arr.ravel(), (h, w), "4:4:4")
+        got, bits = eng.entropy_encode(arr.ravel(), h, w, "4:4:4")
+        assert bits == want_bits and got == want
+    # values without a baseline code are refused, not mis-coded
+    bad = c.copy()
+    bad[3, 5] = 1024
+    with pytest.raises(Exception, match="baseline"):
+        eng.entropy_encode(bad.ravel(), h, w, "4:4:4")
+    bad = c.copy()
+    bad[3, 0], bad[4, 0] = 2047, -2047
+    with pytest.raises(Exception, match="baseline"):
+        eng.entropy_encode(bad.ravel(), h, w, "4:4:4")
+
+
+@pytest.mark.parametrize("shape,q,mode", [((240, 320), 50, "4:2:0"), ((96, 64), 10, "4:2:2"), ((72, 88), 95, "4:4:4")])
+def test_jfif_file_matches_oracle_and_decodes(J, shape, q, mode):
+    """the whole file equals the oracle's (which tests/test_entropy_cpu.py pins to libjpeg-turbo)
+    and libjpeg-turbo (OpenCV) decodes it to the round trip's own reconstruction"""
+    cv2 = pytest.importorskip("cv2")
+    from jpeg_dsp_studio_b200.utils import metrics as M
+    img = CS.photo_tiled(*shape)
+    res, inter = J.compress_reconstruct(img, J.CompressionParams(quality=q, subsampling_mode=mode))
+    want, want_bits = E.encode_jfif(inter.all_quantized_coeffs, shape, mode, P.scale_quant_matrix(q))
+    data = M.encode_jfif(inter.all_quantized_coeffs, shape, mode, q)
+    assert data == want
+    _, bits = J.get_engine().jfif_encode(inter.all_quantized_coeffs, shape[0], shape[1], mode, q)
+    assert bits == want_bits
+    dec = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
+    assert dec is not None and dec.shape == img.shape
+    diff = np.abs(dec[:, :, ::-1].astype(int) - res.reconstructed_image.astype(int))
+    assert diff.mean() < 1.5                               # integer IDCT / fancy upsampling vs ours
+    with pytest.raises(Exception, match="odd frame"):
+        J.get_engine().jfif_encode(np.zeros(64 * 6, np.int16), 15, 16, "4:2:0", q)
+
+
+def test_4k_bitstream_properties(J):
+    """full size: the coder's output decodes (oracle decoder on a prefix is too slow - use
+    libjpeg) to the round trip's reconstruction, and the sizes agree with jds_entropy_bits"""
+    cv2 = pytest.importorskip("cv2")
+    img = CS.photo_tiled(2160, 3840)
+    eng = J.get_engine()
+    out = eng.roundtrip(img, 50, "4:2:0", False, precision="exact", want_coeffs=True)
+    coeffs = out.coeffs
+    scans, bits = eng.entropy_encode(coeffs, 2160, 3840, "4:2:0")
+    assert bits == eng.entropy_bits(coeffs, 2160, 3840, "4:2:0")
+    for s, b in zip(scans, bits):
+        assert len(s) == (b + 7) // 8 + s.count(b"\xff\x00")
+        assert b"\xff" not in s.replace(b"\xff\x00", b"")
+    data, _ = eng.jfif_encode(coeffs, 2160, 3840, "4:2:0", 50)
+    dec = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
+    recon = out.recon if isinstance(out.recon, np.ndarray) else out.recon.cpu().numpy()
+    assert dec.shape == recon.shape
+    assert np.abs(dec[:, :, ::-1].astype(int) - recon.astype(int)).mean() < 1.5
