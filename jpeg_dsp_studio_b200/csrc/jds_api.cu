@@ -386,6 +386,11 @@ struct UnitJob {
     // jds_sweep_records: device-resident fp64 records instead of host structs, no synchronisation
     double* d_records;
     int rec_capacity, unit0, unit_step;
+    // jds_roundtrip_band: no whole-frame comparison; `tail` enqueues the band's own reductions and
+    // copies behind the kernels, before the job's single synchronisation
+    bool no_compare;
+    int (*tail)(jds_ctx*, void*, cudaStream_t);
+    void* tail_arg;
 };
 
 // Kernels of one chunk of `n` units on the compute stream.  Returns which stages ran.
@@ -461,10 +466,12 @@ static int launch_chunk(jds_ctx* c, const UnitJob& J, const ChunkPtrs& P, int n,
         }
         ran[1] = true;
         ran[2] = false;
-        ran[3] = true;      // squared errors always come from the strip kernel here
-        JDS_CUDA(launch_ssim_strip(g.H, g.W, P.d_rgb, P.rgb_stride, P.d_recon, frame_bytes,
-                                   P.d_metrics, n, want_ssim, true, c->sm_count, s));
-        c->launches++;
+        ran[3] = !J.no_compare;      // squared errors always come from the strip kernel here
+        if (ran[3]) {
+            JDS_CUDA(launch_ssim_strip(g.H, g.W, P.d_rgb, P.rgb_stride, P.d_recon, frame_bytes,
+                                       P.d_metrics, n, want_ssim, true, c->sm_count, s));
+            c->launches++;
+        }
     } else if (exact && !c->no_fused && !P.d_ey && !P.d_ergb && !g.general &&
                fused_supported(g, p->prefilter, P.d_rgb, P.rgb_stride, P.d_recon, frame_bytes) &&
                ssim_strip_supported(g.H, g.W, P.d_rgb, P.rgb_stride, P.d_recon, frame_bytes)) {
@@ -499,10 +506,12 @@ static int launch_chunk(jds_ctx* c, const UnitJob& J, const ChunkPtrs& P, int n,
         }
         ran[1] = true;
         ran[2] = false;
-        ran[3] = true;
-        JDS_CUDA(launch_ssim_strip(g.H, g.W, P.d_rgb, P.rgb_stride, P.d_recon, frame_bytes,
-                                   P.d_metrics, n, want_ssim, true, c->sm_count, s));
-        c->launches++;
+        ran[3] = !J.no_compare;
+        if (ran[3]) {
+            JDS_CUDA(launch_ssim_strip(g.H, g.W, P.d_rgb, P.rgb_stride, P.d_recon, frame_bytes,
+                                       P.d_metrics, n, want_ssim, true, c->sm_count, s));
+            c->launches++;
+        }
     } else {
         ran[0] = !J.shared_input || P.first_chunk;
         ran[1] = ran[2] = true;
@@ -783,6 +792,7 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
         c->launches++;
         return JDS_OK;
     }
+    if (J.tail && (rc = J.tail(c, J.tail_arg, s))) return rc;
     JDS_CUDA(cudaMemcpyAsync(h_metrics, d_metrics, sizeof(DevMetrics) * J.units,
                              cudaMemcpyDeviceToHost, s));
     if (pipelined) {
@@ -1015,6 +1025,56 @@ static int compare_device(jds_ctx* c, const uint8_t* d_a, const uint8_t* d_b, in
     return JDS_OK;
 }
 
+// The band's own share of the metrics and outputs, enqueued behind the kernels of its extent
+// (UnitJob::tail): squared errors over its rows, SSIM over its window centres, bit counts over its
+// blocks, then the copies of its rows / blocks to the caller.
+struct BandTail {
+    const uint8_t* d_in;
+    const uint8_t* d_recon;
+    int W, sse_row0, sse_rows, ssim_row0, ssim_rows;
+    const int16_t* src[3];
+    size_t cnt[3];
+    uint8_t* recon_rows;
+    int16_t* coeffs_rows;
+    cudaMemcpyKind kind;
+};
+
+static int band_tail(jds_ctx* c, void* arg, cudaStream_t s) {
+    const BandTail& T = *(const BandTail*)arg;
+    DevMetrics* dm = (DevMetrics*)c->metrics.p + 1;
+    const size_t row_bytes = (size_t)T.W * 3;
+    JDS_CUDA(cudaMemsetAsync(dm, 0, sizeof(DevMetrics), s));
+    const size_t own = row_bytes * (size_t)T.sse_row0;
+    launch_sse_u8(T.d_in + own, T.d_recon + own, (long long)T.sse_rows * T.W, dm, c->sm_count, s);
+    c->launches++;
+    if (T.ssim_rows) {
+        const size_t off = row_bytes * (size_t)T.ssim_row0, fb = row_bytes * (size_t)T.ssim_rows;
+        if (!c->legacy_ssim && ssim_strip_supported(T.ssim_rows, T.W, T.d_in + off, fb, T.d_recon + off, fb))
+            JDS_CUDA(launch_ssim_strip(T.ssim_rows, T.W, T.d_in + off, fb, T.d_recon + off, fb, dm, 1, true,
+                                       false, c->sm_count, s));
+        else
+            launch_ssim(true, T.ssim_rows, T.W, T.d_in + off, fb, T.d_recon + off, fb, dm, 1, s);
+        c->launches++;
+    }
+    for (int k = 0; k < 3; ++k)
+        if (T.cnt[k]) {
+            launch_bitcount(T.src[k], T.cnt[k], dm, c->sm_count, s);
+            c->launches++;
+        }
+    JDS_CUDA(cudaGetLastError());
+    JDS_CUDA(cudaMemcpyAsync((DevMetrics*)c->h_metrics + 1, dm, sizeof(DevMetrics), cudaMemcpyDeviceToHost, s));
+    if (T.recon_rows)
+        JDS_CUDA(cudaMemcpyAsync(T.recon_rows, T.d_recon + own, row_bytes * (size_t)T.sse_rows, T.kind, s));
+    if (T.coeffs_rows) {
+        size_t at = 0;
+        for (int k = 0; k < 3; ++k) {
+            if (T.cnt[k]) JDS_CUDA(cudaMemcpyAsync(T.coeffs_rows + at, T.src[k], T.cnt[k] * 2, T.kind, s));
+            at += T.cnt[k];
+        }
+    }
+    return JDS_OK;
+}
+
 // Tile-band sharding of ONE frame: the rows [row0, row1) of a frame as one
 // rank's share of engines/pipeline.py:17-167.  The band is run with a halo of whole MCU rows on
 // each interior edge - everything a pixel of the band depends on lies inside it:
@@ -1071,6 +1131,33 @@ extern "C" int jds_roundtrip_band(jds_ctx* c, const jds_params* p, const uint8_t
     }
     uint8_t* d_recon = base + o_recon;
     int16_t* d_coef = (int16_t*)(base + o_coef);
+    // accumulator [1] (device and pinned host) is the band's; [0] is run_job's whole-extent one
+    if ((rc = ensure(c, c->metrics, 2 * sizeof(DevMetrics)))) return rc;
+    if ((rc = ensure_pinned(&c->h_metrics, &c->h_metrics_bytes, 2 * sizeof(DevMetrics)))) return rc;
+    BandTail T;
+    T.d_in = d_in;
+    T.d_recon = d_recon;
+    T.W = W;
+    T.sse_row0 = row0 - e0;
+    T.sse_rows = row1 - row0;
+    // window centres of the frame are rows [3, H-3): this band's are [c0, c1)
+    const int c0 = row0 > 3 ? row0 : 3, c1 = row1 < H - 3 ? row1 : H - 3;
+    const bool want_ssim = (p->outputs & JDS_OUT_SSIM) != 0 && c1 > c0 && W >= 7;
+    T.ssim_row0 = want_ssim ? c0 - 3 - e0 : 0;
+    T.ssim_rows = want_ssim ? c1 - c0 + 6 : 0;
+    // blocks of the band: block rows [row0/8, row1/8) of Y, [row0/8v, row1/8v) of Cb and Cr
+    const int v = sub == JDS_SUB_420 ? 2 : 1;
+    const int by0 = row0 / 8, by1 = row1 == H ? gf.nby_y : row1 / 8;
+    const int cy0 = row0 / (8 * v), cy1 = row1 == H ? gf.nby_c : row1 / (8 * v);
+    const size_t n_y = 64ull * (size_t)(by1 - by0) * gf.nbx_y, n_c = 64ull * (size_t)(cy1 - cy0) * gf.nbx_c;
+    T.src[0] = d_coef + 64ull * (size_t)(by0 - e0 / 8) * g.nbx_y;
+    T.src[1] = d_coef + 64ull * ((size_t)g.nblk_y + (size_t)(cy0 - e0 / (8 * v)) * g.nbx_c);
+    T.src[2] = T.src[1] + 64ull * (size_t)g.nblk_c;
+    T.cnt[0] = n_y;
+    T.cnt[1] = T.cnt[2] = n_c;
+    T.recon_rows = ((p->outputs & JDS_OUT_RECON) && recon_rows) ? recon_rows : nullptr;
+    T.coeffs_rows = ((p->outputs & JDS_OUT_COEFFS) && coeffs_rows) ? coeffs_rows : nullptr;
+    T.kind = out_loc == JDS_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
     jds_metrics ext;
     J.p = &pe;
     J.units = 1;
@@ -1080,57 +1167,11 @@ extern "C" int jds_roundtrip_band(jds_ctx* c, const jds_params* p, const uint8_t
     J.coeffs = d_coef;
     J.out_loc = JDS_DEVICE;
     J.metrics = &ext;
-    if ((rc = run_job(c, J))) return rc;
-
-    // the band's own share of the metrics
-    if ((rc = ensure(c, c->metrics, sizeof(DevMetrics)))) return rc;
-    if ((rc = ensure_pinned(&c->h_metrics, &c->h_metrics_bytes, sizeof(DevMetrics)))) return rc;
-    DevMetrics* dm = (DevMetrics*)c->metrics.p;
-    JDS_CUDA(cudaMemsetAsync(dm, 0, sizeof(DevMetrics), s));
-    const size_t own_off = row_bytes * (size_t)(row0 - e0);
-    launch_sse_u8(d_in + own_off, d_recon + own_off, (long long)(row1 - row0) * W, dm, c->sm_count, s);
-    c->launches++;
-    // window centres of the frame are rows [3, H-3): this band's are [c0, c1)
-    const int c0 = row0 > 3 ? row0 : 3, c1 = row1 < H - 3 ? row1 : H - 3;
-    const bool want_ssim = (p->outputs & JDS_OUT_SSIM) != 0 && c1 > c0 && W >= 7;
-    if (want_ssim) {
-        const int hs = c1 - c0 + 6;
-        const size_t off = row_bytes * (size_t)(c0 - 3 - e0), fb = row_bytes * hs;
-        if (!c->legacy_ssim && ssim_strip_supported(hs, W, d_in + off, fb, d_recon + off, fb))
-            JDS_CUDA(launch_ssim_strip(hs, W, d_in + off, fb, d_recon + off, fb, dm, 1, true, false,
-                                       c->sm_count, s));
-        else
-            launch_ssim(true, hs, W, d_in + off, fb, d_recon + off, fb, dm, 1, s);
-        c->launches++;
-    }
-    // blocks of the band: block rows [row0/8, row1/8) of Y, [row0/8v, row1/8v) of Cb and Cr
-    const int v = sub == JDS_SUB_420 ? 2 : 1;
-    const int by0 = row0 / 8, by1 = row1 == H ? gf.nby_y : row1 / 8;
-    const int cy0 = row0 / (8 * v), cy1 = row1 == H ? gf.nby_c : row1 / (8 * v);
-    const size_t n_y = 64ull * (size_t)(by1 - by0) * gf.nbx_y, n_c = 64ull * (size_t)(cy1 - cy0) * gf.nbx_c;
-    const int16_t* src[3] = {d_coef + 64ull * (size_t)(by0 - e0 / 8) * g.nbx_y,
-                             d_coef + 64ull * ((size_t)g.nblk_y + (size_t)(cy0 - e0 / (8 * v)) * g.nbx_c),
-                             d_coef + 64ull * ((size_t)g.nblk_y + g.nblk_c + (size_t)(cy0 - e0 / (8 * v)) * g.nbx_c)};
-    const size_t cnt[3] = {n_y, n_c, n_c};
-    for (int k = 0; k < 3; ++k)
-        if (cnt[k]) {
-            launch_bitcount(src[k], cnt[k], dm, c->sm_count, s);
-            c->launches++;
-        }
-    JDS_CUDA(cudaGetLastError());
-    JDS_CUDA(cudaMemcpyAsync(c->h_metrics, dm, sizeof(DevMetrics), cudaMemcpyDeviceToHost, s));
-    const cudaMemcpyKind kind = out_loc == JDS_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
-    if ((p->outputs & JDS_OUT_RECON) && recon_rows)
-        JDS_CUDA(cudaMemcpyAsync(recon_rows, d_recon + own_off, row_bytes * (size_t)(row1 - row0), kind, s));
-    if ((p->outputs & JDS_OUT_COEFFS) && coeffs_rows) {
-        size_t at = 0;
-        for (int k = 0; k < 3; ++k) {
-            if (cnt[k]) JDS_CUDA(cudaMemcpyAsync(coeffs_rows + at, src[k], cnt[k] * 2, kind, s));
-            at += cnt[k];
-        }
-    }
-    JDS_CUDA(cudaStreamSynchronize(s));
-    const DevMetrics& d = *(const DevMetrics*)c->h_metrics;
+    J.no_compare = true;
+    J.tail = band_tail;
+    J.tail_arg = &T;
+    if ((rc = run_job(c, J))) return rc;          // kernels, tail, one synchronisation
+    const DevMetrics& d = ((const DevMetrics*)c->h_metrics)[1];
     memset(m, 0, sizeof *m);
     m->sse_rgb = d.sse_rgb;
     m->sse_y = d.sse_y;

@@ -374,11 +374,15 @@ def _gather_rows(rows, bounds, h, w, dist, device):
     cap = max((b[1] - b[0]) for b in bounds if b is not None)
     on_gpu = device is not None and torch.device(device).type == "cuda"
     dev = device if on_gpu else "cpu"
-    send = torch.zeros((cap, w, 3), dtype=torch.uint8, device=dev)
+    key = ("rows", len(bounds), cap, w, str(dev))
+    bufs = _gather_cache.get(key)
+    if bufs is None:
+        bufs = _gather_cache[key] = (torch.zeros((cap, w, 3), dtype=torch.uint8, device=dev),
+                                     torch.empty((len(bounds) * cap, w, 3), dtype=torch.uint8, device=dev))
+    send, recv = bufs
     if rows is not None:
         t = rows if isinstance(rows, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(rows))
         send[:t.shape[0]].copy_(t)
-    recv = torch.empty((len(bounds) * cap, w, 3), dtype=torch.uint8, device=dev)
     dist.all_gather_into_tensor(recv, send)
     parts = [recv[r * cap:r * cap + (b[1] - b[0])] for r, b in enumerate(bounds) if b is not None]
     full = torch.cat(parts, dim=0)
