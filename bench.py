@@ -494,6 +494,13 @@ def run_ours(args):
         reduce_partials(outs)
         return outs
 
+    def step_host_metrics(precision):
+        # what the batch / sweep consumers read (gui/worker.py:66-72: scalars only): frames go up,
+        # only the metric structs come back - compress_batch(keep_images=False)
+        outs = eng.roundtrip_batch(host_in, QUALITY, MODE, PREFILTER, precision=precision, want_recon=False)
+        reduce_partials(outs)
+        return outs
+
     def timed(fn, precision, steps, warmup, sample_clocks=False, stage_timing=False):
         eng.set_stage_timing(stage_timing)
         for _ in range(warmup):
@@ -555,6 +562,8 @@ def run_ours(args):
 
     ms_e2e, _, _, _, _ = timed(step_host, "fast", K, Wm)
     e2e = world * px_per_step * K / (ms_e2e / 1e3) / 1e6
+    ms_e2e_m, _, _, _, _ = timed(step_host_metrics, "fast", K, Wm)
+    e2e_metrics = world * px_per_step * K / (ms_e2e_m / 1e3) / 1e6
 
     Kx = max(1, min(K, 3))
     ms_x, stages_x, _, _, outs_x = timed(step_device, "exact", Kx, 1, stage_timing=True)
@@ -658,7 +667,14 @@ def run_ours(args):
                 "ms_per_step": round(ms_e2e / K, 4),
                 "pcie_gbs_per_rank_each_way": round(FRAMES * H * W * 3 / (ms_e2e / K * 1e-3) / 1e9, 2),
                 "host_numa": numa,
-                "api": "Engine.roundtrip_batch(pinned host uint8 frames) -> jds_roundtrip_batch (C ABI)"},
+                "api": "Engine.roundtrip_batch(pinned host uint8 frames) -> jds_roundtrip_batch (C ABI)",
+                "metrics_only": {"value": round(e2e_metrics, 2), "unit": "Mpixel/s",
+                                 "ms_per_step": round(ms_e2e_m / K, 4),
+                                 "h2d_bytes_per_step": FRAMES * H * W * 3,
+                                 "d2h_bytes_per_step": FRAMES * 504,
+                                 "pcie_gbs_per_rank_h2d": round(FRAMES * H * W * 3 / (ms_e2e_m / K * 1e-3) / 1e9, 2),
+                                 "api": "the same call with want_recon=False (compress_batch(keep_images=False)): "
+                                        "what the reference's batch / sweep consumers read, gui/worker.py:66-72"}},
         "gpu_launches": launches,
         "value_mode": "streamed: per-step kernels and device-resident metric records enqueued without "
                       "host synchronisation (jds_roundtrip_batch_records), steps alternating over "

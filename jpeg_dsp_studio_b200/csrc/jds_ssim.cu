@@ -59,6 +59,12 @@
 #ifndef JDS_SSIM_PREP_BY1
 #define JDS_SSIM_PREP_BY1 160        // with PAIRBAR: prep tasks [0, n) go to the (B,Y) threads, the rest to (R,G)
 #endif
+#ifndef JDS_SSIM_PREP_RG
+#define JDS_SSIM_PREP_RG 0           // > 0: the (R,G) warps take only the first n of the 252 prep tasks, the (B,Y) warps the rest
+#endif
+#ifndef JDS_SSIM_SM_ALTERNATE
+#define JDS_SSIM_SM_ALTERNATE 1      // successive CTAs of an SM swap which warps take (R,G) and which (B,Y)
+#endif
 #ifndef JDS_SSIM_SSE_FROM_SUMS
 #define JDS_SSIM_SSE_FROM_SUMS 1     // squared error of a task's 8 pixels from its first window's sums + pixel 7
 #endif
@@ -95,6 +101,7 @@ struct SsimSmem {
     alignas(16) float4 hxy[S_R][S_HPITCH];          // horizontal sums (sx, sy) [row][pair*64+col]
     alignas(16) float4 hqc[S_R][S_HPITCH];          // horizontal sums (sq, sc)
     alignas(8) unsigned long long bar[2];
+    int swap;
     double red_ssim[4][2];
     double red_sse[4][4];
 };
@@ -270,6 +277,14 @@ __device__ __forceinline__ float2 pass1_task(SsimSmem& sm, int buf, int p1_row, 
 #ifndef JDS_SSIM_MIN_CTAS
 #define JDS_SSIM_MIN_CTAS 4
 #endif
+#if JDS_SSIM_SM_ALTERNATE
+// The (R,G) warps convert bytes inside pass 1 and carry ~15 % more instructions than the (B,Y)
+// warps.  Warps w of all resident CTAs share scheduler w % 4, so with a fixed assignment two of an
+// SM's four schedulers would always hold the heavy warps.  Every CTA takes a turn number from its
+// SM and odd turns swap the roles: each scheduler then sees both kinds.  Only a balance hint -
+// results do not depend on it.
+__device__ unsigned int g_ssim_sm_turn[1024];
+#endif
 __global__ void __launch_bounds__(S_NT, JDS_SSIM_MIN_CTAS)
 k_ssim_strip(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
              int H, int W, int seg_rows, int a_unit_step, int b_unit_step,
@@ -293,8 +308,18 @@ k_ssim_strip(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         mbar_init(&sm.bar[0], 1);
         mbar_init(&sm.bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#if JDS_SSIM_SM_ALTERNATE
+        unsigned int smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        sm.swap = (int)(atomicAdd(&g_ssim_sm_turn[smid & 1023], 1u) & 1u);
+#endif
     }
     __syncthreads();
+#if JDS_SSIM_SM_ALTERNATE
+    const int swap = sm.swap;
+#else
+    const int swap = 0;
+#endif
 
     auto issue = [&](int chunk) {
         // one thread: two tile loads (original, reconstruction) of 7 rows x 240 bytes; rows past
@@ -312,7 +337,7 @@ k_ssim_strip(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
 
     // pass-2 role: thread = (window column, channel pair)
     const int col = tid & (S_OW - 1);
-    const int pair = tid >> 6;                      // warps 0,1: (R,G); warps 2,3: (B,Y)
+    const int pair = (tid >> 6) ^ swap;             // warps 0,1: (R,G); warps 2,3: (B,Y) - or swapped
     const int hidx = pair * S_OW + col;
 #if JDS_SSIM_ST64
     // the two 8-byte halves of a 16-byte slot swap places in odd segments so that the 16 lanes
@@ -486,7 +511,13 @@ k_ssim_strip(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
             else prep_tasks(c + 1, JDS_SSIM_PREP_BY1 + tid, N_PREP, S_OW);
 #else
             mbar_wait(&sm.bar[buf ^ 1], (uint32_t)(((c + 1) >> 1) & 1));
+#if JDS_SSIM_PREP_RG > 0
+            // the (R,G) warps converted bytes inside pass 1: the (B,Y) warps take more of the prep
+            if (pair == 0) prep_tasks(c + 1, tid & (S_OW - 1), JDS_SSIM_PREP_RG, S_OW);
+            else prep_tasks(c + 1, JDS_SSIM_PREP_RG + (tid & (S_OW - 1)), N_PREP, S_OW);
+#else
             prep_tasks(c + 1, tid, N_PREP, S_NT);
+#endif
 #endif
         }
         __syncthreads();
@@ -518,9 +549,8 @@ k_ssim_strip(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     __syncthreads();
     if (tid < 4 && want_ssim) {
         // channel tid: pair = tid / 2 (warps 2*pair, 2*pair+1), half = tid % 2
-        const int pr = tid >> 1, hf = tid & 1;
-        atomicAdd(&metrics[unit].ssim_sum[tid],
-                  2.0 * (sm.red_ssim[2 * pr][hf] + sm.red_ssim[2 * pr + 1][hf]));
+        const int pr = tid >> 1, hf = tid & 1, w0 = 2 * (pr ^ swap);
+        atomicAdd(&metrics[unit].ssim_sum[tid], 2.0 * (sm.red_ssim[w0][hf] + sm.red_ssim[w0 + 1][hf]));
     }
     if (tid == 32 && want_sse) {
         double t[4] = {0.0, 0.0, 0.0, 0.0};
