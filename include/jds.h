@@ -166,6 +166,20 @@ int jds_roundtrip_batch(jds_ctx* ctx, const jds_params* params, int n_frames,
                         jds_metrics* metrics);
 
 /*
+ * jds_roundtrip_batch split in two, for callers that stream batch after batch: begin enqueues the
+ * batch's copies and kernels and returns; jds_ctx_finish waits for them and fills `metrics`.
+ * With two contexts used alternately the PCIe transfers of consecutive batches overlap (the
+ * drain of one hides the fill of the next).  rgb / recon / coeffs / metrics must stay valid until
+ * jds_ctx_finish; no other call on the context in between (JDS_ERR_INVALID).  jds_ctx_finish
+ * without a pending batch is a no-op.
+ */
+int jds_roundtrip_batch_begin(jds_ctx* ctx, const jds_params* params, int n_frames,
+                              const uint8_t* rgb, int rgb_loc,
+                              uint8_t* recon, int16_t* coeffs, int out_loc,
+                              jds_metrics* metrics);
+int jds_ctx_finish(jds_ctx* ctx);
+
+/*
  * Tile-band sharding of ONE frame (second row): rows [row0, row1) of the frame as
  * one rank's share of engines/pipeline.py:17-167, for single-image latency on several GPUs.
  * params->height / width describe the WHOLE frame and rgb points at its first row (host or

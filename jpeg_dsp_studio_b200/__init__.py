@@ -13,10 +13,10 @@ from . import _native
 _native.load()          # fail loudly at import when the CUDA library is missing
 
 from .models import CompressionParams, CompressionResult, IntermediateData  # noqa: E402
-from .engines.pipeline import compress_reconstruct, quality_sweep, compress_batch, plot_payload  # noqa: E402
+from .engines.pipeline import compress_reconstruct, quality_sweep, compress_batch, compress_stream, plot_payload  # noqa: E402
 from .engine import Engine, get_engine  # noqa: E402
 
 __all__ = ['CompressionParams', 'CompressionResult', 'IntermediateData',
-           'compress_reconstruct', 'quality_sweep', 'compress_batch', 'plot_payload', 'Engine',
+           'compress_reconstruct', 'quality_sweep', 'compress_batch', 'compress_stream', 'plot_payload', 'Engine',
            'get_engine']
 __version__ = "0.1.0"

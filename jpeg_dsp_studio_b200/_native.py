@@ -80,6 +80,9 @@ PROTOTYPES = {
                                        C.POINTER(JdsMetrics), C.POINTER(JdsMetrics)]),
     "jds_entropy_bits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.POINTER(C.c_uint64)]),
+    "jds_roundtrip_batch_begin": (C.c_int, [C.c_void_p, C.POINTER(JdsParams), C.c_int, C.c_void_p, C.c_int,
+                                            C.c_void_p, C.c_void_p, C.c_int, C.POINTER(JdsMetrics)]),
+    "jds_ctx_finish": (C.c_int, [C.c_void_p]),
     "jds_roundtrip_band": (C.c_int, [C.c_void_p, C.POINTER(JdsParams), C.c_void_p, C.c_int, C.c_int,
                                      C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(JdsMetrics)]),
     "jds_entropy_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,

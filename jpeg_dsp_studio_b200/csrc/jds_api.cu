@@ -88,6 +88,14 @@ struct jds_ctx {
     bool ev_tables_used[kTableRing] = {};
     int tables_slot = 0;
     size_t scratch_budget = (size_t)1 << 30;
+    // a jds_roundtrip_batch_begin whose results jds_ctx_finish has not collected yet
+    struct Pending {
+        bool active = false;
+        bool pipelined = false;
+        int units = 0;
+        jds_metrics* metrics = nullptr;
+        uint64_t ssim_count = 0, ncoef = 0, luma_blocks = 0;
+    } pend;
 };
 
 static int ensure(jds_ctx* c, DevBuf& b, size_t bytes) {
@@ -389,6 +397,7 @@ struct UnitJob {
     // jds_roundtrip_band: no whole-frame comparison; `tail` enqueues the band's own reductions and
     // copies behind the kernels, before the job's single synchronisation
     bool no_compare;
+    bool defer;                 // jds_roundtrip_batch_begin: return without synchronising
     int (*tail)(jds_ctx*, void*, cudaStream_t);
     void* tail_arg;
 };
@@ -555,7 +564,30 @@ static int launch_chunk(jds_ctx* c, const UnitJob& J, const ChunkPtrs& P, int n,
 // kernels, device->host copies - with double-buffered staging, so that with host
 // buffers the PCIe transfers of neighbouring chunks overlap the kernels and each other
 // (full duplex).  With device buffers the copy streams stay idle.
+// sync + host-side metric structs of a finished job (shared by run_job and jds_ctx_finish)
+static void fill_job_metrics(const jds_ctx* c, jds_metrics* out, int units, uint64_t ssim_count,
+                             uint64_t ncoef, uint64_t luma_blocks, double ms_per_unit) {
+    const DevMetrics* h_metrics = (const DevMetrics*)c->h_metrics;
+    for (int i = 0; i < units; ++i) {
+        jds_metrics* m = &out[i];
+        const DevMetrics& d = h_metrics[i];
+        memset(m, 0, sizeof *m);
+        m->sse_rgb = d.sse_rgb;
+        m->sse_y = d.sse_y;
+        for (int k = 0; k < 4; ++k) m->ssim_sum[k] = d.ssim_sum[k];
+        m->ssim_count = ssim_count;
+        m->coeff_bits = d.coeff_bits;
+        m->nnz = d.nnz;
+        m->total_coeffs = ncoef;
+        m->luma_blocks = luma_blocks;
+        for (int k = 0; k < 50; ++k) m->hist50[k] = (int64_t)d.hist[k];
+        m->gpu_ms = ms_per_unit;
+    }
+}
+
 static int run_job(jds_ctx* c, const UnitJob& J) {
+    if (c->pend.active)
+        return fail(JDS_ERR_INVALID, "a deferred batch is pending on this context: call jds_ctx_finish first");
     const Geom& g = J.g;
     const jds_params* p = J.p;
     const bool exact = p->precision == JDS_EXACT;
@@ -795,6 +827,19 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
     if (J.tail && (rc = J.tail(c, J.tail_arg, s))) return rc;
     JDS_CUDA(cudaMemcpyAsync(h_metrics, d_metrics, sizeof(DevMetrics) * J.units,
                              cudaMemcpyDeviceToHost, s));
+    const uint64_t ssim_count = (want_ssim && g.H >= 7 && g.W >= 7)
+                                    ? (uint64_t)(g.H - 6) * (uint64_t)(g.W - 6) : 0;
+    if (J.defer) {
+        // everything is enqueued; jds_ctx_finish synchronises and fills the metric structs
+        c->pend.active = true;
+        c->pend.pipelined = pipelined;
+        c->pend.units = J.units;
+        c->pend.metrics = J.metrics;
+        c->pend.ssim_count = ssim_count;
+        c->pend.ncoef = ncoef;
+        c->pend.luma_blocks = (uint64_t)g.nblk_y;
+        return JDS_OK;
+    }
     if (pipelined) {
         JDS_CUDA(cudaStreamSynchronize(s_in));
         JDS_CUDA(cudaStreamSynchronize(s_out));
@@ -811,22 +856,7 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
                 c->stage_launches[k] += 1;
             }
         }
-    for (int i = 0; i < J.units; ++i) {
-        jds_metrics* m = &J.metrics[i];
-        const DevMetrics& d = h_metrics[i];
-        memset(m, 0, sizeof *m);
-        m->sse_rgb = d.sse_rgb;
-        m->sse_y = d.sse_y;
-        for (int k = 0; k < 4; ++k) m->ssim_sum[k] = d.ssim_sum[k];
-        m->ssim_count = (want_ssim && g.H >= 7 && g.W >= 7)
-                            ? (uint64_t)(g.H - 6) * (uint64_t)(g.W - 6) : 0;
-        m->coeff_bits = d.coeff_bits;
-        m->nnz = d.nnz;
-        m->total_coeffs = ncoef;
-        m->luma_blocks = (uint64_t)g.nblk_y;
-        for (int k = 0; k < 50; ++k) m->hist50[k] = (int64_t)d.hist[k];
-        m->gpu_ms = (double)ms / J.units;
-    }
+    fill_job_metrics(c, J.metrics, J.units, ssim_count, ncoef, (uint64_t)g.nblk_y, (double)ms / J.units);
     return JDS_OK;
 }
 
@@ -880,6 +910,54 @@ extern "C" int jds_roundtrip_batch(jds_ctx* c, const jds_params* p, int n_frames
     J.out_loc = out_loc;
     J.metrics = metrics;
     return run_job(c, J);
+}
+
+// The batch call split in two (pipelining consecutive batches over two contexts: while one
+// context's last chunks drain over PCIe the other's first chunks are already on their way).
+// begin enqueues everything - host->device copies, kernels, device->host copies - and returns;
+// the buffers and the metrics array must stay valid until jds_ctx_finish, which synchronises and
+// fills the metric structs.  No other call on this context in between.
+extern "C" int jds_roundtrip_batch_begin(jds_ctx* c, const jds_params* p, int n_frames,
+                                         const uint8_t* rgb, int rgb_loc, uint8_t* recon,
+                                         int16_t* coeffs, int out_loc, jds_metrics* metrics) {
+    if (!c || !rgb || !metrics) return fail(JDS_ERR_INVALID, "NULL argument");
+    if (n_frames < 1) return fail(JDS_ERR_INVALID, "n_frames must be >= 1, got %d", n_frames);
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (p->quality < 1 || p->quality > 100)
+        return fail(JDS_ERR_INVALID, "Quality must be 1-100, got %d", p->quality);
+    if (p->outputs & (JDS_OUT_ERR_Y | JDS_OUT_ERR_RGB))
+        return fail(JDS_ERR_INVALID, "error maps are not produced in batch mode");
+    UnitJob J;
+    memset(&J, 0, sizeof J);
+    if ((rc = make_geom(p->height, p->width, p->subsampling, &J.g))) return rc;
+    J.p = p;
+    J.units = n_frames;
+    J.rgb = rgb;
+    J.rgb_loc = rgb_loc;
+    J.recon = recon;
+    J.coeffs = coeffs;
+    J.out_loc = out_loc;
+    J.metrics = metrics;
+    J.defer = true;
+    return run_job(c, J);
+}
+
+extern "C" int jds_ctx_finish(jds_ctx* c) {
+    if (!c) return fail(JDS_ERR_INVALID, "ctx is NULL");
+    if (!c->pend.active) return JDS_OK;
+    JDS_CUDA(cudaSetDevice(c->device));
+    c->pend.active = false;
+    if (c->pend.pipelined) {
+        JDS_CUDA(cudaStreamSynchronize(c->s_in));
+        JDS_CUDA(cudaStreamSynchronize(c->s_out));
+    }
+    JDS_CUDA(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    JDS_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    fill_job_metrics(c, c->pend.metrics, c->pend.units, c->pend.ssim_count, c->pend.ncoef,
+                     c->pend.luma_blocks, (double)ms / c->pend.units);
+    return JDS_OK;
 }
 
 extern "C" int jds_sweep(jds_ctx* c, const jds_params* p, const int32_t* qualities, int n_q,

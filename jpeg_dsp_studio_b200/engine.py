@@ -125,6 +125,22 @@ class PlotPayload:
         return self.outputs.scalars
 
 
+class PendingBatch:
+    """A batch in flight (``Engine.roundtrip_batch_begin``); keeps its buffers alive."""
+
+    def __init__(self, engine, frames, recon, metrics, hw, loc):
+        self._engine, self._frames, self._recon, self._ms, self._hw, self._loc = engine, frames, recon, metrics, hw, loc
+        self._outs = None
+
+    def result(self) -> List[RoundTripOutputs]:
+        if self._outs is None:
+            self._engine._finish()                 # synchronises the context's streams
+            r, ms = self._recon, self._ms
+            self._outs = [RoundTripOutputs(r[i] if r is not None else None, None, None, None, ms[i], self._hw, ms)
+                          for i in range(len(ms))]
+        return self._outs
+
+
 class Engine:
     """A libjds context bound to one CUDA device."""
 
@@ -572,6 +588,38 @@ class Engine:
                                  coeffs[i] if coeffs is not None else None, None, None, ms[i],
                                  (h, w), ms) for i in range(n)]
 
+    def roundtrip_batch_begin(self, frames, quality=50, mode="4:2:0", prefilter=False, *,
+                              precision="fast", want_recon=True, want_ssim=True, recon_out=None):
+        """``roundtrip_batch`` without the wait: enqueues the batch (copies included) and returns
+        a ``PendingBatch``; ``.result()`` waits and returns the list of ``RoundTripOutputs``.
+        One pending batch per engine - alternate two engines to overlap consecutive batches
+        (``engines.pipeline.compress_stream`` does)."""
+        shape = tuple(frames.shape)
+        if len(shape) != 4 or shape[-1] != 3:
+            raise ValueError(f"expected N x H x W x 3 frames, got shape {shape}")
+        n, h, w, _ = shape
+        ptr, loc, keep = self._in_ptr(frames)
+        flags = N.JDS_OUT_PSNR | (N.JDS_OUT_RECON if want_recon else 0) | (N.JDS_OUT_SSIM if want_ssim else 0)
+        p = self._params(h, w, quality, mode, prefilter, precision, flags)
+        ms = (N.JdsMetrics * n)()
+        recon = None
+        if want_recon:
+            if recon_out is not None:
+                recon = recon_out
+            elif loc == N.JDS_DEVICE:
+                import torch
+                recon = torch.empty((n, h, w, 3), dtype=torch.uint8, device=keep.device)
+            else:
+                recon = host_array((n, h, w, 3), np.uint8)
+        rp = None if recon is None else C.c_void_p(recon.data_ptr() if _is_torch(recon) else recon.ctypes.data)
+        with self._lock:
+            N.check(self._lib.jds_roundtrip_batch_begin(self._ctx, C.byref(p), n, ptr, loc, rp, None, loc, ms))
+        return PendingBatch(self, keep, recon, ms, (h, w), loc)
+
+    def _finish(self):
+        with self._lock:
+            N.check(self._lib.jds_ctx_finish(self._ctx))
+
     # -- quality sweep (BASELINE config 4; gui/worker.py:55-74) -------------------------
     def sweep(self, image, qualities: Sequence[int], mode="4:2:0", prefilter=False, *,
               precision="fast", want_recon=False, want_ssim=True) -> List[RoundTripOutputs]:
@@ -663,6 +711,20 @@ class Engine:
 
 _engines = {}
 _engines_lock = threading.Lock()
+
+
+def stream_engines(device: Optional[int] = None, n: int = 2) -> List["Engine"]:
+    """``n`` engines on one device for callers that keep several batches in flight: the
+    process-wide engine plus ``n - 1`` more contexts (created on first use, kept)."""
+    first = get_engine(device)
+    with _engines_lock:
+        extra = _extra_engines.setdefault(first.device, [])
+        while len(extra) < n - 1:
+            extra.append(Engine(first.device))
+        return [first] + extra[:n - 1]
+
+
+_extra_engines = {}
 
 
 def get_engine(device: Optional[int] = None) -> Engine:

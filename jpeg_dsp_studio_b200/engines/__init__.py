@@ -8,9 +8,9 @@ from .color_space import rgb_to_ycbcr, ycbcr_to_rgb, subsample_chroma, upsample_
 from .block_processor import pad_to_multiple, split_into_blocks, merge_blocks
 from .dct_engine import dct2, idct2, encode_block, decode_block
 from .quantizer import scale_quant_matrix, quantize, dequantize
-from .pipeline import compress_reconstruct, quality_sweep, compress_batch, plot_payload
+from .pipeline import compress_reconstruct, quality_sweep, compress_batch, compress_stream, plot_payload
 
 __all__ = ['rgb_to_ycbcr', 'ycbcr_to_rgb', 'subsample_chroma', 'upsample_chroma', 'pad_to_multiple',
            'split_into_blocks', 'merge_blocks', 'dct2', 'idct2', 'encode_block', 'decode_block', 'scale_quant_matrix', 'quantize',
            'dequantize', 'JPEG_LUMA_Q50', 'compress_reconstruct', 'quality_sweep',
-           'compress_batch', 'plot_payload']
+           'compress_batch', 'compress_stream', 'plot_payload']

@@ -197,6 +197,50 @@ def compress_batch(frames, params: CompressionParams, *, precision: str = "fast"
     return results
 
 
+def compress_stream(batches, params: CompressionParams, *, precision: str = "fast",
+                    device: Optional[int] = None, keep_images: bool = True, recon_out=None):
+    """A stream of same-sized batches (an iterable of N x H x W x 3 uint8 arrays - a folder of
+    frames, a video): yields ``compress_batch``'s list of results for every batch, in order,
+    with consecutive batches overlapped - batch k+1 is enqueued on a second context before the
+    results of batch k are awaited, so its host->device copies run while batch k's last
+    reconstructions are still on their way back.  ``recon_out``: optional pair of N x H x W x 3
+    uint8 host buffers to receive the reconstructions alternately (pinned memory makes the
+    copies asynchronous); the arrays of a yielded batch are valid until two batches later."""
+    from ..engine import stream_engines
+    engines = stream_engines(device, 2)
+
+    def finish(pending, frames, t0):
+        outs = pending.result()
+        wall_ms = (time.perf_counter() - t0) * 1000.0
+        results = []
+        for i, o in enumerate(outs):
+            s = o.scalars
+            results.append(CompressionResult(
+                original_image=frames[i], reconstructed_image=o.recon,
+                psnr_y=s['psnr_y'], ssim_y=s['ssim_y'], psnr_rgb=s['psnr_rgb'],
+                ssim_rgb=s['ssim_rgb'], bpp=s['bpp'], compression_ratio=s['compression_ratio'],
+                nonzero_coeffs=s['nonzero_count'], total_coeffs=s['total_coeffs'],
+                encode_time_ms=float(o.metrics.gpu_ms),
+                decode_time_ms=max(wall_ms / max(len(outs), 1) - float(o.metrics.gpu_ms), 0.0),
+                bitrate_label=BITRATE_LABEL))
+        return results
+
+    prev = None
+    for k, frames in enumerate(batches):
+        if frames.ndim != 4:
+            raise ValueError(f"expected N x H x W x 3 frames, got shape {tuple(frames.shape)}")
+        _validate(frames[0], params)
+        t0 = time.perf_counter()
+        pending = engines[k & 1].roundtrip_batch_begin(
+            frames, params.quality, params.subsampling_mode, params.use_prefilter, precision=precision,
+            want_recon=keep_images, recon_out=None if recon_out is None else recon_out[k & 1])
+        if prev is not None:
+            yield finish(*prev)
+        prev = (pending, frames, t0)
+    if prev is not None:
+        yield finish(*prev)
+
+
 def plot_payload(image_rgb, params: CompressionParams, *, precision: str = "exact",
                  device: Optional[int] = None, want_heat_rgb: bool = False, bins: int = 50):
     """The round trip for the GUI's analysis plots (gui/compression_tab.py:653-676) without

@@ -633,3 +633,38 @@ def test_extreme_aspect_strips(J, oracle):
         assert np.array_equal(np.asarray(o.coeffs), ref["all_quantized_coeffs"]), shape
         assert np.array_equal(np.asarray(o.recon), ref["reconstructed_image"]), shape
         assert abs(o.scalars["ssim_y"] - ref["ssim_y"]) <= SSIM_TOL
+
+
+def test_compress_stream_overlapped_batches_equal_single_batches(J):
+    """compress_stream (jds_roundtrip_batch_begin / jds_ctx_finish on two alternating contexts)
+    yields, in order, exactly what compress_batch returns for every batch - host frames, CUDA
+    frames, exact and fast mode; a context with a pending batch refuses other calls."""
+    import torch
+    from jpeg_dsp_studio_b200 import _native as NAT
+    from jpeg_dsp_studio_b200.engine import stream_engines
+    p = J.CompressionParams(quality=40, subsampling_mode="4:2:0", use_prefilter=True)
+    batches = [np.stack([CS.rand_rgb(900 + 7 * b + k, 144, 256) for k in range(3)]) for b in range(5)]
+    for precision in ("fast", "exact"):
+        want = [J.compress_batch(b, p, precision=precision) for b in batches]
+        got = list(J.compress_stream(iter(batches), p, precision=precision))
+        assert len(got) == len(want)
+        for gb, wb in zip(got, want):
+            for g, w in zip(gb, wb):
+                assert np.array_equal(g.reconstructed_image, w.reconstructed_image)
+                assert (g.psnr_rgb, g.bpp, g.nonzero_coeffs) == (w.psnr_rgb, w.bpp, w.nonzero_coeffs)
+                assert abs(g.ssim_rgb - w.ssim_rgb) <= 1e-9 and abs(g.psnr_y - w.psnr_y) <= 1e-9
+    # device-resident frames, metrics only
+    dev = [torch.from_numpy(b).cuda() for b in batches]
+    got = list(J.compress_stream(dev, p, keep_images=False))
+    want = [J.compress_batch(b, p, keep_images=False) for b in batches]
+    for gb, wb in zip(got, want):
+        assert [g.psnr_rgb for g in gb] == [w.psnr_rgb for w in wb]
+        assert all(g.reconstructed_image is None for g in gb)
+    # one pending batch per context
+    eng = stream_engines(None, 2)[1]
+    pending = eng.roundtrip_batch_begin(batches[0], 40, "4:2:0", True)
+    with pytest.raises(NAT.NativeError, match="pending"):
+        eng.roundtrip(batches[0][0], 40, "4:2:0", True, precision="fast")
+    outs = pending.result()
+    assert np.array_equal(outs[1].recon, J.compress_batch(batches[0], p)[1].reconstructed_image)
+    eng.roundtrip(batches[0][0], 40, "4:2:0", True, precision="fast")      # usable again
