@@ -88,6 +88,7 @@ struct jds_ctx {
     bool ev_tables_used[kTableRing] = {};
     int tables_slot = 0;
     size_t scratch_budget = (size_t)1 << 30;
+    int pipe_chunk = 0;
     // a jds_roundtrip_batch_begin whose results jds_ctx_finish has not collected yet
     struct Pending {
         bool active = false;
@@ -193,6 +194,8 @@ extern "C" int jds_ctx_create(int device, jds_ctx** out) {
     const char* l2c = getenv("JDS_L2_CHUNK");
     c->l2_chunking = l2c ? atoi(l2c) : 0;
     if (c->l2_chunking < 0) c->l2_chunking = 0;
+    const char* pc = getenv("JDS_PIPE_CHUNK");      // A/B runs: frames per chunk of the host pipeline
+    c->pipe_chunk = pc ? atoi(pc) : 0;
     const char* mb = getenv("JDS_SCRATCH_MB");
     if (mb && atol(mb) > 0) c->scratch_budget = (size_t)atol(mb) << 20;
     *out = c;
@@ -638,6 +641,7 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
         if (target < min_units) target = min_units;
         if (target < 1) target = 1;
         if (chunk > target) chunk = target;
+        if (c->pipe_chunk > 0) chunk = c->pipe_chunk < J.units ? c->pipe_chunk : J.units;
     }
     c->plan_chunk = chunk;
     const int nbuf = pipelined ? 2 : 1;

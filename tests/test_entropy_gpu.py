@@ -134,6 +134,14 @@ def test_scan_bytes_extremes(J):
         want, want_bits = _oracle_scans(arr.ravel(), (h, w), "4:4:4")
         got, bits = eng.entropy_encode(arr.ravel(), h, w, "4:4:4")
         assert bits == want_bits and got == want
+    # the smallest frames: one block per scan; one CTA-sized and one CTA-sized-plus-one scan
+    for (hh, ww) in ((1, 1), (8, 8), (64, 64), (64, 72)):
+        nb = ((hh + 7) // 8) * ((ww + 7) // 8)
+        arr = np.random.default_rng(hh * ww).integers(-40, 41, (3 * nb, 64)).astype(np.int16)
+        arr[:, 20:] = 0
+        want, want_bits = _oracle_scans(arr.ravel(), (hh, ww), "4:4:4")
+        got, bits = eng.entropy_encode(arr.ravel(), hh, ww, "4:4:4")
+        assert bits == want_bits and got == want, (hh, ww)
     # values without a baseline code are refused, not mis-coded
     bad = c.copy()
     bad[3, 5] = 1024

@@ -548,6 +548,13 @@ def test_cli_entry_matches_reference_demo(J, capsys, tmp_path):
     assert f"SSIM (Y): {ref['ssim_y']:.4f}" in text
     assert f"BPP: {ref['bpp']:.3f}" in text
     assert f"Compression Ratio: {ref['compression_ratio']:.2f}x" in text
+    # --jpeg: the coefficients as a real baseline JPEG (entropy-coded on the GPU) = the oracle's file
+    from oracle import entropy_port as E
+    jpg = str(tmp_path / "out.jpg")
+    assert main(["--cli", "--output", out, "--jpeg", jpg]) == 0
+    want, _ = E.encode_jfif(ref["all_quantized_coeffs"], (256, 256), "4:2:0", P.scale_quant_matrix(50))
+    assert open(jpg, "rb").read() == want
+    assert f"JPEG: {jpg} ({len(want)} bytes" in capsys.readouterr().out
 
 
 def test_calls_from_worker_threads(J, oracle):
