@@ -71,8 +71,17 @@ constexpr int kMagicRoundBits = 0x4B400000;
 constexpr float kInv255 = 1.0f / 255.0f;
 constexpr float k128_255 = 128.0f / 255.0f;
 constexpr int BLK_STRIDE = 68;                    // floats per 8x8 block slot in shared memory
-// luma tiles: which blocks keep the two halves of their rows swapped (bit 3 of the slot index)
-__device__ __forceinline__ int slot_swz(int blk) { return (blk >> 3) & 1; }
+// luma tiles: which block rows keep their two 16-byte halves swapped - bit 3 of the slot index
+// (the eight lanes of a quarter-warp that walks eight blocks of one row) XOR one bit of the row
+// (SHIFT = 1 for 4:2:0, 0 for 4:2:2: a quarter-warp of the compose phase walks four blocks of two
+// tasks whose rows differ in exactly that bit)
+#ifndef JDS_LU_ROWSWZ
+#define JDS_LU_ROWSWZ 1
+#endif
+template <int SHIFT>
+__device__ __forceinline__ int slot_swz(int blk, int ry) {
+    return JDS_LU_ROWSWZ ? (((blk >> 3) ^ (ry >> SHIFT)) & 1) : ((blk >> 3) & 1);
+}
 
 template <int B>
 __device__ __forceinline__ float f_byte_centered(uint32_t w) {
@@ -574,12 +583,18 @@ k_fast_chroma_pf(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
 constexpr int LU_BX = 32, LU_BY = 4, LU_NT = 128;
 constexpr int LU_TW = LU_BX * 8, LU_TH = LU_BY * 8;      // 256 x 32
 constexpr int CT_COLS = LU_TW / 2 + 8;                   // 136 chroma columns staged
+// Row pitch of the staged chroma tile.  A compose warp reads two tile rows (lanes 0-15 / 16-31),
+// lanes of a row 8 floats apart; 140 = 12 (mod 32) puts the two rows on disjoint bank sets, which
+// halves the conflicts of the scalar loads of the outer samples (8-way -> 4-way; 136 = 8 (mod 32)
+// mapped both rows onto the same four banks).  The 16-byte loads stay 2-way: inherent in lanes that
+// sit 32 B apart (profiles/r2_luma_smem_conflicts.txt).
+constexpr int CT_PITCH = CT_COLS + 4;
 
 template <int SUB>
 struct LumaSmem {
     static constexpr int CT_ROWS = (SUB == 2) ? LU_TH / 2 + 2 : LU_TH;
     alignas(16) float plane[LU_BX * LU_BY][BLK_STRIDE];
-    alignas(128) float ctile[2][CT_ROWS][CT_COLS];
+    alignas(128) float ctile[2][CT_ROWS][CT_PITCH];
     alignas(16) float fq[64];
     alignas(16) float dq[64];
     alignas(8) unsigned long long bar;
@@ -627,6 +642,7 @@ k_fast_luma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
     const int x0 = blockIdx.x * LU_TW, y0 = blockIdx.y * LU_TH;
     const int n_rows = min(LU_TH, g.H - y0);
     const int n_px = min(LU_TW, g.W - x0);
+    constexpr int SWZ_SHIFT = (SUB == 2) ? 1 : 0;             // row bit of the slot swizzle
 
     // chroma tile geometry: columns [ccol0, ccol0 + ncc), rows [crow0, crow0 + ncr)
     const int cx0 = x0 >> 1;
@@ -699,7 +715,7 @@ k_fast_luma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
                 // slot swizzle: the two 16-byte halves of a block row swap places in blocks with
                 // bit 3 set (SLOT_SWZ), so the eight lanes of a quarter-warp - blocks 2s, s = 0..7,
                 // 32 B apart modulo 128 - hit eight different bank groups instead of four twice
-                const int f = slot_swz(blk);
+                const int f = slot_swz<SWZ_SHIFT>(blk, ry);
                 float4* p0 = reinterpret_cast<float4*>(&sm.plane[blk][ry * 8]);
                 float4* p1 = reinterpret_cast<float4*>(&sm.plane[blk + 1][ry * 8]);
                 p0[f] = make_float4(yv[0], yv[1], yv[2], yv[3]);
@@ -718,16 +734,22 @@ k_fast_luma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
         if (bx < g.nbx_y && by < g.nby_y) {
             float v[64];
             float4* slot = reinterpret_cast<float4*>(&sm.plane[tid][0]);
-            // swizzled halves (see above): float4 i lives at i ^ f - two bases, constant offsets
-            const int f = slot_swz(tid);
+            // swizzled halves (see above): float4 i = 2 * row + half lives at i ^ f(row), f = fb ^ g(row)
+            // with fb fixed per block and g known at compile time - two bases, constant offsets:
+            //   g = 0: even i at slot_e[i], odd i at slot_o[i];  g = 1: even i at slot_o[i+1], odd i at slot_e[i-1]
+            const int f = slot_swz<SWZ_SHIFT>(tid, 0);
             float4* slot_e = slot + f;
             float4* slot_o = slot - f;
+            auto at = [&](int i) -> float4* {
+                const int g = JDS_LU_ROWSWZ ? (((i >> 1) >> SWZ_SHIFT) & 1) : 0;
+                return g ? ((i & 1) ? slot_e + (i - 1) : slot_o + (i + 1)) : ((i & 1) ? slot_o + i : slot_e + i);
+            };
             if (STAGE == STAGE_BACK) {
                 fcoef_load(fcoef_warp_base(fcoef, LU_NT / 32), v);
             } else {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const float4 a = (i & 1) ? slot_o[i] : slot_e[i];
+                    const float4 a = *at(i);
                     v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = a.z; v[4 * i + 3] = a.w;
                 }
                 codec_fast_fwd(v);
@@ -742,7 +764,7 @@ k_fast_luma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
             codec_fast_back<COEFFS>(v, sm.fq, sm.dq, esum, nnz, cout);
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-                ((i & 1) ? slot_o : slot_e)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                *at(i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         }
         if (STAGE == STAGE_FWD) return;
         flush_stats(esum, nnz, metrics + unit);
@@ -754,7 +776,14 @@ k_fast_luma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
     constexpr int RPT = (SUB == 2) ? 2 : 1;                   // rows per task
     uint8_t* out = recon + (size_t)unit * recon_stride;
     for (int task = tid; task < (LU_TH / RPT) * (LU_TW / 16); task += LU_NT) {
+#if JDS_LU_ROWSWZ
+        // a warp = 32 tasks = 16 segments x 2 consecutive rows / row pairs; every quarter-warp takes
+        // FOUR segments of BOTH: its 16-byte loads of the chroma tile (rows 560 B = 48 mod 128 apart)
+        // and of the Y slots (row-dependent swizzle) then cover all 32 banks once
+        const int seg = (task & 3) + 4 * ((task >> 3) & 3), rp = 2 * (task >> 5) + ((task >> 2) & 1);
+#else
         const int rp = task / (LU_TW / 16), seg = task % (LU_TW / 16);
+#endif
         const int r0 = rp * RPT;
         if (r0 >= n_rows || seg * 16 >= n_px) continue;
         // staged chroma columns: smem column of chroma sample k0 is k0 - ccol_lo = 8*seg + 4
@@ -789,7 +818,7 @@ k_fast_luma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
             const int blk = (r >> 3) * LU_BX + seg * 2, ry = r & 7;
             float yv[16];
             {
-                const int f = slot_swz(blk);
+                const int f = slot_swz<SWZ_SHIFT>(blk, ry);
                 const float4* p0 = reinterpret_cast<const float4*>(&sm.plane[blk][ry * 8]);
                 const float4* p1 = reinterpret_cast<const float4*>(&sm.plane[blk + 1][ry * 8]);
                 float4 a = p0[f], b = p0[1 - f], c = p1[f], d = p1[1 - f];
