@@ -567,6 +567,12 @@ static int launch_chunk(jds_ctx* c, const UnitJob& J, const ChunkPtrs& P, int n,
 // kernels, device->host copies - with double-buffered staging, so that with host
 // buffers the PCIe transfers of neighbouring chunks overlap the kernels and each other
 // (full duplex).  With device buffers the copy streams stay idle.
+// every entry point that uses the context's pinned result buffers refuses to run while a deferred
+// batch (jds_roundtrip_batch_begin) is waiting for jds_ctx_finish
+#define JDS_NO_PENDING(c)                                                                        \
+    if ((c)->pend.active)                                                                        \
+        return fail(JDS_ERR_INVALID, "a deferred batch is pending on this context: call jds_ctx_finish first")
+
 // sync + host-side metric structs of a finished job (shared by run_job and jds_ctx_finish)
 static void fill_job_metrics(const jds_ctx* c, jds_metrics* out, int units, uint64_t ssim_count,
                              uint64_t ncoef, uint64_t luma_blocks, double ms_per_unit) {
@@ -589,8 +595,7 @@ static void fill_job_metrics(const jds_ctx* c, jds_metrics* out, int units, uint
 }
 
 static int run_job(jds_ctx* c, const UnitJob& J) {
-    if (c->pend.active)
-        return fail(JDS_ERR_INVALID, "a deferred batch is pending on this context: call jds_ctx_finish first");
+    JDS_NO_PENDING(c);
     const Geom& g = J.g;
     const jds_params* p = J.p;
     const bool exact = p->precision == JDS_EXACT;
@@ -1351,6 +1356,7 @@ extern "C" int jds_aliasing_demo(jds_ctx* c, const uint8_t* rgb, int rgb_loc, in
 extern "C" int jds_aliasing_metrics(jds_ctx* c, const uint8_t* a, const uint8_t* b, int loc,
                                     int height, int width, jds_metrics* m_rgb, jds_metrics* m_luma) {
     if (!c || !a || !b || !m_rgb || !m_luma) return fail(JDS_ERR_INVALID, "NULL argument");
+    JDS_NO_PENDING(c);
     if (height < 1 || width < 1) return fail(JDS_ERR_INVALID, "bad frame size %dx%d", height, width);
     JDS_CUDA(cudaSetDevice(c->device));
     const size_t n_px = (size_t)height * width, frame_bytes = n_px * 3;
@@ -1379,6 +1385,7 @@ extern "C" int jds_aliasing_metrics(jds_ctx* c, const uint8_t* a, const uint8_t*
 extern "C" int jds_entropy_bits(jds_ctx* c, const int16_t* coeffs, int loc, int height, int width,
                                 int subsampling, uint64_t scan_bits[3]) {
     if (!c || !coeffs || !scan_bits) return fail(JDS_ERR_INVALID, "NULL argument");
+    JDS_NO_PENDING(c);
     Geom g;
     int rc = make_geom(height, width, subsampling, &g);
     if (rc) return rc;
@@ -1474,6 +1481,7 @@ extern "C" int jds_entropy_encode(jds_ctx* c, const int16_t* coeffs, int loc, in
                                   int subsampling, uint8_t* out, int out_loc, uint64_t out_capacity,
                                   uint64_t scan_bytes[3], uint64_t scan_bits[3]) {
     if (!c || !coeffs || !scan_bytes || !scan_bits) return fail(JDS_ERR_INVALID, "NULL argument");
+    JDS_NO_PENDING(c);
     Geom g;
     int rc = make_geom(height, width, subsampling, &g);
     if (rc) return rc;
@@ -1500,6 +1508,7 @@ extern "C" int jds_jfif_encode(jds_ctx* c, const int16_t* coeffs, int loc, int h
                                int subsampling, const double qtable[64], uint8_t* out,
                                uint64_t out_capacity, uint64_t* out_bytes, uint64_t scan_bits[3]) {
     if (!c || !coeffs || !qtable || !out_bytes || !scan_bits) return fail(JDS_ERR_INVALID, "NULL argument");
+    JDS_NO_PENDING(c);
     Geom g;
     int rc = make_geom(height, width, subsampling, &g);
     if (rc) return rc;
@@ -1676,6 +1685,7 @@ extern "C" int jds_selected_block(jds_ctx* c, const jds_params* p, const uint8_t
     if (!c || !rgb || !present || !original || !shifted || !dct || !quantized || !dequantized ||
         !reconstructed)
         return fail(JDS_ERR_INVALID, "NULL argument");
+    JDS_NO_PENDING(c);
     int rc = check_params(p);
     if (rc) return rc;
     if (p->quality < 1 || p->quality > 100)
@@ -1836,6 +1846,7 @@ extern "C" int jds_upsample_plane(jds_ctx* c, const double* plane, int height, i
 extern "C" int jds_compare_images(jds_ctx* c, const uint8_t* a, const uint8_t* b, int loc,
                                   int height, int width, jds_metrics* m) {
     if (!c || !a || !b || !m) return fail(JDS_ERR_INVALID, "NULL argument");
+    JDS_NO_PENDING(c);
     if (height < 1 || width < 1) return fail(JDS_ERR_INVALID, "bad frame size %dx%d", height, width);
     JDS_CUDA(cudaSetDevice(c->device));
     const size_t frame_bytes = (size_t)height * width * 3;
@@ -1858,6 +1869,7 @@ extern "C" int jds_compare_images(jds_ctx* c, const uint8_t* a, const uint8_t* b
 extern "C" int jds_bitrate_partials(jds_ctx* c, const int16_t* coeffs, int loc, uint64_t n,
                                     uint64_t* nnz, uint64_t* coeff_bits) {
     if (!c || !coeffs || !nnz || !coeff_bits) return fail(JDS_ERR_INVALID, "NULL argument");
+    JDS_NO_PENDING(c);
     JDS_CUDA(cudaSetDevice(c->device));
     int rc;
     if ((rc = ensure(c, c->metrics, sizeof(DevMetrics)))) return rc;
