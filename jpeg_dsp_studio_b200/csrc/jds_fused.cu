@@ -75,6 +75,9 @@ constexpr int BLK_STRIDE = 68;                    // floats per 8x8 block slot i
 // (the eight lanes of a quarter-warp that walks eight blocks of one row) XOR one bit of the row
 // (SHIFT = 1 for 4:2:0, 0 for 4:2:2: a quarter-warp of the compose phase walks four blocks of two
 // tasks whose rows differ in exactly that bit)
+#ifndef JDS_CA_PREFETCH
+#define JDS_CA_PREFETCH 1
+#endif
 #ifndef JDS_LU_ROWSWZ
 #define JDS_LU_ROWSWZ 1
 #endif
@@ -340,6 +343,19 @@ k_fast_chroma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
         return;
     }
 
+#if JDS_CA_PREFETCH
+    // the tasks below fetch their rows two at a time: let L2 pull the whole tile in now
+    {
+        constexpr int LINES = CA_BX * 16 * 3 / 128;                   // 6 lines of 128 B per luma row
+        const size_t row_end = (size_t)g.W * 3;
+        for (int i = tid; i < ROWS * LINES; i += CA_NT) {
+            const int r = i / LINES, l = i % LINES;
+            const size_t off = (size_t)x0 * 3 + 128 * (size_t)l;
+            if (r < n_rows && off < row_end)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(in + (size_t)(y0 + r) * row_end + off));
+        }
+    }
+#endif
     // ---- decimation: a task = one chroma row x 8 chroma samples (16 luma pixels) ----
     // channel sums over the 2x1 / 2x2 footprint with IDP4A on the interleaved bytes,
     // accumulated on top of 2^23's bit pattern so the fp32 value is one FADD away
@@ -473,6 +489,19 @@ k_fast_chroma_pf(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
     if (STAGE != STAGE_FWD) load_tables(tables + (size_t)unit * table_stride, sm.fq, sm.dq, tid, CA_NT);
 
     constexpr int PROWS = ChromaPfSmem<SUB>::PROWS;
+#if JDS_CA_PREFETCH
+    // the row filter runs in passes: let L2 pull the rows of the later passes in while the first runs
+    {
+        constexpr int LINES = CA_BX * 16 * 3 / 128;
+        const size_t row_end = (size_t)g.W * 3;
+        for (int i = tid; i < (LROWS - 2) * LINES; i += CA_NT) {
+            const int r = i / LINES, l = i % LINES;
+            const size_t off = (size_t)x0 * 3 + 128 * (size_t)l;
+            if (r >= PROWS && r < n_rows && off < row_end)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(in + (size_t)(y0 + r) * row_end + off));
+        }
+    }
+#endif
     for (int part = 0; part < ChromaPfSmem<SUB>::PARTS; ++part) {
     const int lr0 = part * PROWS;                                         // first luma row (tile local, halo = -1)
     if (lr0 >= n_rows) break;

@@ -27,6 +27,12 @@ namespace jds {
 #define JDS_XL_MIN_CTAS 3      // CTAs per SM the exact kernels are compiled for: 168 registers, 4-8 bytes of spills,
                                // 12 warps per SM (2: 255 registers, luma 0.96 ms; 3: 0.85 ms; 4: 1.01 ms per 16 x 4K)
 #endif
+#ifndef JDS_XC_PREFETCH
+#define JDS_XC_PREFETCH 1
+#endif
+#ifndef JDS_XL_PREFETCH
+#define JDS_XL_PREFETCH 1
+#endif
 constexpr int XL_BX = 32, XL_BY = 4, XL_NT = 128;     // 32 x 4 luma blocks = 256 x 32 pixels per CTA
 constexpr int XL_TW = XL_BX * 8, XL_TH = XL_BY * 8;
 constexpr int XL_STRIDE = 66;                         // doubles per block slot: 528 B = 4 * 128 + 16,
@@ -72,6 +78,25 @@ k_exact_luma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
         }
     }
 
+#if JDS_XL_PREFETCH
+    // The compose phase at the end reads this tile's reconstructed chroma straight from the planes
+    // (16 frames of fp64 planes are not L2 resident): ask L2 for those lines now, so that the loads
+    // find them there ~30 us later instead of waiting on DRAM one dependent task after the other.
+    if (SUB != 0) {
+        constexpr int NCR = (SUB == 2) ? XL_TH / 2 + 2 : XL_TH;
+        constexpr int LINES = XL_TW / 2 * 8 / 128 + 1;             // 128-byte lines per row segment
+        const int cr_lo = (SUB == 2) ? max((y0 >> 1) - 1, 0) : y0;
+        const double* Cb0 = rec + (size_t)unit * rec_stride + g.plane_y;
+        for (int i = tid; i < 2 * NCR * LINES; i += XL_NT) {
+            const int chn = i / (NCR * LINES), r = (i / LINES) % NCR, l = i % LINES;
+            const int row = min(cr_lo + r, g.hc - 1), col = (x0 >> 1) + 16 * l;
+            if (col < g.wcp) {
+                const double* pl = Cb0 + (size_t)chn * g.plane_c + (size_t)row * g.wcp + col;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pl));
+            }
+        }
+    }
+#endif
     // ---- RGB -> Y (A1), block layout: a task = one row x 16 pixels ---------------------
     {
         constexpr int NTASK = XL_TH * (XL_TW / 16) / XL_NT;        // 4
@@ -305,6 +330,19 @@ k_exact_chroma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
             sm.tb.dqx[i] = src->dqx[i];
         }
     }
+#if JDS_XC_PREFETCH
+    // the four tasks below load their rows one after the other: have L2 fetch the whole tile now
+    {
+        constexpr int LINES = XC_BX * 16 * 3 / 128;                 // 6 lines of 128 B per luma row
+        const size_t row_end = (size_t)g.W * 3;
+        for (int i = tid; i < XC_BY * 8 * VS * LINES; i += XC_NT) {
+            const int r = i / LINES, l = i % LINES;
+            const size_t off = (size_t)x0 * 3 + 128 * (size_t)l;
+            if (r < n_rows && off < row_end)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(in + (size_t)(y0 + r) * row_end + off));
+        }
+    }
+#endif
     // ---- decimation: a task = one chroma row x 8 chroma samples (16 luma pixels) ---------
     {
         constexpr int NTASK = XC_BY * 8 * XC_BX / XC_NT;            // 4
