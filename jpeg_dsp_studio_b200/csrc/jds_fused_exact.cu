@@ -27,6 +27,9 @@ namespace jds {
 #define JDS_XL_MIN_CTAS 3      // CTAs per SM the exact kernels are compiled for: 168 registers, 4-8 bytes of spills,
                                // 12 warps per SM (2: 255 registers, luma 0.96 ms; 3: 0.85 ms; 4: 1.01 ms per 16 x 4K)
 #endif
+#ifndef JDS_XL_COMPOSE_UNROLL
+#define JDS_XL_COMPOSE_UNROLL 1
+#endif
 #ifndef JDS_XC_PREFETCH
 #define JDS_XC_PREFETCH 1
 #endif
@@ -196,6 +199,8 @@ k_exact_luma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
     const double* Cbr = rec + (size_t)unit * rec_stride + g.plane_y;
     const double* Crr = Cbr + g.plane_c;
     uint8_t* out = recon + (size_t)unit * recon_stride;
+    constexpr int COMPOSE_UNROLL = JDS_XL_COMPOSE_UNROLL;
+#pragma unroll COMPOSE_UNROLL
     for (int task = tid; task < (XL_TH / RPT) * (XL_TW / 4); task += XL_NT) {
         const int rp = task / (XL_TW / 4), g4 = task % (XL_TW / 4);
         const int r0 = rp * RPT;
