@@ -89,6 +89,7 @@ struct jds_ctx {
     int tables_slot = 0;
     size_t scratch_budget = (size_t)1 << 30;
     int pipe_chunk = 0;
+    bool no_dual_sweep = false;
     // a jds_roundtrip_batch_begin whose results jds_ctx_finish has not collected yet
     struct Pending {
         bool active = false;
@@ -194,6 +195,8 @@ extern "C" int jds_ctx_create(int device, jds_ctx** out) {
     const char* l2c = getenv("JDS_L2_CHUNK");
     c->l2_chunking = l2c ? atoi(l2c) : 0;
     if (c->l2_chunking < 0) c->l2_chunking = 0;
+    const char* nds = getenv("JDS_NO_DUAL_SWEEP");
+    c->no_dual_sweep = nds && atoi(nds) != 0;
     const char* pc = getenv("JDS_PIPE_CHUNK");      // A/B runs: frames per chunk of the host pipeline
     c->pipe_chunk = pc ? atoi(pc) : 0;
     const char* mb = getenv("JDS_SCRATCH_MB");
@@ -450,18 +453,11 @@ static int launch_chunk(jds_ctx* c, const UnitJob& J, const ChunkPtrs& P, int n,
         // each compute stream has its own chroma-plane scratch
         float* cpl = (float*)c->planes.p + (size_t)scratch_slot * cpl_stride * (size_t)c->plan_chunk;
         // sweeps (one shared frame, metrics only): the quality-independent forward half - colour,
-        // decimation / prefilter, forward DCT - runs once per frame into c->fcoef (first chunk),
-        // every quality point then starts at quantisation (gui/worker.py:55-74 redoes it all)
+        // decimation / prefilter, forward DCT - ran once per frame into c->fcoef (run_job's pre-pass),
+        // every quality point starts at quantisation (gui/worker.py:55-74 redoes it all)
         const bool hoist = P.hoist;
         float* fcoef = hoist ? (float*)c->fcoef.p : nullptr;
         const int stage = hoist ? 2 : 0;
-        if (hoist && P.first_chunk) {
-            JDS_CUDA(launch_fused_chroma(g, p->prefilter, P.d_rgb, 0, nullptr, 0, nullptr, 0, nullptr, 0,
-                                         nullptr, 1, s, 1, fcoef));
-            JDS_CUDA(launch_fused_luma(g, P.d_rgb, 0, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0, nullptr,
-                                       1, s, 1, fcoef));
-            c->launches += 2;
-        }
         ran[0] = g.sub != 0;
         if (ran[0]) {
             JDS_CUDA(launch_fused_chroma(g, p->prefilter, P.d_rgb, P.rgb_stride, cpl, cpl_stride, P.d_tables,
@@ -664,8 +660,16 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
     // hoisted sweep: one shared frame, fused kernels, metrics (and optionally recon) only
     const bool hoist = J.shared_input && will_fuse && J.units > 1 && !want_coeffs && !want_hist &&
                        fused_fcoef_floats(g) > 0 && !c->no_hoist;
-    // (a hoisted sweep's pre-pass runs on the first stream only: no second compute stream)
-    const bool dual = c->l2_chunking > 0 && will_fuse && !c->stage_timing && J.units > chunk && !hoist;
+    // A hoisted sweep's points split into two halves that alternate over the two compute streams
+    // (after the pre-pass): the ragged last wave of one half's kernels is filled by the other
+    // half's - what limits the strong scaling of a 12 / 13-point share (JDS_NO_DUAL_SWEEP=1: off)
+    const bool dual_sweep = hoist && !c->stage_timing && !c->no_dual_sweep && J.units >= 4;
+    if (dual_sweep && chunk >= J.units) {
+        chunk = (J.units + 1) / 2;
+        c->plan_chunk = chunk;
+    }
+    const bool dual = (c->l2_chunking > 0 && will_fuse && !c->stage_timing && J.units > chunk && !hoist) ||
+                      (dual_sweep && J.units > chunk);
     const int nscr = (pipelined || dual) ? 2 : 1;        // recon / coefficient scratch slots
 
     int rc;
@@ -726,6 +730,17 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
     JDS_CUDA(cudaMemsetAsync(d_metrics, 0, sizeof(DevMetrics) * J.units, s));
     if (J.shared_input && in_host)
         JDS_CUDA(cudaMemcpyAsync(c->in.p, J.rgb, frame_bytes, cudaMemcpyHostToDevice, s));
+    if (hoist) {
+        JDS_CUDA(cudaEventRecord(c->ev0, s));              // gpu_ms of a sweep includes its pre-pass
+        // pre-pass of the sweep's one frame: colour, prefilter / decimation, forward DCT -> c->fcoef
+        const uint8_t* d_frame = in_host ? (const uint8_t*)c->in.p : J.rgb;
+        float* fcoef = (float*)c->fcoef.p;
+        JDS_CUDA(launch_fused_chroma(g, p->prefilter, d_frame, 0, nullptr, 0, nullptr, 0, nullptr, 0,
+                                     nullptr, 1, s, 1, fcoef));
+        JDS_CUDA(launch_fused_luma(g, d_frame, 0, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0, nullptr,
+                                   1, s, 1, fcoef));
+        c->launches += 2;
+    }
     if (dual) {
         JDS_CUDA(cudaEventRecord(c->ev_setup, s));
         JDS_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_setup, 0));
@@ -778,7 +793,7 @@ static int run_job(jds_ctx* c, const UnitJob& J) {
 
         // ev0 .. ev1 bracket the kernels: after the first chunk's input is on its way, before
         // the last chunk's results are copied out
-        if (u0 == 0) JDS_CUDA(cudaEventRecord(c->ev0, s));
+        if (u0 == 0 && !hoist) JDS_CUDA(cudaEventRecord(c->ev0, s));
         // per-stage events for the first kTimedChunks chunks of the call
         cudaEvent_t* evs = (c->stage_timing && !J.d_records && chunk_idx < jds_ctx::kTimedChunks)
                                ? &c->evs[5 * chunk_idx] : nullptr;

@@ -48,11 +48,15 @@ inline void fill_tables(int quality, QTables* t) {
         t->rq[i] = r;
         t->dqx[i] = ldexp(t->q[i], -exact_coeff_shift(i) - 4);   // Q * 2^-shift / 16, exact
     }
-    static double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};      // AAN scale factors, computed once
-    if (s[0] == 0.0) {
-        for (int k = 7; k >= 1; --k) s[k] = sqrt(2.0) * cos(k * M_PI / 16.0);
-        s[0] = 1.0;
-    }
+    struct Aan {                                        // AAN scale factors
+        double s[8];
+        Aan() {
+            s[0] = 1.0;
+            for (int k = 1; k < 8; ++k) s[k] = sqrt(2.0) * cos(k * M_PI / 16.0);
+        }
+    };
+    static const Aan aan;                               // C++11: initialised once, thread safe
+    const double* s = aan.s;
     for (int u = 0; u < 8; ++u)
         for (int v = 0; v < 8; ++v) {
             const double fwd = (2.0 * sqrt(2.0) * s[u]) * (2.0 * sqrt(2.0) * s[v]);
