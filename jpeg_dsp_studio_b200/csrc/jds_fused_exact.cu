@@ -320,13 +320,15 @@ k_exact_chroma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ExactChromaSmem& sm = *reinterpret_cast<ExactChromaSmem*>(smem_raw);
     constexpr int VS = (SUB == 2) ? 2 : 1;            // luma rows per chroma row
+    constexpr int HS = (SUB == 0) ? 1 : 2;            // luma pixels per chroma sample (4:4:4: the planes are the pixels)
+    constexpr int SEG_PX = 8 * HS;                    // luma pixels of a task (8 chroma samples)
     const int tid = threadIdx.x;
     const int unit = blockIdx.z;
     const uint8_t* in = rgb + (size_t)unit * rgb_stride;
     const int bx0 = blockIdx.x * XC_BX, by0 = blockIdx.y * XC_BY;   // chroma block origin
-    const int x0 = bx0 * 16, y0 = by0 * 8 * VS;                      // luma pixel origin
+    const int x0 = bx0 * SEG_PX, y0 = by0 * 8 * VS;                  // luma pixel origin
     const int n_rows = min(XC_BY * 8 * VS, g.H - y0);
-    const int n_px = min(XC_BX * 16, g.W - x0);
+    const int n_px = min(XC_BX * SEG_PX, g.W - x0);
     {
         const QTables* src = tables + (size_t)unit * table_stride;
         for (int i = tid; i < 64; i += XC_NT) {
@@ -338,7 +340,7 @@ k_exact_chroma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
 #if JDS_XC_PREFETCH
     // the four tasks below load their rows one after the other: have L2 fetch the whole tile now
     {
-        constexpr int LINES = XC_BX * 16 * 3 / 128;                 // 6 lines of 128 B per luma row
+        constexpr int LINES = XC_BX * SEG_PX * 3 / 128;             // 6 (3) lines of 128 B per luma row
         const size_t row_end = (size_t)g.W * 3;
         for (int i = tid; i < XC_BY * 8 * VS * LINES; i += XC_NT) {
             const int r = i / LINES, l = i % LINES;
@@ -348,11 +350,11 @@ k_exact_chroma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
         }
     }
 #endif
-    // ---- decimation: a task = one chroma row x 8 chroma samples (16 luma pixels) ---------
+    // ---- decimation: a task = one chroma row x 8 chroma samples (16 / 8 luma pixels) -----
     {
         constexpr int NTASK = XC_BY * 8 * XC_BX / XC_NT;            // 4
         const int seg = tid & 15, crbase = tid >> 4;
-        const bool seg_ok = seg * 16 < n_px;
+        const bool seg_ok = seg * SEG_PX < n_px;
 #pragma unroll 1
         for (int k = 0; k < NTASK; ++k) {
             const int cr = crbase + 8 * k;
@@ -360,12 +362,21 @@ k_exact_chroma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
             uint32_t w[VS][12];
 #pragma unroll
             for (int v = 0; v < VS; ++v) {
-                const uint4* q = reinterpret_cast<const uint4*>(
-                    in + ((size_t)(y0 + cr * VS + v) * g.W + x0 + seg * 16) * 3);
+                const uint8_t* row = in + ((size_t)(y0 + cr * VS + v) * g.W + x0 + seg * SEG_PX) * 3;
+                if (SUB == 0) {                         // 24 bytes, 8-byte aligned
+                    const uint2* q = reinterpret_cast<const uint2*>(row);
 #pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const uint4 a = __ldg(q + i);
-                    w[v][4 * i] = a.x; w[v][4 * i + 1] = a.y; w[v][4 * i + 2] = a.z; w[v][4 * i + 3] = a.w;
+                    for (int i = 0; i < 3; ++i) {
+                        const uint2 a = __ldg(q + i);
+                        w[v][2 * i] = a.x; w[v][2 * i + 1] = a.y;
+                    }
+                } else {
+                    const uint4* q = reinterpret_cast<const uint4*>(row);
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        const uint4 a = __ldg(q + i);
+                        w[v][4 * i] = a.x; w[v][4 * i + 1] = a.y; w[v][4 * i + 2] = a.z; w[v][4 * i + 3] = a.w;
+                    }
                 }
             }
             const int blk = (cr >> 3) * XC_BX + seg, ry = cr & 7;
@@ -376,19 +387,22 @@ k_exact_chroma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
                 double ob[2], orr[2];
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const int px = 2 * (2 * s2 + e);    // first luma pixel of the sample
+                    const int px = HS * (2 * s2 + e);   // first luma pixel of the sample
                     double cb[VS][2], cr_[VS][2];
 #pragma unroll
                     for (int v = 0; v < VS; ++v)
 #pragma unroll
-                        for (int d = 0; d < 2; ++d) {
+                        for (int d = 0; d < HS; ++d) {
                             const int b = 3 * (px + d);
                             const double rr = byte_to_double(w[v][b >> 2], b & 3);
                             const double gg = byte_to_double(w[v][(b + 1) >> 2], (b + 1) & 3);
                             const double bb = byte_to_double(w[v][(b + 2) >> 2], (b + 2) & 3);
                             rgb_to_cbcr<P>(rr, gg, bb, cb[v][d], cr_[v][d]);
                         }
-                    if (SUB == 1) {                     // A3, 4:2:2: (a+b)*0.5
+                    if (SUB == 0) {                     // 4:4:4: subsample_chroma copies (color_space.py:35-36)
+                        ob[e] = cb[0][0];
+                        orr[e] = cr_[0][0];
+                    } else if (SUB == 1) {              // A3, 4:2:2: (a+b)*0.5
                         ob[e] = P::mul(P::add(cb[0][0], cb[0][1]), 0.5);
                         orr[e] = P::mul(P::add(cr_[0][0], cr_[0][1]), 0.5);
                     } else {                            // A3, 4:2:0: (((a+b)+c)+d)*0.25
@@ -478,6 +492,7 @@ cudaError_t exact_fused_configure_device() {
 #define JDS_SET(K)                                                                              \
     if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize,                \
                                   (int)sizeof(ExactChromaSmem))) != cudaSuccess) return e
+    JDS_SET((k_exact_chroma<0, false>)); JDS_SET((k_exact_chroma<0, true>));
     JDS_SET((k_exact_chroma<1, false>)); JDS_SET((k_exact_chroma<1, true>));
     JDS_SET((k_exact_chroma<2, false>)); JDS_SET((k_exact_chroma<2, true>));
 #undef JDS_SET
@@ -485,7 +500,9 @@ cudaError_t exact_fused_configure_device() {
 }
 
 // chroma of a subsampled, block-aligned frame WITHOUT prefilter in one kernel
-bool exact_chroma_supported(const Geom& g, int prefilter) { return g.sub != 0 && !prefilter && !g.general; }
+bool exact_chroma_supported(const Geom& g, int prefilter) {
+    return g.sub == 0 || (!prefilter && !g.general);      // 4:4:4 has no decimation, hence no prefilter
+}
 
 cudaError_t launch_exact_chroma(const Geom& g, const uint8_t* rgb, size_t rgb_stride, double* rec,
                                 size_t rec_stride, const QTables* tables, int table_stride,
@@ -496,7 +513,8 @@ cudaError_t launch_exact_chroma(const Geom& g, const uint8_t* rgb, size_t rgb_st
 #define JDS_LAUNCH_XC(SUBV, CO)                                                                 \
     k_exact_chroma<SUBV, CO><<<grid, XC_NT, smem, s>>>(g, rgb, rgb_stride, rec, rec_stride, tables, \
                                                        table_stride, coeffs, coeff_stride, metrics)
-    if (g.sub == 1) { if (coeffs) JDS_LAUNCH_XC(1, true); else JDS_LAUNCH_XC(1, false); }
+    if (g.sub == 0) { if (coeffs) JDS_LAUNCH_XC(0, true); else JDS_LAUNCH_XC(0, false); }
+    else if (g.sub == 1) { if (coeffs) JDS_LAUNCH_XC(1, true); else JDS_LAUNCH_XC(1, false); }
     else { if (coeffs) JDS_LAUNCH_XC(2, true); else JDS_LAUNCH_XC(2, false); }
 #undef JDS_LAUNCH_XC
     return cudaGetLastError();
