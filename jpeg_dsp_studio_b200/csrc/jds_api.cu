@@ -489,7 +489,7 @@ static int launch_chunk(jds_ctx* c, const UnitJob& J, const ChunkPtrs& P, int n,
         if (exact_chroma_supported(g, p->prefilter)) {
             // decimation + chroma codec in one kernel (stage "forward_colour" in the timings)
             ran[0] = true;
-            JDS_CUDA(launch_exact_chroma(g, P.d_rgb, P.rgb_stride, (double*)rec, rec_stride, P.d_tables,
+            JDS_CUDA(launch_exact_chroma(g, p->prefilter, P.d_rgb, P.rgb_stride, (double*)rec, rec_stride, P.d_tables,
                                          tstride, P.d_coeffs, ncoef, P.d_metrics, n, s));
             c->launches++;
             if (timed) JDS_CUDA(cudaEventRecord(evs[1], s));

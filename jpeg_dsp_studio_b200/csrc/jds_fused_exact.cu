@@ -85,14 +85,15 @@ k_exact_luma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
     // The compose phase at the end reads this tile's reconstructed chroma straight from the planes
     // (16 frames of fp64 planes are not L2 resident): ask L2 for those lines now, so that the loads
     // find them there ~30 us later instead of waiting on DRAM one dependent task after the other.
-    if (SUB != 0) {
+    {
         constexpr int NCR = (SUB == 2) ? XL_TH / 2 + 2 : XL_TH;
-        constexpr int LINES = XL_TW / 2 * 8 / 128 + 1;             // 128-byte lines per row segment
+        constexpr int CW = (SUB == 0) ? XL_TW : XL_TW / 2;         // chroma samples under the tile's row
+        constexpr int LINES = CW * 8 / 128 + (SUB == 0 ? 0 : 1);   // 128-byte lines per row segment
         const int cr_lo = (SUB == 2) ? max((y0 >> 1) - 1, 0) : y0;
         const double* Cb0 = rec + (size_t)unit * rec_stride + g.plane_y;
         for (int i = tid; i < 2 * NCR * LINES; i += XL_NT) {
             const int chn = i / (NCR * LINES), r = (i / LINES) % NCR, l = i % LINES;
-            const int row = min(cr_lo + r, g.hc - 1), col = (x0 >> 1) + 16 * l;
+            const int row = min(cr_lo + r, g.hc - 1), col = (SUB == 0 ? x0 : (x0 >> 1)) + 16 * l;
             if (col < g.wcp) {
                 const double* pl = Cb0 + (size_t)chn * g.plane_c + (size_t)row * g.wcp + col;
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(pl));
@@ -310,6 +311,81 @@ struct ExactChromaSmem {
     QTables tb;
 };
 
+// codec of the tile's 2 x 64 chroma blocks in place (thread t: channel t / 64, block t % 64) and
+// the reconstructed planes out; shared by the plain and the prefilter chroma kernels
+template <bool COEFFS>
+__device__ __forceinline__ void exact_chroma_tail(const Geom& g, double (*plane)[XC_BX * XC_BY][XL_STRIDE],
+                                                  const QTables& tb, int bx0, int by0, int unit,
+                                                  double* __restrict__ rec, size_t rec_stride,
+                                                  int16_t* __restrict__ coeffs, size_t coeff_stride,
+                                                  DevMetrics* __restrict__ metrics) {
+    typedef Exact P;
+    const int tid = threadIdx.x;
+    // ---- codec: thread t -> channel t / 64, block t % 64, in place ------------------------
+    {
+        const int ch = tid >> 6, blk = tid & 63;
+        const int bx = bx0 + (blk & (XC_BX - 1)), by = by0 + (blk >> 4);
+        unsigned long long bits = 0, nnz = 0;
+        if (bx < g.nbx_c && by < g.nby_c) {
+            double v[64];
+            double2* slot = reinterpret_cast<double2*>(&plane[ch][blk][0]);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const double2 a = slot[i];
+                v[2 * i] = a.x;
+                v[2 * i + 1] = a.y;
+            }
+            int16_t q[64];
+            BlockStats st;
+            BlockCodec<P>::run(v, q, tb, st, nullptr, nullptr);
+            bits = st.bits;
+            nnz = st.nnz;
+            if (COEFFS) {
+                uint4* out = reinterpret_cast<uint4*>(
+                    coeffs + (size_t)unit * coeff_stride +
+                    ((size_t)g.nblk_y + (size_t)ch * g.nblk_c + (size_t)by * g.nbx_c + bx) * 64);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    uint4 pk;
+                    pk.x = (uint16_t)q[i * 8 + 0] | ((uint32_t)(uint16_t)q[i * 8 + 1] << 16);
+                    pk.y = (uint16_t)q[i * 8 + 2] | ((uint32_t)(uint16_t)q[i * 8 + 3] << 16);
+                    pk.z = (uint16_t)q[i * 8 + 4] | ((uint32_t)(uint16_t)q[i * 8 + 5] << 16);
+                    pk.w = (uint16_t)q[i * 8 + 6] | ((uint32_t)(uint16_t)q[i * 8 + 7] << 16);
+                    out[i] = pk;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) slot[i] = make_double2(v[2 * i], v[2 * i + 1]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            bits += __shfl_down_sync(0xffffffffu, bits, o);
+            nnz += __shfl_down_sync(0xffffffffu, nnz, o);
+        }
+        if ((tid & 31) == 0 && nnz) {
+            atomicAdd(&metrics[unit].coeff_bits, bits);
+            atomicAdd(&metrics[unit].nnz, nnz);
+        }
+    }
+    __syncthreads();
+    // ---- reconstructed planes out: a task = (channel, chroma row, 8 samples): consecutive
+    // threads write consecutive 64-byte pieces of a plane row --------------------------------
+    for (int task = tid; task < 2 * XC_BY * 8 * XC_BX; task += XC_NT) {
+        const int ch = task / (XC_BY * 8 * XC_BX);
+        const int rem = task % (XC_BY * 8 * XC_BX);
+        const int cr = rem / XC_BX, seg = rem % XC_BX;
+        const int bx = bx0 + seg, cy = by0 * 8 + cr;
+        if (bx >= g.nbx_c || cy >= g.hcp) continue;
+        const int blk = (cr >> 3) * XC_BX + seg, ry = cr & 7;
+        const double2* src = reinterpret_cast<const double2*>(&plane[ch][blk][ry * 8]);
+        double2* dst = reinterpret_cast<double2*>(rec + (size_t)unit * rec_stride + g.plane_y +
+                                                  (size_t)ch * g.plane_c + (size_t)cy * g.wcp + bx * 8);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dst[i] = src[i];
+    }
+}
+
+
 template <int SUB, bool COEFFS>
 __global__ void __launch_bounds__(XC_NT, JDS_XL_MIN_CTAS)
 k_exact_chroma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
@@ -416,68 +492,149 @@ k_exact_chroma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
         }
     }
     __syncthreads();
-    // ---- codec: thread t -> channel t / 64, block t % 64, in place ------------------------
+    exact_chroma_tail<COEFFS>(g, sm.plane, sm.tb, bx0, by0, unit, rec, rec_stride, coeffs, coeff_stride, metrics);
+}
+
+// ------------------------------------------------------------------------------
+// exact chroma kernel WITH the anti-alias prefilter (use_prefilter=True, 4:2:2 / 4:2:0):
+// cv2.GaussianBlur(3x3, sigma 0.75, REFLECT_101) of the full-resolution Cb / Cr (A2) and the
+// INTER_AREA average (A3) in the reference's own operation order - the blur cannot be folded
+// into the average here, every product and sum is individually rounded.  The tile's luma rows
+// go through the row pass in passes of XP_PROWS rows (+1 halo row above and below) into a
+// shared-memory buffer; the column pass and the average then produce the pass's chroma rows.
+// Replaces k_forward(chroma_only) - which recomputes the colour conversion and the row pass of
+// the 4 x 4 pixels under every chroma sample - plus the chroma-only k_codec.
+// Block-aligned frames only (fused_supported: W % 16 == 0, so A2's non-FMA tail columns do
+// not occur: W4 == W).
+// ------------------------------------------------------------------------------
+constexpr int XP_PROWS = 8;                               // luma rows per pass
+
+template <int SUB>
+struct ExactChromaPfSmem {
+    static constexpr int VS = (SUB == 2) ? 2 : 1;
+    static constexpr int LROWS = XC_BY * 8 * VS;          // luma rows of the tile
+    static constexpr int PARTS = LROWS / XP_PROWS;
+    alignas(16) double plane[2][XC_BX * XC_BY][XL_STRIDE];
+    QTables tb;
+    // row-filtered Cb / Cr of the pass's luma rows (row 0 = the row above the pass), pixel pair i of
+    // segment seg at [i][seg]: consecutive lanes (segments) touch consecutive 16-byte slots
+    alignas(16) double2 hrow[XP_PROWS + 2][2][8][XC_BX];
+};
+
+template <int SUB, bool COEFFS>
+__global__ void __launch_bounds__(XC_NT, 2)
+k_exact_chroma_pf(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
+                  double* __restrict__ rec, size_t rec_stride,
+                  const QTables* __restrict__ tables, int table_stride,
+                  int16_t* __restrict__ coeffs, size_t coeff_stride, DevMetrics* __restrict__ metrics) {
+    typedef Exact P;
+    typedef ExactChromaPfSmem<SUB> Smem;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    constexpr int VS = Smem::VS;
+    const int tid = threadIdx.x;
+    const int unit = blockIdx.z;
+    const uint8_t* in = rgb + (size_t)unit * rgb_stride;
+    const int bx0 = blockIdx.x * XC_BX, by0 = blockIdx.y * XC_BY;   // chroma block origin
+    const int x0 = bx0 * 16, y0 = by0 * 8 * VS;                      // luma pixel origin
+    const int n_rows = min(Smem::LROWS, g.H - y0);
+    const int n_px = min(XC_BX * 16, g.W - x0);
     {
-        const int ch = tid >> 6, blk = tid & 63;
-        const int bx = bx0 + (blk & (XC_BX - 1)), by = by0 + (blk >> 4);
-        unsigned long long bits = 0, nnz = 0;
-        if (bx < g.nbx_c && by < g.nby_c) {
-            double v[64];
-            double2* slot = reinterpret_cast<double2*>(&sm.plane[ch][blk][0]);
+        const QTables* src = tables + (size_t)unit * table_stride;
+        for (int i = tid; i < 64; i += XC_NT) {
+            sm.tb.q[i] = src->q[i];
+            sm.tb.rq[i] = src->rq[i];
+            sm.tb.dqx[i] = src->dqx[i];
+        }
+    }
+#if JDS_XC_PREFETCH
+    {   // rows of the later passes: ask L2 for them while the first pass runs
+        constexpr int LINES = XC_BX * 16 * 3 / 128;
+        const size_t row_end = (size_t)g.W * 3;
+        for (int i = tid; i < Smem::LROWS * LINES; i += XC_NT) {
+            const int r = i / LINES, l = i % LINES;
+            const size_t off = (size_t)x0 * 3 + 128 * (size_t)l;
+            if (r >= XP_PROWS && r < n_rows && off < row_end)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(in + (size_t)(y0 + r) * row_end + off));
+        }
+    }
+#endif
+    for (int part = 0; part < Smem::PARTS; ++part) {
+        const int lr0 = part * XP_PROWS;                  // first luma row of the pass (tile local)
+        if (lr0 >= n_rows) break;
+        if (part) __syncthreads();                        // the last pass's phase B is done with hrow
+        // ---- phase A: a task = one luma row (halo rows included) x 16 pixels: colour (A1) and
+        // the row pass of the blur (A2) ------------------------------------------------------
+        for (int task = tid; task < (XP_PROWS + 2) * XC_BX; task += XC_NT) {
+            const int hr = task / XC_BX, seg = task % XC_BX;
+            if (lr0 + hr - 1 >= n_rows + 1 || seg * 16 >= n_px) continue;
+            const int y = reflect101(y0 + lr0 + hr - 1, g.H);          // REFLECT_101 at the frame's top / bottom
+            const int xs = x0 + seg * 16;
+            const uint8_t* row = in + ((size_t)y * g.W + xs) * 3;
+            const bool has_l = xs > 0, has_r = xs + 16 < g.W;
+            const uint4* q = reinterpret_cast<const uint4*>(row);
+            const uint4 c0 = __ldg(q), c1 = __ldg(q + 1), c2 = __ldg(q + 2);
+            const uint32_t wl = has_l ? __ldg(reinterpret_cast<const uint32_t*>(row) - 1) : 0u;   // bytes -4..-1
+            const uint32_t wr = has_r ? __ldg(reinterpret_cast<const uint32_t*>(row) + 12) : 0u;  // bytes 48..51
+            const uint32_t w[12] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w};
+            double cb[18], cr[18];                        // index i <-> pixel xs - 1 + i
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const double2 a = slot[i];
-                v[2 * i] = a.x;
-                v[2 * i + 1] = a.y;
+            for (int i = 0; i < 16; ++i) {
+                const int b = 3 * i;
+                rgb_to_cbcr<P>(byte_to_double(w[b >> 2], b & 3), byte_to_double(w[(b + 1) >> 2], (b + 1) & 3),
+                               byte_to_double(w[(b + 2) >> 2], (b + 2) & 3), cb[i + 1], cr[i + 1]);
             }
-            int16_t q[64];
-            BlockStats st;
-            BlockCodec<P>::run(v, q, sm.tb, st, nullptr, nullptr);
-            bits = st.bits;
-            nnz = st.nnz;
-            if (COEFFS) {
-                uint4* out = reinterpret_cast<uint4*>(
-                    coeffs + (size_t)unit * coeff_stride +
-                    ((size_t)g.nblk_y + (size_t)ch * g.nblk_c + (size_t)by * g.nbx_c + bx) * 64);
+            if (has_l) rgb_to_cbcr<P>(byte_to_double(wl, 1), byte_to_double(wl, 2), byte_to_double(wl, 3), cb[0], cr[0]);
+            else { cb[0] = cb[2]; cr[0] = cr[2]; }        // REFLECT_101: pixel -1 = pixel 1
+            if (has_r) rgb_to_cbcr<P>(byte_to_double(wr, 0), byte_to_double(wr, 1), byte_to_double(wr, 2), cb[17], cr[17]);
+            else { cb[17] = cb[15]; cr[17] = cr[15]; }    // pixel W = pixel W - 2
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+                sm.hrow[hr][0][i >> 1][seg] = make_double2(blur_row<P>(cb[i], cb[i + 1], cb[i + 2], false),
+                                                           blur_row<P>(cb[i + 1], cb[i + 2], cb[i + 3], false));
+                sm.hrow[hr][1][i >> 1][seg] = make_double2(blur_row<P>(cr[i], cr[i + 1], cr[i + 2], false),
+                                                           blur_row<P>(cr[i + 1], cr[i + 2], cr[i + 3], false));
+            }
+        }
+        __syncthreads();
+        // ---- phase B: a task = (channel, chroma row of the pass, 8 chroma samples): column pass
+        // (A2) on the VS luma rows under the samples, then the INTER_AREA average (A3) -------------
+        for (int task = tid; task < 2 * (XP_PROWS / VS) * XC_BX; task += XC_NT) {
+            const int ch = task / ((XP_PROWS / VS) * XC_BX);
+            const int rem = task % ((XP_PROWS / VS) * XC_BX);
+            const int crp = rem / XC_BX, seg = rem % XC_BX;               // chroma row inside the pass
+            const int lr = lr0 + crp * VS;                                // its first luma row (tile local)
+            if (lr >= n_rows || seg * 16 >= n_px) continue;
+            double f[VS][16];
+#pragma unroll
+            for (int v = 0; v < VS; ++v) {
+                const int hr = crp * VS + v + 1;                          // buffer row of luma row lr + v
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    uint4 pk;
-                    pk.x = (uint16_t)q[i * 8 + 0] | ((uint32_t)(uint16_t)q[i * 8 + 1] << 16);
-                    pk.y = (uint16_t)q[i * 8 + 2] | ((uint32_t)(uint16_t)q[i * 8 + 3] << 16);
-                    pk.z = (uint16_t)q[i * 8 + 4] | ((uint32_t)(uint16_t)q[i * 8 + 5] << 16);
-                    pk.w = (uint16_t)q[i * 8 + 6] | ((uint32_t)(uint16_t)q[i * 8 + 7] << 16);
-                    out[i] = pk;
+                    const double2 a = sm.hrow[hr - 1][ch][i][seg], b = sm.hrow[hr][ch][i][seg],
+                                  c = sm.hrow[hr + 1][ch][i][seg];
+                    f[v][2 * i] = blur_col<P>(a.x, b.x, c.x);
+                    f[v][2 * i + 1] = blur_col<P>(a.y, b.y, c.y);
                 }
             }
+            const int cr_t = (lr0 / VS) + crp;                            // chroma row inside the tile
+            const int blk = (cr_t >> 3) * XC_BX + seg, ry = cr_t & 7;
+            double2* dst = reinterpret_cast<double2*>(&sm.plane[ch][blk][ry * 8]);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) slot[i] = make_double2(v[2 * i], v[2 * i + 1]);
-        }
+            for (int s2 = 0; s2 < 4; ++s2) {
+                double o[2];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            bits += __shfl_down_sync(0xffffffffu, bits, o);
-            nnz += __shfl_down_sync(0xffffffffu, nnz, o);
-        }
-        if ((tid & 31) == 0 && nnz) {
-            atomicAdd(&metrics[unit].coeff_bits, bits);
-            atomicAdd(&metrics[unit].nnz, nnz);
+                for (int e = 0; e < 2; ++e) {
+                    const int px = 2 * (2 * s2 + e);
+                    if (SUB == 1) o[e] = P::mul(P::add(f[0][px], f[0][px + 1]), 0.5);
+                    else o[e] = P::mul(P::add(P::add(P::add(f[0][px], f[0][px + 1]), f[VS - 1][px]), f[VS - 1][px + 1]), 0.25);
+                }
+                dst[s2] = make_double2(o[0], o[1]);
+            }
         }
     }
     __syncthreads();
-    // ---- reconstructed planes out: a task = (channel, chroma row, 8 samples): consecutive
-    // threads write consecutive 64-byte pieces of a plane row --------------------------------
-    for (int task = tid; task < 2 * XC_BY * 8 * XC_BX; task += XC_NT) {
-        const int ch = task / (XC_BY * 8 * XC_BX);
-        const int rem = task % (XC_BY * 8 * XC_BX);
-        const int cr = rem / XC_BX, seg = rem % XC_BX;
-        const int bx = bx0 + seg, cy = by0 * 8 + cr;
-        if (bx >= g.nbx_c || cy >= g.hcp) continue;
-        const int blk = (cr >> 3) * XC_BX + seg, ry = cr & 7;
-        const double2* src = reinterpret_cast<const double2*>(&sm.plane[ch][blk][ry * 8]);
-        double2* dst = reinterpret_cast<double2*>(rec + (size_t)unit * rec_stride + g.plane_y +
-                                                  (size_t)ch * g.plane_c + (size_t)cy * g.wcp + bx * 8);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) dst[i] = src[i];
-    }
+    exact_chroma_tail<COEFFS>(g, sm.plane, sm.tb, bx0, by0, unit, rec, rec_stride, coeffs, coeff_stride, metrics);
 }
 
 cudaError_t exact_fused_configure_device() {
@@ -496,19 +653,36 @@ cudaError_t exact_fused_configure_device() {
     JDS_SET((k_exact_chroma<1, false>)); JDS_SET((k_exact_chroma<1, true>));
     JDS_SET((k_exact_chroma<2, false>)); JDS_SET((k_exact_chroma<2, true>));
 #undef JDS_SET
+#define JDS_SET(K, BYTES)                                                                       \
+    if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES))) != cudaSuccess) return e
+    JDS_SET((k_exact_chroma_pf<1, false>), sizeof(ExactChromaPfSmem<1>));
+    JDS_SET((k_exact_chroma_pf<1, true>), sizeof(ExactChromaPfSmem<1>));
+    JDS_SET((k_exact_chroma_pf<2, false>), sizeof(ExactChromaPfSmem<2>));
+    JDS_SET((k_exact_chroma_pf<2, true>), sizeof(ExactChromaPfSmem<2>));
+#undef JDS_SET
     return cudaSuccess;
 }
 
-// chroma of a subsampled, block-aligned frame WITHOUT prefilter in one kernel
+// chroma of a block-aligned frame in one kernel (4:4:4 has no decimation, hence no prefilter)
 bool exact_chroma_supported(const Geom& g, int prefilter) {
-    return g.sub == 0 || (!prefilter && !g.general);      // 4:4:4 has no decimation, hence no prefilter
+    (void)prefilter;
+    return g.sub == 0 || !g.general;
 }
 
-cudaError_t launch_exact_chroma(const Geom& g, const uint8_t* rgb, size_t rgb_stride, double* rec,
+cudaError_t launch_exact_chroma(const Geom& g, int prefilter, const uint8_t* rgb, size_t rgb_stride, double* rec,
                                 size_t rec_stride, const QTables* tables, int table_stride,
                                 int16_t* coeffs, size_t coeff_stride, DevMetrics* metrics, int units,
                                 cudaStream_t s) {
     dim3 grid((g.nbx_c + XC_BX - 1) / XC_BX, (g.nby_c + XC_BY - 1) / XC_BY, units);
+    if (prefilter && g.sub != 0) {
+#define JDS_LAUNCH_XP(SUBV, CO)                                                                 \
+    k_exact_chroma_pf<SUBV, CO><<<grid, XC_NT, sizeof(ExactChromaPfSmem<SUBV>), s>>>(            \
+        g, rgb, rgb_stride, rec, rec_stride, tables, table_stride, coeffs, coeff_stride, metrics)
+        if (g.sub == 1) { if (coeffs) JDS_LAUNCH_XP(1, true); else JDS_LAUNCH_XP(1, false); }
+        else { if (coeffs) JDS_LAUNCH_XP(2, true); else JDS_LAUNCH_XP(2, false); }
+#undef JDS_LAUNCH_XP
+        return cudaGetLastError();
+    }
     const size_t smem = sizeof(ExactChromaSmem);
 #define JDS_LAUNCH_XC(SUBV, CO)                                                                 \
     k_exact_chroma<SUBV, CO><<<grid, XC_NT, smem, s>>>(g, rgb, rgb_stride, rec, rec_stride, tables, \

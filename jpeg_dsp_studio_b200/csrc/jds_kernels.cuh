@@ -59,7 +59,7 @@ cudaError_t launch_exact_luma(const Geom& g, const uint8_t* rgb, size_t rgb_stri
                               int16_t* coeffs, size_t coeff_stride, uint8_t* recon,
                               size_t recon_stride, DevMetrics* metrics, int units, cudaStream_t s);
 bool exact_chroma_supported(const Geom& g, int prefilter);
-cudaError_t launch_exact_chroma(const Geom& g, const uint8_t* rgb, size_t rgb_stride, double* rec,
+cudaError_t launch_exact_chroma(const Geom& g, int prefilter, const uint8_t* rgb, size_t rgb_stride, double* rec,
                                 size_t rec_stride, const QTables* tables, int table_stride,
                                 int16_t* coeffs, size_t coeff_stride, DevMetrics* metrics, int units,
                                 cudaStream_t s);

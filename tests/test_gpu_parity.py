@@ -119,6 +119,32 @@ def test_exact_batch_matches_oracle(J, oracle):
         assert abs(o.scalars["ssim_rgb"] - ref["ssim_rgb"]) <= SSIM_TOL
 
 
+@pytest.mark.parametrize("shape,mode,pf", [((96, 128), "4:2:2", True), ((112, 272), "4:2:0", True),
+                                           ((72, 128), "4:4:4", True), ((16, 16), "4:2:0", True),
+                                           ((80, 528), "4:2:2", True), ((64, 64), "4:4:4", False)])
+def test_fused_exact_kernels_match_oracle(J, oracle, shape, mode, pf):
+    """block-aligned frames WITHOUT error maps run the fused exact kernels (k_exact_chroma[_pf] +
+    k_exact_luma): pixels, coefficients, histogram and bit count equal the oracle's - prefilter
+    row / column passes at tile seams and frame borders included (528 px = three chroma tiles wide,
+    112 rows = two tiles high)"""
+    frames = np.stack([CS.rand_rgb(7000 + 13 * k + shape[1], *shape) for k in range(3)] +
+                      [np.ascontiguousarray(CS.photo_tiled(*shape))])
+    eng = J.get_engine()
+    eng.stage_times(reset=True)
+    eng.set_stage_timing(True)
+    outs = eng.roundtrip_batch(frames, 65, mode, pf, precision="exact", want_coeffs=True, want_hist=True)
+    st = eng.stage_times(reset=True)
+    eng.set_stage_timing(False)
+    assert st["inverse_colour"]["launches"] == 0, st          # fused, not staged
+    for k, o in enumerate(outs):
+        ref = oracle.compress_reconstruct(frames[k], 65, mode, pf)
+        assert np.array_equal(o.coeffs, ref["all_quantized_coeffs"]), (k, mode, pf)
+        assert np.array_equal(o.recon, ref["reconstructed_image"]), (k, mode, pf)
+        assert np.array_equal(np.array(list(o.metrics.hist50)), ref["quantized_histogram"])
+        assert o.scalars["estimated_bits"] == ref["exact_bits"]
+        assert o.scalars["psnr_rgb"] == ref["psnr_rgb"]
+
+
 def test_batch_chunking_is_transparent(J, oracle, monkeypatch):
     """A batch larger than the scratch budget is processed in chunks with the same
     results (fresh engine with a tiny budget)."""
