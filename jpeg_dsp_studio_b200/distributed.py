@@ -88,12 +88,14 @@ def scalars_from_table(table: np.ndarray, height: int, width: int) -> List[dict]
     bits = np.where(none, exact, est32.astype(np.int64))
     bpp = np.where(none, exact / n_px, bpp32.astype(np.float64))
     ratio = np.where(none, (n_px * 24) / np.maximum(exact, 1), ratio32.astype(np.float64))
-    return [{"quality": int(f["quality"][i]), "psnr_rgb": float(psnr_rgb[i]), "psnr_y": float(psnr_y[i]),
-             "ssim_rgb": float(ssim_rgb[i]), "ssim_y": float(ssim_y[i]), "estimated_bits": int(bits[i]),
-             "exact_bits": int(exact[i]),
-             "bpp": float(bpp[i]), "compression_ratio": float(ratio[i]),
-             "nonzero_count": int(f["nnz"][i]), "total_coeffs": int(f["total_coeffs"][i])}
-            for i in range(len(t))]
+    # ndarray.tolist() yields Python ints / floats in C; one dict(zip()) per row (a 100-point table:
+    # 0.16 ms with per-element float() / int() calls, 0.05 ms this way - it sits on a sweep's latency)
+    cols = (f["quality"].astype(np.int64).tolist(), psnr_rgb.tolist(), psnr_y.tolist(), ssim_rgb.tolist(),
+            ssim_y.tolist(), bits.astype(np.int64).tolist(), exact.tolist(), bpp.astype(np.float64).tolist(),
+            ratio.astype(np.float64).tolist(), nnz.tolist(), f["total_coeffs"].astype(np.int64).tolist())
+    keys = ("quality", "psnr_rgb", "psnr_y", "ssim_rgb", "ssim_y", "estimated_bits", "exact_bits", "bpp",
+            "compression_ratio", "nonzero_count", "total_coeffs")
+    return [dict(zip(keys, row)) for row in zip(*cols)]
 
 
 def scalars_from_record(rec: np.ndarray, height: int, width: int) -> dict:
