@@ -898,7 +898,10 @@ struct F444Smem {
 };
 
 template <bool COEFFS>
-__global__ void __launch_bounds__(F4_NT)
+#ifndef JDS_F4_MIN_CTAS
+#define JDS_F4_MIN_CTAS 3      // 65 KB of shared memory, 100 registers: three CTAs fit an SM once the carve-out is maximal
+#endif
+__global__ void __launch_bounds__(F4_NT, JDS_F4_MIN_CTAS)
 k_fast_444(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
            const QTables* __restrict__ tables, int table_stride,
            int16_t* __restrict__ coeffs, size_t coeff_stride,
@@ -1076,6 +1079,11 @@ cudaError_t fused_configure_device() {
     JDS_SET((k_fast_luma<2, true, STAGE_FULL>), sizeof(LumaSmem<2>));
     JDS_SET((k_fast_444<false>), sizeof(F444Smem));
     JDS_SET((k_fast_444<true>), sizeof(F444Smem));
+    // the driver's default carve-out left room for two CTAs of this kernel only
+    if ((e = cudaFuncSetAttribute(k_fast_444<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_fast_444<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
 #undef JDS_SET
     return cudaSuccess;
 }
