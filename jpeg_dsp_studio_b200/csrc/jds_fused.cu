@@ -75,6 +75,9 @@ constexpr int BLK_STRIDE = 68;                    // floats per 8x8 block slot i
 // (the eight lanes of a quarter-warp that walks eight blocks of one row) XOR one bit of the row
 // (SHIFT = 1 for 4:2:0, 0 for 4:2:2: a quarter-warp of the compose phase walks four blocks of two
 // tasks whose rows differ in exactly that bit)
+#ifndef JDS_LU_NEXT_PREFETCH
+#define JDS_LU_NEXT_PREFETCH 592     // luma kernel: L2 prefetch distance in CTAs (0 = off); 592 = 4 CTAs x 148 SMs
+#endif
 #ifndef JDS_CA_PREFETCH
 #define JDS_CA_PREFETCH 1
 #endif
@@ -724,6 +727,28 @@ k_fast_luma(Geom g, const uint8_t* __restrict__ rgb, size_t rgb_stride,
                 ld[k][2] = __ldg(q + 2);
             }
         }
+#if JDS_LU_NEXT_PREFETCH > 0
+        {
+            // Every CTA starts with DRAM-latency loads of its own tile (20 % of this kernel's stall
+            // samples, directly and at the barrier behind them).  CTAs start in linear block order,
+            // so this CTA asks L2 for the tile of the CTA that starts about one wave of resident
+            // CTAs later - that CTA's first loads then hit L2.
+            const int lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z) + JDS_LU_NEXT_PREFETCH;
+            const int tx = lin % gridDim.x, ty = (lin / gridDim.x) % gridDim.y, tz = lin / (gridDim.x * gridDim.y);
+            if (tz < (int)gridDim.z) {
+                const uint8_t* nin = rgb + (size_t)tz * rgb_stride;
+                const int nx0 = tx * LU_TW, ny0 = ty * LU_TH;
+                const size_t row_end = (size_t)g.W * 3;
+                constexpr int LINES = LU_TW * 3 / 128;                 // 6 lines of 128 B per row
+                for (int i = tid; i < LU_TH * LINES; i += LU_NT) {
+                    const int r = i / LINES, l = i % LINES;
+                    const size_t off = (size_t)nx0 * 3 + 128 * (size_t)l;
+                    if (ny0 + r < g.H && off < row_end)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(nin + (size_t)(ny0 + r) * row_end + off));
+                }
+            }
+        }
+#endif
 #pragma unroll
         for (int k = 0; k < NTASK; ++k) {
             const int r = rbase + 8 * k;
