@@ -59,6 +59,9 @@
 #ifndef JDS_SSIM_PREP_BY1
 #define JDS_SSIM_PREP_BY1 160        // with PAIRBAR: prep tasks [0, n) go to the (B,Y) threads, the rest to (R,G)
 #endif
+#ifndef JDS_SSIM_PREP_HOIST
+#define JDS_SSIM_PREP_HOIST 1        // prep's per-task index arithmetic once per CTA instead of once per chunk
+#endif
 #ifndef JDS_SSIM_PREP_RG
 #define JDS_SSIM_PREP_RG 0           // > 0: the (R,G) warps take only the first n of the 252 prep tasks, the (B,Y) warps the rest
 #endif
@@ -361,6 +364,43 @@ k_ssim_strip(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
 
     // prep: (B, Y) of both images, bytes -> centred fp32; task = 4 pixels of one (image, row).
     // Tasks tl, tl + ts, ... below t1.
+#if JDS_SSIM_PREP_HOIST
+    // the default split gives thread t the tasks t and t + 128 of every chunk: their source and
+    // destination offsets never change, so the index arithmetic (two divisions by constants per
+    // task) is done once here instead of in every chunk
+    uint32_t prep_pk[2];                 // source byte offset | destination byte offset << 16
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int task = min(tid + k * S_NT, 2 * S_R * S_PG - 1);
+        const int img = task / (S_R * S_PG);
+        const int rem = task - img * (S_R * S_PG);
+        const int r = rem / S_PG, g4 = rem - r * S_PG;
+        const uint32_t dst = (uint32_t)(((img * S_R + r) * S_BPITCH + g4) * sizeof(float4));
+        prep_pk[k] = (uint32_t)(img * S_TILEB + r * S_ROWB + 12 * g4) | (dst << 16);
+    }
+    const int prep_n = (tid + S_NT < 2 * S_R * S_PG) ? 2 : 1;
+    auto prep_own = [&](int chunk) {
+        const uint8_t* base = &sm.raw[chunk & 1][0][0];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (k < prep_n) {
+                const uint32_t* w = reinterpret_cast<const uint32_t*>(base + (prep_pk[k] & 0xffffu));
+                float4* dst = reinterpret_cast<float4*>(reinterpret_cast<char*>(&sm.by[0][0][0][0]) + (prep_pk[k] >> 16));
+                const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+                const float R0 = byte_centered<0>(w0), G0 = byte_centered<1>(w0), B0 = byte_centered<2>(w0);
+                const float R1 = byte_centered<3>(w0), G1 = byte_centered<0>(w1), B1 = byte_centered<1>(w1);
+                const float R2 = byte_centered<2>(w1), G2 = byte_centered<3>(w1), B2 = byte_centered<0>(w2);
+                const float R3 = byte_centered<1>(w2), G3 = byte_centered<2>(w2), B3 = byte_centered<3>(w2);
+                const float Y0 = fmaf(0.299f, R0, fmaf(0.587f, G0, 0.114f * B0));
+                const float Y1 = fmaf(0.299f, R1, fmaf(0.587f, G1, 0.114f * B1));
+                const float Y2 = fmaf(0.299f, R2, fmaf(0.587f, G2, 0.114f * B2));
+                const float Y3 = fmaf(0.299f, R3, fmaf(0.587f, G3, 0.114f * B3));
+                dst[0] = make_float4(B0, Y0, B1, Y1);
+                dst[S_BHALF] = make_float4(B2, Y2, B3, Y3);
+            }
+        }
+    };
+#endif
     auto prep_tasks = [&](int chunk, int tl, int t1, int ts) {
         const int buf = chunk & 1;
         for (int task = tl; task < t1; task += ts) {
@@ -392,7 +432,11 @@ k_ssim_strip(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
 
     // chunk 0: everyone waits for the first tiles and prepares (B,Y)
     mbar_wait(&sm.bar[0], 0u);
+#if JDS_SSIM_PREP_HOIST
+    prep_own(0);
+#else
     prep_tasks(0, tid, N_PREP, S_NT);
+#endif
     __syncthreads();
 
     // one vertical step of pass 2: take row r's horizontal sums, emit (optionally), drop the
@@ -515,6 +559,8 @@ k_ssim_strip(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
             // the (R,G) warps converted bytes inside pass 1: the (B,Y) warps take more of the prep
             if (pair == 0) prep_tasks(c + 1, tid & (S_OW - 1), JDS_SSIM_PREP_RG, S_OW);
             else prep_tasks(c + 1, JDS_SSIM_PREP_RG + (tid & (S_OW - 1)), N_PREP, S_OW);
+#elif JDS_SSIM_PREP_HOIST
+            prep_own(c + 1);
 #else
             prep_tasks(c + 1, tid, N_PREP, S_NT);
 #endif
