@@ -226,19 +226,29 @@ def compress_stream(batches, params: CompressionParams, *, precision: str = "fas
         return results
 
     prev = None
-    for k, frames in enumerate(batches):
-        if frames.ndim != 4:
-            raise ValueError(f"expected N x H x W x 3 frames, got shape {tuple(frames.shape)}")
-        _validate(frames[0], params)
-        t0 = time.perf_counter()
-        pending = engines[k & 1].roundtrip_batch_begin(
-            frames, params.quality, params.subsampling_mode, params.use_prefilter, precision=precision,
-            want_recon=keep_images, recon_out=None if recon_out is None else recon_out[k & 1])
+    try:
+        for k, frames in enumerate(batches):
+            if frames.ndim != 4:
+                raise ValueError(f"expected N x H x W x 3 frames, got shape {tuple(frames.shape)}")
+            _validate(frames[0], params)
+            t0 = time.perf_counter()
+            pending = engines[k & 1].roundtrip_batch_begin(
+                frames, params.quality, params.subsampling_mode, params.use_prefilter, precision=precision,
+                want_recon=keep_images, recon_out=None if recon_out is None else recon_out[k & 1])
+            done, prev = prev, (pending, frames, t0)
+            if done is not None:
+                yield finish(*done)
+        done, prev = prev, None
+        if done is not None:
+            yield finish(*done)
+    finally:
+        # the consumer stopped early or a batch was rejected: collect the batch still in flight so
+        # that its context accepts calls again
         if prev is not None:
-            yield finish(*prev)
-        prev = (pending, frames, t0)
-    if prev is not None:
-        yield finish(*prev)
+            try:
+                prev[0].result()
+            except Exception:
+                pass
 
 
 def plot_payload(image_rgb, params: CompressionParams, *, precision: str = "exact",

@@ -693,6 +693,13 @@ def test_compress_stream_overlapped_batches_equal_single_batches(J):
     for gb, wb in zip(got, want):
         assert [g.psnr_rgb for g in gb] == [w.psnr_rgb for w in wb]
         assert all(g.reconstructed_image is None for g in gb)
+    # a consumer that stops early leaves no batch pending behind
+    gen = J.compress_stream(iter(batches), p)
+    first = next(gen)
+    gen.close()
+    assert np.array_equal(first[0].reconstructed_image, J.compress_batch(batches[0], p)[0].reconstructed_image)
+    for e in stream_engines(None, 2):
+        e.roundtrip(batches[0][0], 40, "4:2:0", True, precision="fast")
     # one pending batch per context
     eng = stream_engines(None, 2)[1]
     pending = eng.roundtrip_batch_begin(batches[0], 40, "4:2:0", True)
