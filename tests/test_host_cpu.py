@@ -184,3 +184,43 @@ def test_histogram_from_value_counts_equals_numpy_histogram_of_the_coefficients(
     c, e = histogram_from_values(vh, 50)
     wc, we = np.histogram(np.zeros(4096, dtype=np.int16), bins=50)
     assert np.array_equal(c, wc) and np.array_equal(e, we)
+
+
+def test_sweep_quality_validation_keeps_the_reference_message():
+    """Engine.sweep / sweep_records validate every point without a dataclass per point, with the
+    reference's message (models/compression_params.py:16-17)."""
+    from jpeg_dsp_studio_b200.engine import _check_qualities
+    _check_qualities(list(range(1, 101)))
+    for bad in (0, 101, -5):
+        with pytest.raises(ValueError, match=f"Quality must be 1-100, got {bad}"):
+            _check_qualities([50, bad, 60])
+
+
+def test_table_finalisation_equals_per_record_formulas():
+    """distributed.scalars_from_table (vectorised, one dict per row) against the per-record
+    formulas of utils.metrics, incl. the float32 bit arithmetic and the all-zero-coefficient case;
+    band partial records add up field by field."""
+    from types import SimpleNamespace
+    from jpeg_dsp_studio_b200 import distributed as D
+    from jpeg_dsp_studio_b200.utils import metrics as M
+    rng = np.random.default_rng(5)
+    h, w = 2160, 3840
+    rows = []
+    for k in range(12):
+        nnz = 0 if k == 3 else int(rng.integers(1, 12_000_000))
+        m = SimpleNamespace(sse_rgb=int(rng.integers(0, 1 << 40)), sse_y=float(rng.random() * 1e9),
+                            ssim_sum=[float(rng.random() * 8e6) for _ in range(4)], ssim_count=(h - 6) * (w - 6),
+                            coeff_bits=6 * nnz + int(rng.integers(0, 5 * nnz + 1)), nnz=nnz,
+                            total_coeffs=12441600, luma_blocks=129600)
+        rows.append((m, D.record_from_metrics(k, k + 1, m)))
+    table = D.scalars_from_table(np.stack([r for _, r in rows]), h, w)
+    for (m, _), t in zip(rows, table):
+        a, b = M.metrics_from_partials(m, h, w), M.bitrate_from_partials(m, h, w)
+        assert t["psnr_rgb"] == a["psnr_rgb"] and t["psnr_y"] == a["psnr_y"]
+        assert t["ssim_rgb"] == pytest.approx(a["ssim_rgb"], rel=1e-15) and t["ssim_y"] == a["ssim_y"]
+        for key in ("estimated_bits", "exact_bits", "bpp", "compression_ratio", "nonzero_count", "total_coeffs"):
+            assert t[key] == b[key], key
+        assert all(type(v) in (int, float) for v in t.values())
+    merged = D.merge_band_records([r for _, r in rows[:5]])
+    assert merged[0] == rows[0][1][0] and merged[1] == rows[0][1][1]
+    assert np.array_equal(merged[2:], np.sum([r[2:] for _, r in rows[:5]], axis=0))
