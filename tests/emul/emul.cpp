@@ -206,3 +206,51 @@ extern "C" void emul_ssim_strip_formula(int n, const float* sx, const float* sy,
         out[i] = 2.0f * r.x;
     }
 }
+
+// ---------------------------------------------------------------------------------------
+// entropy coder: the per-block code of jds_entropy.cu (jds_entropy_block.cuh) run block after
+// block on the host - sizes by CountSink, bits by BitSink at the running bit position, the padding
+// 1-bits, big-endian bytes and the 0xFF stuffing - for one scan.  Returns 0, or -1 if a value has
+// no baseline code, or -2 if `cap` is too small.
+// ---------------------------------------------------------------------------------------
+#include "../../jpeg_dsp_studio_b200/csrc/jds_entropy_block.cuh"
+
+extern "C" int emul_entropy_scan(const int16_t* blocks, long long n_blocks, int table_id, uint8_t* out,
+                                 uint64_t cap, uint64_t* out_bytes, uint64_t* out_bits) {
+    static const uint8_t zz[64] = JDS_ZIGZAG_TABLE;
+    const HuffPacked hp = make_packed();
+    const uint32_t* dc = hp.dc[table_id ? 1 : 0];
+    const uint32_t* ac = hp.ac[table_id ? 1 : 0];
+    // pass 1: sizes (what k_entropy_block_bits + k_entropy_layout produce)
+    std::vector<uint64_t> start((size_t)n_blocks + 1, 0);
+    int pred = 0;
+    for (long long b = 0; b < n_blocks; ++b) {
+        CountSink cs;
+        if (!walk_block(blocks + 64 * b, pred, dc, ac, zz, cs)) return -1;
+        pred = blocks[64 * b];
+        start[(size_t)b + 1] = start[(size_t)b] + cs.bits;
+    }
+    const uint64_t bits = start[(size_t)n_blocks];
+    const int pad = (int)((8 - (bits & 7)) & 7);
+    std::vector<uint32_t> words((size_t)((bits + pad + 31) / 32) + 1, 0u);
+    // pass 2: every block at its own offset (k_entropy_pack), in REVERSE order to show that the
+    // result does not depend on the order in which blocks write
+    for (long long b = n_blocks - 1; b >= 0; --b) {
+        BitSink sink(words.data(), (unsigned int)start[(size_t)b]);
+        walk_block(blocks + 64 * b, b ? (int)blocks[64 * (b - 1)] : 0, dc, ac, zz, sink);
+        if (b == n_blocks - 1 && pad) sink.put((1u << pad) - 1u, pad);
+        sink.finish();
+    }
+    // bytes, first bit = MSB of byte 0, 0x00 after every 0xFF (k_stuff_*)
+    const uint64_t nbytes = (bits + pad) / 8;
+    uint64_t at = 0;
+    for (uint64_t i = 0; i < nbytes; ++i) {
+        const uint8_t v = (uint8_t)(words[(size_t)(i >> 2)] >> (24 - 8 * (i & 3)));
+        if (at + 2 > cap) return -2;
+        out[at++] = v;
+        if (v == 0xFF) out[at++] = 0;
+    }
+    *out_bytes = at;
+    *out_bits = bits;
+    return 0;
+}

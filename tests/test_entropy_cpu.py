@@ -102,3 +102,51 @@ def test_coder_round_trips_its_own_bitstream():
         back, used = E.decode_scan(data, 40, table_id)
         assert np.array_equal(back, blocks)
         assert used == nbits == E.component_scan_bits(blocks, table_id)
+
+
+# ---------------------------------------------------------------------------------------
+# the product's per-block coder (csrc/jds_entropy_block.cuh: code tables, zig-zag walk, bit sink)
+# compiled for the host (tests/emul) against the oracle coder above - the CUDA kernels run the
+# same source per thread (tests/test_entropy_gpu.py checks them on the device)
+# ---------------------------------------------------------------------------------------
+def _emul_scan(lib, blocks, table_id):
+    import ctypes as C
+    blocks = np.ascontiguousarray(blocks, dtype=np.int16)
+    cap = 4 * blocks.size + 64
+    out = np.zeros(cap, dtype=np.uint8)
+    nbytes, nbits = C.c_uint64(), C.c_uint64()
+    rc = lib.emul_entropy_scan(blocks.ctypes.data_as(C.c_void_p), C.c_longlong(blocks.shape[0]), table_id,
+                               out.ctypes.data_as(C.c_void_p), C.c_uint64(cap), C.byref(nbytes), C.byref(nbits))
+    return rc, bytes(out[:nbytes.value]), int(nbits.value)
+
+
+def test_device_block_coder_on_cpu_matches_oracle():
+    import ctypes as C
+    from tests.emul import build as EB
+    lib = C.CDLL(EB.build())
+    lib.emul_entropy_scan.restype = C.c_int
+    rng = np.random.default_rng(17)
+    cases = []
+    for n, spread, keep in ((1, 30, 64), (7, 300, 20), (64, 40, 10), (65, 1023, 64), (200, 8, 3), (33, 0, 0)):
+        b = rng.integers(-spread, spread + 1, (n, 64)).astype(np.int16)
+        b[:, keep:] = 0
+        cases.append(b)
+    ext = np.zeros((12, 64), dtype=np.int16)
+    ext[:, 0] = [-1024, 1016, 0, 5, -1024, 1016, 1016, -1024, 0, 0, 7, 7]
+    ext[1, 63] = -1                                   # three ZRL then one coefficient
+    ext[2, 1] = 1023
+    ext[5] = 1023                                     # all-ones amplitudes: 0xFF bytes to stuff
+    ext[6] = -1023
+    ext[9, 62] = 77
+    cases.append(ext)
+    for blocks in cases:
+        for tid in (0, 1):
+            want, want_bits = E._encode_scan(blocks.astype(np.int64), tid)
+            rc, got, bits = _emul_scan(lib, blocks, tid)
+            assert rc == 0 and bits == want_bits and got == want, (blocks.shape, tid)
+    bad = ext.copy()
+    bad[3, 5] = 1024                                  # no baseline code: refused
+    assert _emul_scan(lib, bad, 0)[0] == -1
+    bad = ext.copy()
+    bad[3, 0], bad[4, 0] = 2047, -2047                # DC difference of 12 bits
+    assert _emul_scan(lib, bad, 1)[0] == -1
