@@ -17,7 +17,8 @@ def _load(name):
         return json.load(f)
 
 
-@pytest.mark.parametrize("name,n", [("r1_bench_n1.json", 1), ("r1_bench_n2.json", 2), ("r1_bench_n8.json", 8)])
+@pytest.mark.parametrize("name,n", [("r1_bench_n1.json", 1), ("r1_bench_n2.json", 2), ("r1_bench_n8.json", 8),
+                                    ("r2_bench_n1.json", 1), ("r2_bench_n8.json", 8)])
 def test_bench_line_has_the_contract_keys(name, n):
     d = _load(name)
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
@@ -43,6 +44,30 @@ def test_bench_line_has_the_contract_keys(name, n):
         for k in ("value", "unit", "cores", "kind", "sample"):
             assert k in c, k
         assert c["kind"] in ("port", "reference") and c["cores"] >= 1
+
+
+@pytest.mark.parametrize("name,n", [("r2_bench_n1.json", 1), ("r2_bench_n8.json", 8)])
+def test_round2_line_has_the_round2_records(name, n):
+    """what the round-1 verdict asked the line to carry: exact mode with its own e2e, the mismatch
+    rate of the fast mode on the workload, the sweep sub-record, whole-path traffic; plus the
+    pipelined and metrics-only e2e legs"""
+    d = _load(name)
+    x = d["exact_mode"]
+    assert x["dtype"] == "f64" and x["e2e"]["value"] > 0 and x["e2e"]["h2d_bytes_per_step"] > 0
+    assert 0 < x["value"] < d["value"] and x["sync_api"]["value"] <= x["value"] * 1.02
+    mm = d["fast_mode_mismatch"]
+    assert 0 <= mm["coeff"] < 1e-4 and 0 <= mm["pixel"] < 1e-3 and mm["d_psnr_y_db"] < 1e-3 and mm["d_ssim_y"] < 1e-5
+    sw = d["sweep"]
+    assert sw["scaling"] == "strong" and sw["points"] == 100 and sw["n_gpus"] == n
+    for leg in ("single_sweep", "single_device", "pipelined"):
+        assert sw[leg]["ms_per_sweep"] > 0
+    assert sw["single_device"]["ms_per_sweep"] <= sw["single_sweep"]["ms_per_sweep"]
+    wp = d["roofline"]["whole_path"]
+    assert wp["traffic"]["dram_bytes_per_pixel"] > wp["traffic"]["algorithmic_bytes_per_pixel"] == 6.0
+    e = d["e2e"]
+    assert e["pipelined"]["h2d_bytes_per_step"] == e["h2d_bytes_per_step"]
+    assert e["pipelined"]["d2h_bytes_per_step"] == e["d2h_bytes_per_step"]
+    assert e["metrics_only"]["d2h_bytes_per_step"] < 1e5 and e["metrics_only"]["value"] > e["value"]
 
 
 def test_bench_source_mentions_every_contract_key():
